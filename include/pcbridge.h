@@ -1,0 +1,126 @@
+/*
+ * pcbridge.h -- C ABI of libpcbridge.so: sm_100a CUDA kernels for the sampling-and-grouping
+ * hot path of the bridge point-cloud segmentation networks.
+ *
+ * The reference (UT-Team-Chun/Pointcloud-bridge) has no FFI layer: the hot path is a set of
+ * module-level Python functions executed by ATen.  Each entry point below replaces one of
+ * those functions (cited as reference file:line, relative to the reference root) and is what
+ * a binding of that function would call.  INTEGRATION.md shows the ctypes stub.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name says host; buffers are dense,
+ *     row-major, in the layout written next to the argument;
+ *   - coordinates/features are fp32, indices are int64 (the reference returns LongTensors);
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it and the call
+ *     returns without synchronising; the library keeps no state between calls;
+ *   - return value: 0 on success, a positive cudaError_t if the launch failed, or a
+ *     negative PCB_E* code for arguments outside the supported envelope.  No CPU fallback
+ *     exists: without a CUDA device every call fails.
+ *   - callable from any host thread.
+ */
+#ifndef PCBRIDGE_H_
+#define PCBRIDGE_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PCB_VERSION 100
+
+#define PCB_EINVAL (-1)      /* null pointer / non-positive size */
+#define PCB_ERANGE (-2)      /* size outside the supported envelope (see each function) */
+#define PCB_EALIGN (-3)      /* pointer not aligned as required */
+
+typedef void *pcb_stream_t;
+
+int pcb_version(void);
+/* static string for a return code of any function below */
+const char *pcb_error_string(int code);
+
+/* ---- a1  farthest_point_sample            Partsize-identical/models/pointnet_util.py:66-88
+ *                                           Highway_bridge/models/pointnet2_utils.py:63-80
+ * xyz [B,N,3]; start [B] = the torch.randint draw of pointnet_util.py:79 (made by the caller);
+ * out_idx [B,npoint].  One persistent CTA per cloud.  N <= 49152. */
+int pcb_fps_f32(const float *xyz, int B, int N, const int64_t *start, int npoint,
+                int64_t *out_idx, pcb_stream_t stream);
+
+/* ---- a2  square_distance                  pointnet_util.py:22-43; pointnet2_utils.py:7-14
+ * src [B,N,C], dst [B,M,C] -> out [B,N,M].  C <= 512. */
+int pcb_square_distance_f32(const float *src, const float *dst, int B, int N, int M, int C,
+                            float *out, pcb_stream_t stream);
+
+/* ---- a3  query_ball_point                 pointnet_util.py:91-112; pointnet2_utils.py:97-112
+ * xyz [B,N,3], new_xyz [B,S,3]; radius2 = (float)((double)radius * radius) as the Python
+ * comparison sees it; out_idx [B,S,nsample].  Row = first nsample in-ball indices in
+ * ascending order, padded with the first one; empty ball -> N. */
+int pcb_ball_query_f32(const float *xyz, const float *new_xyz, int B, int N, int S,
+                       float radius2, int nsample, int64_t *out_idx, pcb_stream_t stream);
+
+/* ---- a4  index_points                     pointnet_util.py:46-63 (errors on idx >= N)
+ *                                           pointnet2_utils.py:17-39 (clamps to [0,N-1])
+ * points [B,N,C], idx [B,M] -> out [B,M,C].  clamp != 0: Highway flavour.  clamp == 0:
+ * out-of-range entries (after Python negative-index wrap) write zeros and, when
+ * err_count != NULL, atomically increment *err_count (device int32) so the host side can
+ * raise IndexError as the reference does. */
+int pcb_gather_f32(const float *points, const int64_t *idx, int B, int N, int C, int64_t M,
+                   int clamp, float *out, int *err_count, pcb_stream_t stream);
+/* backward of pcb_gather_f32 w.r.t. points: grad_points [B,N,C] += scatter(grad_out [B,M,C]).
+ * grad_points must be zero-initialised (or hold a value to accumulate into). */
+int pcb_gather_bwd_f32(const float *grad_out, const int64_t *idx, int B, int N, int C, int64_t M,
+                       int clamp, float *grad_points, pcb_stream_t stream);
+
+/* ---- a5  grouping step of sample_and_group       pointnet_util.py:137-147, 260-267
+ *                                                  pointnet2_utils.py:50-58, 342-349
+ * xyz [B,N,3], points [B,N,D] or NULL (D = 0), new_xyz [B,S,3], idx [B,S,K]
+ * -> out [B,S,K,3+D] = cat(xyz[idx] - new_xyz, points[idx]) when xyz_first != 0
+ *                      cat(points[idx], xyz[idx] - new_xyz) otherwise (MSG order).
+ * points may be channels-first ([B,D,N]) when points_cf != 0, saving the caller a transpose. */
+int pcb_group_points_f32(const float *xyz, const float *points, const float *new_xyz,
+                         const int64_t *idx, int B, int N, int S, int K, int D, int xyz_first,
+                         int points_cf, int clamp, float *out, pcb_stream_t stream);
+/* backward w.r.t. points: grad_points ([B,N,D] or [B,D,N]) += scatter(grad_out[..., feature part]) */
+int pcb_group_points_bwd_f32(const float *grad_out, const int64_t *idx, int B, int N, int S, int K,
+                             int D, int xyz_first, int points_cf, int clamp, float *grad_points,
+                             pcb_stream_t stream);
+
+/* ---- a7  k nearest of xyz2 for each xyz1 point + inverse-distance weights
+ *          pointnet_util.py:325-332; pointnet2_utils.py:183-191 (k=3), 253-262 (k=4)
+ * xyz1 [B,N,3], xyz2 [B,S,3] -> out_dist [B,N,k] (squared, ascending, ties by index),
+ * out_idx [B,N,k], out_weight [B,N,k] (may be NULL).  1 <= k <= 8, k <= S. */
+int pcb_three_nn_f32(const float *xyz1, const float *xyz2, int B, int N, int S, int k,
+                     float *out_dist, int64_t *out_idx, float *out_weight, pcb_stream_t stream);
+/* ---- a7  interpolation     pointnet_util.py:333-334; pointnet2_utils.py:196, 264-268
+ * channels_first == 0: points2 [B,S,D] -> out [B,N,D];  != 0: points2 [B,D,S] -> out [B,D,N]. */
+int pcb_interpolate_f32(const float *points2, const int64_t *idx, const float *weight, int B, int N,
+                        int S, int D, int k, int channels_first, float *out, pcb_stream_t stream);
+int pcb_interpolate_bwd_f32(const float *grad_out, const int64_t *idx, const float *weight, int B,
+                            int N, int S, int D, int k, int channels_first, float *grad_points2,
+                            pcb_stream_t stream);
+
+/* ---- a8  DGCNN.knn                        Highway_bridge/models/DGCNN.py:49-70
+ * x [B,D,N] (channels_first != 0, as DGCNN passes it) or [B,N,D]; out_idx [B,N,k] ordered by
+ * (pairwise distance, index), self included; out_dist [B,N,k] may be NULL.  1 <= k <= 64,
+ * k <= N, D <= 512. */
+int pcb_knn_f32(const float *x, int B, int N, int D, int k, int channels_first, int64_t *out_idx,
+                float *out_dist, pcb_stream_t stream);
+
+/* ---- a10 cdist + topk(largest=False)      Highway_bridge/models/attention_modules.py:584-586,
+ *                                           736-738
+ * xyz [B,N,3]; out_idx [B,N,k]; out_dist [B,N,k] = Euclidean (sqrt'd) distances, may be NULL. */
+int pcb_knn_cdist_f32(const float *xyz, int B, int N, int k, int64_t *out_idx, float *out_dist,
+                      pcb_stream_t stream);
+
+/* ---- a9  DGCNN.get_graph_feature          Highway_bridge/models/DGCNN.py:72-109
+ * x [B,D,N], idx [B,N,k] -> out [B,2D,N,k] = cat(x[idx] - x, x) on the channel axis. */
+int pcb_graph_feature_f32(const float *x, const int64_t *idx, int B, int D, int N, int k,
+                          float *out, pcb_stream_t stream);
+/* backward w.r.t. x: grad_x [B,D,N] (zero-initialised by the caller) */
+int pcb_graph_feature_bwd_f32(const float *grad_out, const int64_t *idx, int B, int D, int N, int k,
+                              float *grad_x, pcb_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PCBRIDGE_H_ */

@@ -1,0 +1,472 @@
+// Gather-type kernels (HBM-bound):
+//   pcb_gather_f32 / _bwd          index_points          pointnet_util.py:46-63; pointnet2_utils.py:17-39
+//   pcb_group_points_f32 / _bwd    grouping + concat     pointnet_util.py:137-147, 260-267;
+//                                                        pointnet2_utils.py:50-58, 342-349
+//   pcb_graph_feature_f32 / _bwd   get_graph_feature     Highway_bridge/models/DGCNN.py:72-109
+//   pcb_interpolate_f32 / _bwd     inverse-distance interpolation   pointnet_util.py:333-334
+//   pcb_square_distance_f32        square_distance       pointnet_util.py:22-43
+// The output (the big operand) is written once with streaming stores, fully coalesced, with
+// 128-bit accesses wherever the row length allows; the gathered source stays L1/L2 resident.
+#include "pcb_common.cuh"
+
+namespace pcb {
+
+constexpr int kThreads = 256;
+
+__device__ __forceinline__ bool resolve_index(long long &i, int N, int clamp)
+{
+    if (clamp) {
+        i = i < 0 ? 0 : (i > N - 1 ? N - 1 : i);
+        return true;
+    }
+    if (i < 0) i += N;                                  // Python negative indexing
+    return i >= 0 && i < N;
+}
+
+// ------------------------------------------------------------------------------------------
+// index_points.  VEC = 4: C % 4 == 0 and 16-byte aligned rows; VEC = 1: anything.
+// One thread per VEC consecutive output floats -> coalesced stores.
+// ------------------------------------------------------------------------------------------
+template <int VEC>
+__global__ void __launch_bounds__(kThreads)
+gather_kernel(const float *__restrict__ points, const int64_t *__restrict__ idx, int N, int C,
+              int64_t M, int64_t total, int clamp, float *__restrict__ out, int *__restrict__ err)
+{
+    const int CV = C / VEC;
+    for (int64_t t = (int64_t)blockIdx.x * kThreads + threadIdx.x; t < total; t += (int64_t)gridDim.x * kThreads) {
+        const int64_t rowg = t / CV;                   // b * M + m
+        const int c = (int)(t - rowg * CV) * VEC;
+        const int64_t b = rowg / M;
+        long long i = idx[rowg];
+        const bool ok = resolve_index(i, N, clamp);
+        if (VEC == 4) {
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ok) v = __ldg(reinterpret_cast<const float4 *>(points + ((size_t)b * N + i) * C + c));
+            st_stream_f4(reinterpret_cast<float4 *>(out + (size_t)rowg * C + c), v);
+        } else {
+            float v = ok ? __ldg(points + ((size_t)b * N + i) * C + c) : 0.f;
+            st_stream_f1(out + (size_t)rowg * C + c, v);
+        }
+        if (!ok && err && c == 0) atomicAdd(err, 1);
+    }
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(kThreads)
+gather_bwd_kernel(const float *__restrict__ gout, const int64_t *__restrict__ idx, int N, int C,
+                  int64_t M, int64_t total, int clamp, float *__restrict__ gpoints)
+{
+    const int CV = C / VEC;
+    for (int64_t t = (int64_t)blockIdx.x * kThreads + threadIdx.x; t < total; t += (int64_t)gridDim.x * kThreads) {
+        const int64_t rowg = t / CV;
+        const int c = (int)(t - rowg * CV) * VEC;
+        const int64_t b = rowg / M;
+        long long i = idx[rowg];
+        if (!resolve_index(i, N, clamp)) continue;
+        float *dst = gpoints + ((size_t)b * N + i) * C + c;
+        if (VEC == 4) {
+            float4 g = ld_stream_f4(reinterpret_cast<const float4 *>(gout + (size_t)rowg * C + c));
+            atomicAdd(reinterpret_cast<float4 *>(dst), g);
+        } else {
+            atomicAdd(dst, __ldg(gout + (size_t)rowg * C + c));
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// grouping + concat.  out[b,s,k,:] = cat(xyz[idx]-new_xyz, points[idx]) (or the MSG order).
+// One thread per output float; threads of a row share the index (broadcast load).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+group_points_kernel(const float *__restrict__ xyz, const float *__restrict__ points,
+                    const float *__restrict__ new_xyz, const int64_t *__restrict__ idx, int N, int S, int K,
+                    int D, int xyz_first, int points_cf, int clamp, int64_t total, float *__restrict__ out)
+{
+    const int C = 3 + D;
+    for (int64_t t = (int64_t)blockIdx.x * kThreads + threadIdx.x; t < total; t += (int64_t)gridDim.x * kThreads) {
+        const int64_t rowg = t / C;                    // (b*S + s)*K + k
+        const int c = (int)(t - rowg * C);
+        const int64_t bs = rowg / K;                   // b*S + s
+        const int64_t b = bs / S;
+        long long i = idx[rowg];
+        const bool ok = resolve_index(i, N, clamp);
+        const int cx = xyz_first ? c : c - D;          // coordinate channel if in [0,3)
+        float v = 0.f;
+        if (ok) {
+            if (cx >= 0 && cx < 3) {
+                v = __fsub_rn(__ldg(xyz + ((size_t)b * N + i) * 3 + cx), __ldg(new_xyz + (size_t)bs * 3 + cx));
+            } else {
+                const int cf = xyz_first ? c - 3 : c;
+                v = points_cf ? __ldg(points + ((size_t)b * D + cf) * N + i)
+                              : __ldg(points + ((size_t)b * N + i) * D + cf);
+            }
+        }
+        st_stream_f1(out + t, v);
+    }
+}
+
+__global__ void __launch_bounds__(kThreads)
+group_points_bwd_kernel(const float *__restrict__ gout, const int64_t *__restrict__ idx, int N, int S, int K,
+                        int D, int xyz_first, int points_cf, int clamp, int64_t total,
+                        float *__restrict__ gpoints)
+{
+    const int C = 3 + D;
+    // one thread per (row, feature channel)
+    for (int64_t t = (int64_t)blockIdx.x * kThreads + threadIdx.x; t < total; t += (int64_t)gridDim.x * kThreads) {
+        const int64_t rowg = t / D;
+        const int cf = (int)(t - rowg * D);
+        const int64_t b = rowg / ((int64_t)S * K);
+        long long i = idx[rowg];
+        if (!resolve_index(i, N, clamp)) continue;
+        const float g = __ldg(gout + (size_t)rowg * C + (xyz_first ? 3 + cf : cf));
+        float *dst = points_cf ? gpoints + ((size_t)b * D + cf) * N + i : gpoints + ((size_t)b * N + i) * D + cf;
+        atomicAdd(dst, g);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// get_graph_feature.  x [B,D,N], idx [B,N,k] -> out [B,2D,N,k].
+// A thread owns one (n, j) edge and walks CPT channels: the index is read once per CPT
+// channels, stores are coalesced along (n, j), gathers hit one 4*N-byte row per channel.
+// ------------------------------------------------------------------------------------------
+constexpr int kGfCPT = 8;
+
+__global__ void __launch_bounds__(kThreads)
+graph_feature_kernel(const float *__restrict__ x, const int64_t *__restrict__ idx, int D, int N, int k,
+                     float *__restrict__ out)
+{
+    const int b = blockIdx.z;
+    const int c0 = blockIdx.y * kGfCPT;
+    const int64_t NK = (int64_t)N * k;
+    const int64_t e = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (e >= NK) return;
+    const int n = (int)(e / k);
+    long long nb = idx[(size_t)b * NK + e];
+    nb = nb < 0 ? 0 : (nb > N - 1 ? N - 1 : nb);
+#pragma unroll
+    for (int cc = 0; cc < kGfCPT; ++cc) {
+        const int c = c0 + cc;
+        if (c < D) {
+            const float *row = x + ((size_t)b * D + c) * N;
+            const float ctr = __ldg(row + n);
+            const float nbr = __ldg(row + nb);
+            st_stream_f1(out + ((size_t)b * 2 * D + c) * NK + e, __fsub_rn(nbr, ctr));
+            st_stream_f1(out + ((size_t)b * 2 * D + D + c) * NK + e, ctr);
+        }
+    }
+}
+
+// grad_x[b,c,n] += sum_j g2[b,c,n,j] - sum_j g1[b,c,n,j];  grad_x[b,c,idx[n,j]] += g1[b,c,n,j]
+__global__ void __launch_bounds__(kThreads)
+graph_feature_bwd_kernel(const float *__restrict__ gout, const int64_t *__restrict__ idx, int D, int N, int k,
+                         float *__restrict__ gx)
+{
+    const int b = blockIdx.z;
+    const int c0 = blockIdx.y * kGfCPT;
+    const int64_t NK = (int64_t)N * k;
+    const int64_t e = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (e >= NK) return;
+    const int n = (int)(e / k);
+    long long nb = idx[(size_t)b * NK + e];
+    nb = nb < 0 ? 0 : (nb > N - 1 ? N - 1 : nb);
+#pragma unroll
+    for (int cc = 0; cc < kGfCPT; ++cc) {
+        const int c = c0 + cc;
+        if (c < D) {
+            const float g1 = __ldg(gout + ((size_t)b * 2 * D + c) * NK + e);
+            const float g2 = __ldg(gout + ((size_t)b * 2 * D + D + c) * NK + e);
+            float *row = gx + ((size_t)b * D + c) * N;
+            atomicAdd(row + nb, g1);
+            atomicAdd(row + n, g2 - g1);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// interpolation: out[b,n,:] = sum_j w[b,n,j] * points2[b, idx[b,n,j], :]   (products rounded,
+// summed in j order -- pointnet_util.py:334)
+// ------------------------------------------------------------------------------------------
+template <int VEC>
+__global__ void __launch_bounds__(kThreads)
+interp_rows_kernel(const float *__restrict__ p2, const int64_t *__restrict__ idx, const float *__restrict__ w,
+                   int N, int S, int D, int k, int64_t total, float *__restrict__ out)
+{
+    const int DV = D / VEC;
+    for (int64_t t = (int64_t)blockIdx.x * kThreads + threadIdx.x; t < total; t += (int64_t)gridDim.x * kThreads) {
+        const int64_t rowg = t / DV;                   // b*N + n
+        const int c = (int)(t - rowg * DV) * VEC;
+        const int64_t b = rowg / N;
+        float acc[VEC];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
+        for (int j = 0; j < k; ++j) {
+            long long i = idx[rowg * k + j];
+            i = i < 0 ? 0 : (i > S - 1 ? S - 1 : i);
+            const float wj = __ldg(w + rowg * k + j);
+            const float *src = p2 + ((size_t)b * S + i) * D + c;
+            if (VEC == 4) {
+                float4 f = __ldg(reinterpret_cast<const float4 *>(src));
+                float pr[4] = {__fmul_rn(f.x, wj), __fmul_rn(f.y, wj), __fmul_rn(f.z, wj), __fmul_rn(f.w, wj)};
+#pragma unroll
+                for (int v = 0; v < 4; ++v) acc[v] = j == 0 ? pr[v] : __fadd_rn(acc[v], pr[v]);
+            } else {
+                float pr = __fmul_rn(__ldg(src), wj);
+                acc[0] = j == 0 ? pr : __fadd_rn(acc[0], pr);
+            }
+        }
+        if (VEC == 4)
+            st_stream_f4(reinterpret_cast<float4 *>(out + (size_t)rowg * D + c),
+                         make_float4(acc[0], acc[1], acc[2], acc[3]));
+        else
+            st_stream_f1(out + (size_t)rowg * D + c, acc[0]);
+    }
+}
+
+// channels-first: p2 [B,D,S] -> out [B,D,N]; a thread owns one n and walks CPT channels
+constexpr int kIpCPT = 8;
+constexpr int kIpMaxK = 8;
+
+__global__ void __launch_bounds__(kThreads)
+interp_cf_kernel(const float *__restrict__ p2, const int64_t *__restrict__ idx, const float *__restrict__ w,
+                 int N, int S, int D, int k, float *__restrict__ out)
+{
+    const int b = blockIdx.z;
+    const int c0 = blockIdx.y * kIpCPT;
+    const int n = blockIdx.x * kThreads + threadIdx.x;
+    if (n >= N) return;
+    int id[kIpMaxK];
+    float wt[kIpMaxK];
+#pragma unroll
+    for (int j = 0; j < kIpMaxK; ++j) {
+        if (j < k) {
+            long long i = idx[((size_t)b * N + n) * k + j];
+            id[j] = (int)(i < 0 ? 0 : (i > S - 1 ? S - 1 : i));
+            wt[j] = __ldg(w + ((size_t)b * N + n) * k + j);
+        }
+    }
+#pragma unroll
+    for (int cc = 0; cc < kIpCPT; ++cc) {
+        const int c = c0 + cc;
+        if (c < D) {
+            const float *row = p2 + ((size_t)b * D + c) * S;
+            float acc = 0.f;
+#pragma unroll
+            for (int j = 0; j < kIpMaxK; ++j) {
+                if (j < k) {
+                    float pr = __fmul_rn(__ldg(row + id[j]), wt[j]);
+                    acc = j == 0 ? pr : __fadd_rn(acc, pr);
+                }
+            }
+            st_stream_f1(out + ((size_t)b * D + c) * N + n, acc);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kThreads)
+interp_bwd_kernel(const float *__restrict__ gout, const int64_t *__restrict__ idx, const float *__restrict__ w,
+                  int N, int S, int D, int k, int cf, int64_t total, float *__restrict__ gp2)
+{
+    // one thread per (b, n, c) in the layout of gout (coalesced read), k atomics each
+    for (int64_t t = (int64_t)blockIdx.x * kThreads + threadIdx.x; t < total; t += (int64_t)gridDim.x * kThreads) {
+        int64_t b, n;
+        int c;
+        if (cf) {                                       // gout [B,D,N]
+            n = t % N;
+            int64_t bc = t / N;
+            c = (int)(bc % D);
+            b = bc / D;
+        } else {                                        // gout [B,N,D]
+            c = (int)(t % D);
+            int64_t bn = t / D;
+            n = bn % N;
+            b = bn / N;
+        }
+        const float g = __ldg(gout + t);
+        for (int j = 0; j < k; ++j) {
+            long long i = idx[((size_t)b * N + n) * k + j];
+            i = i < 0 ? 0 : (i > S - 1 ? S - 1 : i);
+            const float wj = __ldg(w + ((size_t)b * N + n) * k + j);
+            float *dst = cf ? gp2 + ((size_t)b * D + c) * S + i : gp2 + ((size_t)b * S + i) * D + c;
+            atomicAdd(dst, g * wj);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// square_distance (materialising; kept for API completeness -- the product path never needs it)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+row_sumsq_kernel(const float *__restrict__ x, int64_t rows, int C, int64_t row_stride, int elem_stride,
+                 int64_t rows_per_batch, int64_t batch_stride, float *__restrict__ out)
+{
+    int64_t r = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (r >= rows) return;
+    int64_t b = r / rows_per_batch, i = r - b * rows_per_batch;
+    out[r] = row_sumsq_aten(x + b * batch_stride + i * row_stride, C, elem_stride);
+}
+
+__global__ void __launch_bounds__(kThreads)
+square_distance_kernel(const float *__restrict__ src, const float *__restrict__ dst, int N, int M, int C,
+                       float *__restrict__ out)
+{
+    extern __shared__ float s_src[];                   // one src row + its norm
+    const int b = blockIdx.y, n = blockIdx.x;
+    const float *s = src + ((size_t)b * N + n) * C;
+    for (int c = threadIdx.x; c < C; c += kThreads) s_src[c] = __ldg(s + c);
+    __syncthreads();
+    if (threadIdx.x == 0) s_src[C] = row_sumsq_aten(s_src, C, 1);
+    __syncthreads();
+    const float sn = s_src[C];
+    for (int m = threadIdx.x; m < M; m += kThreads) {
+        const float *d = dst + ((size_t)b * M + m) * C;
+        float acc = 0.f;
+        for (int c = 0; c < C; ++c) acc = __fmaf_rn(s_src[c], __ldg(d + c), acc);
+        float dn = row_sumsq_aten(d, C, 1);
+        float t = __fmul_rn(-2.0f, acc);
+        t = __fadd_rn(t, sn);
+        out[((size_t)b * N + n) * M + m] = __fadd_rn(t, dn);
+    }
+}
+
+static inline unsigned grid_for(int64_t total)
+{
+    int64_t blocks = ceil_div(total, kThreads);
+    int64_t cap = (int64_t)PCB_NUM_SMS * 32;           // grid-stride beyond 32 CTAs per SM
+    return (unsigned)(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
+}
+
+static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+int row_sumsq_launch(const float *x, int64_t rows, int C, int64_t row_stride, int elem_stride,
+                     int64_t rows_per_batch, int64_t batch_stride, float *out, cudaStream_t st)
+{
+    row_sumsq_kernel<<<(unsigned)ceil_div(rows, kThreads), kThreads, 0, st>>>(x, rows, C, row_stride, elem_stride,
+                                                                            rows_per_batch, batch_stride, out);
+    PCB_RETURN_LAUNCH_STATUS();
+}
+
+}  // namespace pcb
+
+using namespace pcb;
+
+PCB_API int pcb_gather_f32(const float *points, const int64_t *idx, int B, int N, int C, int64_t M,
+                           int clamp, float *out, int *err_count, pcb_stream_t stream)
+{
+    PCB_REQUIRE(points && idx && out, PCB_EINVAL);
+    PCB_REQUIRE(B > 0 && N > 0 && C > 0 && M > 0, PCB_EINVAL);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (C % 4 == 0 && aligned16(points) && aligned16(out)) {
+        int64_t total = (int64_t)B * M * (C / 4);
+        gather_kernel<4><<<grid_for(total), kThreads, 0, st>>>(points, idx, N, C, M, total, clamp, out, err_count);
+    } else {
+        int64_t total = (int64_t)B * M * C;
+        gather_kernel<1><<<grid_for(total), kThreads, 0, st>>>(points, idx, N, C, M, total, clamp, out, err_count);
+    }
+    PCB_RETURN_LAUNCH_STATUS();
+}
+
+PCB_API int pcb_gather_bwd_f32(const float *grad_out, const int64_t *idx, int B, int N, int C, int64_t M,
+                               int clamp, float *grad_points, pcb_stream_t stream)
+{
+    PCB_REQUIRE(grad_out && idx && grad_points, PCB_EINVAL);
+    PCB_REQUIRE(B > 0 && N > 0 && C > 0 && M > 0, PCB_EINVAL);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (C % 4 == 0 && aligned16(grad_out) && aligned16(grad_points)) {
+        int64_t total = (int64_t)B * M * (C / 4);
+        gather_bwd_kernel<4><<<grid_for(total), kThreads, 0, st>>>(grad_out, idx, N, C, M, total, clamp, grad_points);
+    } else {
+        int64_t total = (int64_t)B * M * C;
+        gather_bwd_kernel<1><<<grid_for(total), kThreads, 0, st>>>(grad_out, idx, N, C, M, total, clamp, grad_points);
+    }
+    PCB_RETURN_LAUNCH_STATUS();
+}
+
+PCB_API int pcb_group_points_f32(const float *xyz, const float *points, const float *new_xyz,
+                                 const int64_t *idx, int B, int N, int S, int K, int D, int xyz_first,
+                                 int points_cf, int clamp, float *out, pcb_stream_t stream)
+{
+    PCB_REQUIRE(xyz && new_xyz && idx && out, PCB_EINVAL);
+    PCB_REQUIRE(B > 0 && N > 0 && S > 0 && K > 0 && D >= 0, PCB_EINVAL);
+    PCB_REQUIRE(points || D == 0, PCB_EINVAL);
+    int64_t total = (int64_t)B * S * K * (3 + D);
+    group_points_kernel<<<grid_for(total), kThreads, 0, (cudaStream_t)stream>>>(
+        xyz, points, new_xyz, idx, N, S, K, D, xyz_first, points_cf, clamp, total, out);
+    PCB_RETURN_LAUNCH_STATUS();
+}
+
+PCB_API int pcb_group_points_bwd_f32(const float *grad_out, const int64_t *idx, int B, int N, int S, int K,
+                                     int D, int xyz_first, int points_cf, int clamp, float *grad_points,
+                                     pcb_stream_t stream)
+{
+    PCB_REQUIRE(grad_out && idx && grad_points, PCB_EINVAL);
+    PCB_REQUIRE(B > 0 && N > 0 && S > 0 && K > 0 && D > 0, PCB_EINVAL);
+    int64_t total = (int64_t)B * S * K * D;
+    group_points_bwd_kernel<<<grid_for(total), kThreads, 0, (cudaStream_t)stream>>>(
+        grad_out, idx, N, S, K, D, xyz_first, points_cf, clamp, total, grad_points);
+    PCB_RETURN_LAUNCH_STATUS();
+}
+
+PCB_API int pcb_graph_feature_f32(const float *x, const int64_t *idx, int B, int D, int N, int k, float *out,
+                                  pcb_stream_t stream)
+{
+    PCB_REQUIRE(x && idx && out, PCB_EINVAL);
+    PCB_REQUIRE(B > 0 && D > 0 && N > 0 && k > 0, PCB_EINVAL);
+    PCB_REQUIRE(B <= 65535 && ceil_div(D, kGfCPT) <= 65535, PCB_ERANGE);
+    dim3 grid((unsigned)ceil_div((int64_t)N * k, kThreads), (unsigned)ceil_div(D, kGfCPT), (unsigned)B);
+    graph_feature_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(x, idx, D, N, k, out);
+    PCB_RETURN_LAUNCH_STATUS();
+}
+
+PCB_API int pcb_graph_feature_bwd_f32(const float *grad_out, const int64_t *idx, int B, int D, int N, int k,
+                                      float *grad_x, pcb_stream_t stream)
+{
+    PCB_REQUIRE(grad_out && idx && grad_x, PCB_EINVAL);
+    PCB_REQUIRE(B > 0 && D > 0 && N > 0 && k > 0, PCB_EINVAL);
+    PCB_REQUIRE(B <= 65535 && ceil_div(D, kGfCPT) <= 65535, PCB_ERANGE);
+    dim3 grid((unsigned)ceil_div((int64_t)N * k, kThreads), (unsigned)ceil_div(D, kGfCPT), (unsigned)B);
+    graph_feature_bwd_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(grad_out, idx, D, N, k, grad_x);
+    PCB_RETURN_LAUNCH_STATUS();
+}
+
+PCB_API int pcb_interpolate_f32(const float *points2, const int64_t *idx, const float *weight, int B, int N,
+                                int S, int D, int k, int channels_first, float *out, pcb_stream_t stream)
+{
+    PCB_REQUIRE(points2 && idx && weight && out, PCB_EINVAL);
+    PCB_REQUIRE(B > 0 && N > 0 && S > 0 && D > 0 && k > 0, PCB_EINVAL);
+    PCB_REQUIRE(k <= kIpMaxK && B <= 65535, PCB_ERANGE);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (channels_first) {
+        dim3 grid((unsigned)ceil_div(N, kThreads), (unsigned)ceil_div(D, kIpCPT), (unsigned)B);
+        interp_cf_kernel<<<grid, kThreads, 0, st>>>(points2, idx, weight, N, S, D, k, out);
+    } else if (D % 4 == 0 && aligned16(points2) && aligned16(out)) {
+        int64_t total = (int64_t)B * N * (D / 4);
+        interp_rows_kernel<4><<<grid_for(total), kThreads, 0, st>>>(points2, idx, weight, N, S, D, k, total, out);
+    } else {
+        int64_t total = (int64_t)B * N * D;
+        interp_rows_kernel<1><<<grid_for(total), kThreads, 0, st>>>(points2, idx, weight, N, S, D, k, total, out);
+    }
+    PCB_RETURN_LAUNCH_STATUS();
+}
+
+PCB_API int pcb_interpolate_bwd_f32(const float *grad_out, const int64_t *idx, const float *weight, int B,
+                                    int N, int S, int D, int k, int channels_first, float *grad_points2,
+                                    pcb_stream_t stream)
+{
+    PCB_REQUIRE(grad_out && idx && weight && grad_points2, PCB_EINVAL);
+    PCB_REQUIRE(B > 0 && N > 0 && S > 0 && D > 0 && k > 0, PCB_EINVAL);
+    int64_t total = (int64_t)B * N * D;
+    interp_bwd_kernel<<<grid_for(total), kThreads, 0, (cudaStream_t)stream>>>(grad_out, idx, weight, N, S, D, k,
+                                                                            channels_first, total, grad_points2);
+    PCB_RETURN_LAUNCH_STATUS();
+}
+
+PCB_API int pcb_square_distance_f32(const float *src, const float *dst, int B, int N, int M, int C, float *out,
+                                    pcb_stream_t stream)
+{
+    PCB_REQUIRE(src && dst && out, PCB_EINVAL);
+    PCB_REQUIRE(B > 0 && N > 0 && M > 0 && C > 0, PCB_EINVAL);
+    PCB_REQUIRE(C <= 512 && B <= 65535, PCB_ERANGE);
+    dim3 grid((unsigned)N, (unsigned)B);
+    square_distance_kernel<<<grid, kThreads, (C + 1) * sizeof(float), (cudaStream_t)stream>>>(src, dst, N, M, C, out);
+    PCB_RETURN_LAUNCH_STATUS();
+}

@@ -1,0 +1,316 @@
+"""Tensor-level front end of the CUDA kernels: takes/returns torch CUDA tensors, calls the C ABI
+(include/pcbridge.h) through ctypes on the current CUDA stream, and wires the differentiable
+ops into autograd.  PyTorch is used for device memory, streams and autograd bookkeeping only.
+
+Every function fails loudly when the extension is missing or the tensors are not on a CUDA
+device: there is no CPU / eager fallback on this path.
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+
+from . import _lib
+
+__all__ = [
+    "furthest_point_sample", "ball_query", "square_distance", "gather", "group_points",
+    "three_nn", "three_interpolate", "knn", "knn_cdist", "graph_feature", "check_index_errors",
+]
+
+_STRICT = os.environ.get("PCB_STRICT_INDEX", "0") == "1"
+_err_counters: dict[int, torch.Tensor] = {}
+
+
+def _f32(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise _lib.PcbError(f"{name} must be a CUDA tensor (got {t.device}); the hot path has no CPU fallback")
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _i64(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise _lib.PcbError(f"{name} must be a CUDA tensor (got {t.device})")
+    if t.dtype != torch.int64:
+        t = t.long()
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _call(name: str, dev: torch.device, *args, launches: int = 1) -> None:
+    fn = getattr(_lib.lib(), name)
+    if dev.index is not None and dev.index != torch.cuda.current_device():
+        with torch.cuda.device(dev):
+            code = fn(*args, _stream())
+    else:
+        code = fn(*args, _stream())
+    _lib.check(code, name)
+    _lib.count_launches(launches)
+
+
+def _err_counter(dev: torch.device) -> torch.Tensor:
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    t = _err_counters.get(key)
+    if t is None:
+        t = torch.zeros(1, dtype=torch.int32, device=dev)
+        _err_counters[key] = t
+    return t
+
+
+def check_index_errors(device=None) -> None:
+    """Raise IndexError if any non-clamping index_points call since the last check saw an index
+    outside [-N, N) -- the reference's behaviour (pointnet_util.py:62) made explicit, because a
+    stream-ordered kernel cannot raise by itself.  Synchronises."""
+    for key, t in list(_err_counters.items()):
+        if device is not None and torch.device(device).index not in (None, key):
+            continue
+        n = int(t.item())
+        if n:
+            t.zero_()
+            raise IndexError(f"index out of range in index_points ({n} entries)")
+
+
+# ---------------------------------------------------------------------------------------------
+# index producers (not differentiable)
+# ---------------------------------------------------------------------------------------------
+@torch.no_grad()
+def furthest_point_sample(xyz: torch.Tensor, npoint: int, start: torch.Tensor | None = None) -> torch.Tensor:
+    """xyz [B,N,3] -> LongTensor [B,npoint].  `start` [B]: first index of every cloud; when None
+    it is drawn exactly as the reference does (CPU default generator, pointnet_util.py:79)."""
+    xyz = _f32(xyz, "xyz")
+    B, N, C = xyz.shape
+    if C != 3:
+        raise ValueError("farthest point sampling expects 3-D coordinates")
+    if start is None:
+        start = torch.randint(0, N, (B,), dtype=torch.long).to(xyz.device)
+    start = _i64(start.to(xyz.device), "start")
+    out = torch.empty(B, npoint, dtype=torch.long, device=xyz.device)
+    _call("pcb_fps_f32", xyz.device, xyz.data_ptr(), B, N, start.data_ptr(), int(npoint), out.data_ptr())
+    return out
+
+
+@torch.no_grad()
+def ball_query(radius: float, nsample: int, xyz: torch.Tensor, new_xyz: torch.Tensor) -> torch.Tensor:
+    """First `nsample` points of xyz [B,N,3] within `radius` of each new_xyz [B,S,3] point, in index
+    order, padded with the first hit (pointnet_util.py:91-112).  Returns LongTensor [B,S,nsample]."""
+    xyz = _f32(xyz, "xyz")
+    new_xyz = _f32(new_xyz, "new_xyz")
+    B, N, _ = xyz.shape
+    S = new_xyz.shape[1]
+    # `sqrdists > radius ** 2`: Python squares in double, the comparison rounds it to fp32
+    r2 = float(torch.tensor(float(radius) ** 2, dtype=torch.float32).item())
+    out = torch.empty(B, S, nsample, dtype=torch.long, device=xyz.device)
+    _call("pcb_ball_query_f32", xyz.device, xyz.data_ptr(), new_xyz.data_ptr(), B, N, S, r2, int(nsample),
+          out.data_ptr())
+    return out
+
+
+@torch.no_grad()
+def square_distance(src: torch.Tensor, dst: torch.Tensor) -> torch.Tensor:
+    src = _f32(src, "src")
+    dst = _f32(dst, "dst")
+    B, N, C = src.shape
+    M = dst.shape[1]
+    out = torch.empty(B, N, M, dtype=torch.float32, device=src.device)
+    _call("pcb_square_distance_f32", src.device, src.data_ptr(), dst.data_ptr(), B, N, M, C, out.data_ptr())
+    return out
+
+
+@torch.no_grad()
+def three_nn(xyz1: torch.Tensor, xyz2: torch.Tensor, k: int = 3):
+    """k nearest xyz2 [B,S,3] points of every xyz1 [B,N,3] point.
+    Returns (dist [B,N,k] squared ascending, idx [B,N,k] int64, weight [B,N,k])."""
+    xyz1 = _f32(xyz1, "xyz1")
+    xyz2 = _f32(xyz2, "xyz2")
+    B, N, _ = xyz1.shape
+    S = xyz2.shape[1]
+    dist = torch.empty(B, N, k, dtype=torch.float32, device=xyz1.device)
+    idx = torch.empty(B, N, k, dtype=torch.long, device=xyz1.device)
+    weight = torch.empty(B, N, k, dtype=torch.float32, device=xyz1.device)
+    _call("pcb_three_nn_f32", xyz1.device, xyz1.data_ptr(), xyz2.data_ptr(), B, N, S, int(k), dist.data_ptr(),
+          idx.data_ptr(), weight.data_ptr())
+    return dist, idx, weight
+
+
+@torch.no_grad()
+def knn(x: torch.Tensor, k: int, channels_first: bool = True, return_dist: bool = False):
+    """DGCNN.knn: x [B,D,N] (channels_first) or [B,N,D] -> LongTensor [B,N,k], neighbours ordered by
+    (pairwise distance, index), self included."""
+    x = _f32(x, "x")
+    if channels_first:
+        B, D, N = x.shape
+    else:
+        B, N, D = x.shape
+        if D != 3:                       # feature-space kernels read the channels-first layout
+            x = x.transpose(1, 2).contiguous()
+            channels_first = True
+    idx = torch.empty(B, N, k, dtype=torch.long, device=x.device)
+    dist = torch.empty(B, N, k, dtype=torch.float32, device=x.device) if return_dist else None
+    _call("pcb_knn_f32", x.device, x.data_ptr(), B, N, D, int(k), int(channels_first), idx.data_ptr(),
+          dist.data_ptr() if return_dist else None, launches=1 if D == 3 else 2)
+    return (idx, dist) if return_dist else idx
+
+
+@torch.no_grad()
+def knn_cdist(xyz: torch.Tensor, k: int, return_dist: bool = False):
+    """torch.cdist(xyz, xyz).topk(k, largest=False) without the [B,N,N] matrix
+    (attention_modules.py:584-586).  xyz [B,N,3] -> LongTensor [B,N,k]."""
+    xyz = _f32(xyz, "xyz")
+    B, N, C = xyz.shape
+    if C != 3:
+        raise ValueError("knn_cdist expects 3-D coordinates")
+    idx = torch.empty(B, N, k, dtype=torch.long, device=xyz.device)
+    dist = torch.empty(B, N, k, dtype=torch.float32, device=xyz.device) if return_dist else None
+    _call("pcb_knn_cdist_f32", xyz.device, xyz.data_ptr(), B, N, int(k), idx.data_ptr(),
+          dist.data_ptr() if return_dist else None)
+    return (idx, dist) if return_dist else idx
+
+
+# ---------------------------------------------------------------------------------------------
+# differentiable gathers
+# ---------------------------------------------------------------------------------------------
+class _Gather(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, points, idx, clamp):
+        points = _f32(points, "points")
+        idx = _i64(idx, "idx")
+        B, N, C = points.shape
+        M = idx.numel() // B
+        out = torch.empty(*idx.shape, C, dtype=torch.float32, device=points.device)
+        err = None if clamp else _err_counter(points.device)
+        _call("pcb_gather_f32", points.device, points.data_ptr(), idx.data_ptr(), B, N, C, M, int(clamp),
+              out.data_ptr(), err.data_ptr() if err is not None else None)
+        if not clamp and _STRICT:
+            check_index_errors(points.device)
+        ctx.save_for_backward(idx)
+        ctx.shape = (B, N, C, M, int(clamp))
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        (idx,) = ctx.saved_tensors
+        B, N, C, M, clamp = ctx.shape
+        gout = _f32(gout, "grad")
+        gpoints = torch.zeros(B, N, C, dtype=torch.float32, device=gout.device)
+        _call("pcb_gather_bwd_f32", gout.device, gout.data_ptr(), idx.data_ptr(), B, N, C, M, clamp,
+              gpoints.data_ptr())
+        return gpoints, None, None
+
+
+def gather(points: torch.Tensor, idx: torch.Tensor, clamp: bool = False) -> torch.Tensor:
+    """index_points: points [B,N,C], idx [B,...] -> [B,...,C]."""
+    return _Gather.apply(points, idx, bool(clamp))
+
+
+class _GroupPoints(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, xyz, points, new_xyz, idx, xyz_first, points_cf, clamp):
+        xyz = _f32(xyz, "xyz")
+        new_xyz = _f32(new_xyz, "new_xyz")
+        idx = _i64(idx, "idx")
+        B, N, _ = xyz.shape
+        _, S, K = idx.shape
+        if points is not None:
+            points = _f32(points, "points")
+            D = points.shape[1] if points_cf else points.shape[2]
+        else:
+            D = 0
+        out = torch.empty(B, S, K, 3 + D, dtype=torch.float32, device=xyz.device)
+        _call("pcb_group_points_f32", xyz.device, xyz.data_ptr(), points.data_ptr() if D else None,
+              new_xyz.data_ptr(), idx.data_ptr(), B, N, S, K, D, int(xyz_first), int(points_cf), int(clamp),
+              out.data_ptr())
+        ctx.save_for_backward(idx)
+        ctx.meta = (B, N, S, K, D, int(xyz_first), int(points_cf), int(clamp))
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        (idx,) = ctx.saved_tensors
+        B, N, S, K, D, xyz_first, points_cf, clamp = ctx.meta
+        gpoints = None
+        if D and ctx.needs_input_grad[1]:
+            gout = _f32(gout, "grad")
+            shape = (B, D, N) if points_cf else (B, N, D)
+            gpoints = torch.zeros(shape, dtype=torch.float32, device=gout.device)
+            _call("pcb_group_points_bwd_f32", gout.device, gout.data_ptr(), idx.data_ptr(), B, N, S, K, D,
+                  xyz_first, points_cf, clamp, gpoints.data_ptr())
+        return None, gpoints, None, None, None, None, None
+
+
+def group_points(xyz, points, new_xyz, idx, xyz_first: bool = True, points_cf: bool = False,
+                 clamp: bool = False) -> torch.Tensor:
+    """Fused index_points(xyz, idx) - new_xyz, index_points(points, idx) and concat:
+    -> [B,S,K,3+D].  `points` is [B,N,D], or [B,D,N] with points_cf=True, or None."""
+    return _GroupPoints.apply(xyz, points, new_xyz, idx, bool(xyz_first), bool(points_cf), bool(clamp))
+
+
+class _GraphFeature(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, idx):
+        x = _f32(x, "x")
+        idx = _i64(idx, "idx")
+        B, D, N = x.shape
+        k = idx.shape[2]
+        out = torch.empty(B, 2 * D, N, k, dtype=torch.float32, device=x.device)
+        _call("pcb_graph_feature_f32", x.device, x.data_ptr(), idx.data_ptr(), B, D, N, k, out.data_ptr())
+        ctx.save_for_backward(idx)
+        ctx.meta = (B, D, N, k)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        (idx,) = ctx.saved_tensors
+        B, D, N, k = ctx.meta
+        gout = _f32(gout, "grad")
+        gx = torch.zeros(B, D, N, dtype=torch.float32, device=gout.device)
+        _call("pcb_graph_feature_bwd_f32", gout.device, gout.data_ptr(), idx.data_ptr(), B, D, N, k,
+              gx.data_ptr())
+        return gx, None
+
+
+def graph_feature(x: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    """x [B,D,N], idx [B,N,k] -> [B,2D,N,k] = cat(x[idx] - x, x) (DGCNN.py:72-109)."""
+    return _GraphFeature.apply(x, idx)
+
+
+class _Interpolate(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, points2, idx, weight, channels_first):
+        points2 = _f32(points2, "points2")
+        idx = _i64(idx, "idx")
+        weight = _f32(weight, "weight")
+        B, N, k = idx.shape
+        if channels_first:
+            _, D, S = points2.shape
+            out = torch.empty(B, D, N, dtype=torch.float32, device=points2.device)
+        else:
+            _, S, D = points2.shape
+            out = torch.empty(B, N, D, dtype=torch.float32, device=points2.device)
+        _call("pcb_interpolate_f32", points2.device, points2.data_ptr(), idx.data_ptr(), weight.data_ptr(), B, N,
+              S, D, k, int(channels_first), out.data_ptr())
+        ctx.save_for_backward(idx, weight)
+        ctx.meta = (B, N, S, D, k, int(channels_first))
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        idx, weight = ctx.saved_tensors
+        B, N, S, D, k, cf = ctx.meta
+        gout = _f32(gout, "grad")
+        shape = (B, D, S) if cf else (B, S, D)
+        gp2 = torch.zeros(shape, dtype=torch.float32, device=gout.device)
+        _call("pcb_interpolate_bwd_f32", gout.device, gout.data_ptr(), idx.data_ptr(), weight.data_ptr(), B, N, S,
+              D, k, cf, gp2.data_ptr())
+        return gp2, None, None, None
+
+
+def three_interpolate(points2: torch.Tensor, idx: torch.Tensor, weight: torch.Tensor,
+                      channels_first: bool = False) -> torch.Tensor:
+    """sum_j weight[b,n,j] * points2[b, idx[b,n,j]]: points2 [B,S,D] -> [B,N,D], or with
+    channels_first [B,D,S] -> [B,D,N]."""
+    return _Interpolate.apply(points2, idx, weight, bool(channels_first))
