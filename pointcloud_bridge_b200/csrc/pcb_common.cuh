@@ -62,7 +62,7 @@ __device__ __forceinline__ float cdist3_pre(float m2x, float m2y, float m2z, flo
 
 // |v|^2 over C contiguous floats in ATen's CPU order: 4 interleaved accumulators of 8 lanes
 // over the leading floor(C/8) vectors, folded ((A0+A1)+A2)+A3, scalar tail summed first from 0,
-// then the 8 lane partials left to right (oracle/pcb_oracle.c:orc_sumsq).
+// then the 8 lane partials left to right.
 __device__ __forceinline__ float row_sumsq_aten(const float *v, int C, int stride)
 {
     float acc[4][8];
