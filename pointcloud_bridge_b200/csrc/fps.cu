@@ -140,7 +140,7 @@ static int launch_fps_reg(const float *xyz, int B, int N, const int64_t *start, 
                           int64_t *out, cudaStream_t st)
 {
     size_t smem = (size_t)THREADS * PPT * 3 * sizeof(float);
-    if (smem > 48 * 1024) {
+    if (smem + 1024 > 48 * 1024) {               // static smem (s_red) counts against the 48 KB default
         cudaError_t e = cudaFuncSetAttribute(fps_reg_kernel<THREADS, PPT>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
