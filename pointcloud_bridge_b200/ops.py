@@ -42,13 +42,30 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
-def _call(name: str, dev: torch.device, *args, launches: int = 1) -> None:
+# Optional per-launch timing (bench.py / tools): a list that receives
+# (entry point, algorithmic bytes, start event, end event) for every call while it is set.
+_timer: list | None = None
+
+
+def set_kernel_timer(sink: list | None) -> None:
+    global _timer
+    _timer = sink
+
+
+def _call(name: str, dev: torch.device, *args, launches: int = 1, alg_bytes: int = 0) -> None:
     fn = getattr(_lib.lib(), name)
+    timed = _timer is not None
+    if timed:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     if dev.index is not None and dev.index != torch.cuda.current_device():
         with torch.cuda.device(dev):
             code = fn(*args, _stream())
     else:
         code = fn(*args, _stream())
+    if timed:
+        e1.record()
+        _timer.append((name, int(alg_bytes), e0, e1))
     _lib.check(code, name)
     _lib.count_launches(launches)
 
@@ -90,7 +107,8 @@ def furthest_point_sample(xyz: torch.Tensor, npoint: int, start: torch.Tensor | 
         start = torch.randint(0, N, (B,), dtype=torch.long).to(xyz.device)
     start = _i64(start.to(xyz.device), "start")
     out = torch.empty(B, npoint, dtype=torch.long, device=xyz.device)
-    _call("pcb_fps_f32", xyz.device, xyz.data_ptr(), B, N, start.data_ptr(), int(npoint), out.data_ptr())
+    _call("pcb_fps_f32", xyz.device, xyz.data_ptr(), B, N, start.data_ptr(), int(npoint), out.data_ptr(),
+          alg_bytes=B * (12 * N + 8 * npoint))
     return out
 
 
@@ -106,7 +124,7 @@ def ball_query(radius: float, nsample: int, xyz: torch.Tensor, new_xyz: torch.Te
     r2 = float(torch.tensor(float(radius) ** 2, dtype=torch.float32).item())
     out = torch.empty(B, S, nsample, dtype=torch.long, device=xyz.device)
     _call("pcb_ball_query_f32", xyz.device, xyz.data_ptr(), new_xyz.data_ptr(), B, N, S, r2, int(nsample),
-          out.data_ptr())
+          out.data_ptr(), alg_bytes=B * (12 * N + 12 * S + 8 * S * nsample))
     return out
 
 
@@ -117,7 +135,8 @@ def square_distance(src: torch.Tensor, dst: torch.Tensor) -> torch.Tensor:
     B, N, C = src.shape
     M = dst.shape[1]
     out = torch.empty(B, N, M, dtype=torch.float32, device=src.device)
-    _call("pcb_square_distance_f32", src.device, src.data_ptr(), dst.data_ptr(), B, N, M, C, out.data_ptr())
+    _call("pcb_square_distance_f32", src.device, src.data_ptr(), dst.data_ptr(), B, N, M, C, out.data_ptr(),
+          alg_bytes=4 * B * (N * C + M * C + N * M))
     return out
 
 
@@ -133,7 +152,7 @@ def three_nn(xyz1: torch.Tensor, xyz2: torch.Tensor, k: int = 3):
     idx = torch.empty(B, N, k, dtype=torch.long, device=xyz1.device)
     weight = torch.empty(B, N, k, dtype=torch.float32, device=xyz1.device)
     _call("pcb_three_nn_f32", xyz1.device, xyz1.data_ptr(), xyz2.data_ptr(), B, N, S, int(k), dist.data_ptr(),
-          idx.data_ptr(), weight.data_ptr())
+          idx.data_ptr(), weight.data_ptr(), alg_bytes=B * (12 * N + 12 * S + 16 * k * N))
     return dist, idx, weight
 
 
@@ -152,7 +171,8 @@ def knn(x: torch.Tensor, k: int, channels_first: bool = True, return_dist: bool 
     idx = torch.empty(B, N, k, dtype=torch.long, device=x.device)
     dist = torch.empty(B, N, k, dtype=torch.float32, device=x.device) if return_dist else None
     _call("pcb_knn_f32", x.device, x.data_ptr(), B, N, D, int(k), int(channels_first), idx.data_ptr(),
-          dist.data_ptr() if return_dist else None, launches=1 if D == 3 else 2)
+          dist.data_ptr() if return_dist else None, launches=1 if D == 3 else 2,
+          alg_bytes=B * (4 * D * N + 8 * N * k))
     return (idx, dist) if return_dist else idx
 
 
@@ -167,7 +187,7 @@ def knn_cdist(xyz: torch.Tensor, k: int, return_dist: bool = False):
     idx = torch.empty(B, N, k, dtype=torch.long, device=xyz.device)
     dist = torch.empty(B, N, k, dtype=torch.float32, device=xyz.device) if return_dist else None
     _call("pcb_knn_cdist_f32", xyz.device, xyz.data_ptr(), B, N, int(k), idx.data_ptr(),
-          dist.data_ptr() if return_dist else None)
+          dist.data_ptr() if return_dist else None, alg_bytes=B * (12 * N + 8 * N * k))
     return (idx, dist) if return_dist else idx
 
 
@@ -184,7 +204,8 @@ class _Gather(torch.autograd.Function):
         out = torch.empty(*idx.shape, C, dtype=torch.float32, device=points.device)
         err = None if clamp else _err_counter(points.device)
         _call("pcb_gather_f32", points.device, points.data_ptr(), idx.data_ptr(), B, N, C, M, int(clamp),
-              out.data_ptr(), err.data_ptr() if err is not None else None)
+              out.data_ptr(), err.data_ptr() if err is not None else None,
+              alg_bytes=B * (4 * N * C + 8 * M + 4 * M * C))
         if not clamp and _STRICT:
             check_index_errors(points.device)
         ctx.save_for_backward(idx)
@@ -198,7 +219,7 @@ class _Gather(torch.autograd.Function):
         gout = _f32(gout, "grad")
         gpoints = torch.zeros(B, N, C, dtype=torch.float32, device=gout.device)
         _call("pcb_gather_bwd_f32", gout.device, gout.data_ptr(), idx.data_ptr(), B, N, C, M, clamp,
-              gpoints.data_ptr())
+              gpoints.data_ptr(), alg_bytes=B * (4 * N * C + 8 * M + 4 * M * C))
         return gpoints, None, None
 
 
@@ -223,7 +244,7 @@ class _GroupPoints(torch.autograd.Function):
         out = torch.empty(B, S, K, 3 + D, dtype=torch.float32, device=xyz.device)
         _call("pcb_group_points_f32", xyz.device, xyz.data_ptr(), points.data_ptr() if D else None,
               new_xyz.data_ptr(), idx.data_ptr(), B, N, S, K, D, int(xyz_first), int(points_cf), int(clamp),
-              out.data_ptr())
+              out.data_ptr(), alg_bytes=B * (4 * N * (3 + D) + 12 * S + 8 * S * K + 4 * S * K * (3 + D)))
         ctx.save_for_backward(idx)
         ctx.meta = (B, N, S, K, D, int(xyz_first), int(points_cf), int(clamp))
         return out
@@ -238,7 +259,8 @@ class _GroupPoints(torch.autograd.Function):
             shape = (B, D, N) if points_cf else (B, N, D)
             gpoints = torch.zeros(shape, dtype=torch.float32, device=gout.device)
             _call("pcb_group_points_bwd_f32", gout.device, gout.data_ptr(), idx.data_ptr(), B, N, S, K, D,
-                  xyz_first, points_cf, clamp, gpoints.data_ptr())
+                  xyz_first, points_cf, clamp, gpoints.data_ptr(),
+                  alg_bytes=B * (4 * N * D + 8 * S * K + 4 * S * K * D))
         return None, gpoints, None, None, None, None, None
 
 
@@ -257,7 +279,8 @@ class _GraphFeature(torch.autograd.Function):
         B, D, N = x.shape
         k = idx.shape[2]
         out = torch.empty(B, 2 * D, N, k, dtype=torch.float32, device=x.device)
-        _call("pcb_graph_feature_f32", x.device, x.data_ptr(), idx.data_ptr(), B, D, N, k, out.data_ptr())
+        _call("pcb_graph_feature_f32", x.device, x.data_ptr(), idx.data_ptr(), B, D, N, k, out.data_ptr(),
+              alg_bytes=B * (4 * N * D + 8 * N * k + 8 * D * N * k))
         ctx.save_for_backward(idx)
         ctx.meta = (B, D, N, k)
         return out
@@ -269,7 +292,7 @@ class _GraphFeature(torch.autograd.Function):
         gout = _f32(gout, "grad")
         gx = torch.zeros(B, D, N, dtype=torch.float32, device=gout.device)
         _call("pcb_graph_feature_bwd_f32", gout.device, gout.data_ptr(), idx.data_ptr(), B, D, N, k,
-              gx.data_ptr())
+              gx.data_ptr(), alg_bytes=B * (4 * N * D + 8 * N * k + 8 * D * N * k))
         return gx, None
 
 
@@ -292,7 +315,7 @@ class _Interpolate(torch.autograd.Function):
             _, S, D = points2.shape
             out = torch.empty(B, N, D, dtype=torch.float32, device=points2.device)
         _call("pcb_interpolate_f32", points2.device, points2.data_ptr(), idx.data_ptr(), weight.data_ptr(), B, N,
-              S, D, k, int(channels_first), out.data_ptr())
+              S, D, k, int(channels_first), out.data_ptr(), alg_bytes=B * (4 * S * D + 12 * k * N + 4 * N * D))
         ctx.save_for_backward(idx, weight)
         ctx.meta = (B, N, S, D, k, int(channels_first))
         return out
@@ -305,7 +328,7 @@ class _Interpolate(torch.autograd.Function):
         shape = (B, D, S) if cf else (B, S, D)
         gp2 = torch.zeros(shape, dtype=torch.float32, device=gout.device)
         _call("pcb_interpolate_bwd_f32", gout.device, gout.data_ptr(), idx.data_ptr(), weight.data_ptr(), B, N, S,
-              D, k, cf, gp2.data_ptr())
+              D, k, cf, gp2.data_ptr(), alg_bytes=B * (4 * S * D + 12 * k * N + 4 * N * D))
         return gp2, None, None, None
 
 

@@ -1,0 +1,56 @@
+"""PointNet++ single-scale-grouping semantic segmentation network, drop-in for
+Partsize-identical/models/pointnet2_sem_seg.py (same `get_model(num_classes)` / `get_loss()`,
+same parameter names, same [B,9,N] -> ([B,N,num_classes] log-probabilities, l4_points) contract).
+"""
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .pointnet_util import PointNetFeaturePropagation, PointNetSetAbstraction, _bn_rows, _rows
+
+
+class get_model(nn.Module):
+    # layer table: pointnet2_sem_seg.py:11-22
+    SA = [(1024, 0.1, 32, 9 + 3, [32, 32, 64]), (256, 0.2, 32, 64 + 3, [64, 64, 128]),
+          (64, 0.4, 32, 128 + 3, [128, 128, 256]), (16, 0.8, 32, 256 + 3, [256, 256, 512])]
+    FP = [(768, [256, 256]), (384, [256, 256]), (320, [256, 128]), (128, [128, 128, 128])]
+
+    def __init__(self, num_classes):
+        super().__init__()
+        for i, (npoint, radius, nsample, cin, mlp) in enumerate(self.SA, 1):
+            setattr(self, f"sa{i}", PointNetSetAbstraction(npoint, radius, nsample, cin, mlp, False))
+        for i, (cin, mlp) in zip((4, 3, 2, 1), self.FP):
+            setattr(self, f"fp{i}", PointNetFeaturePropagation(cin, mlp))
+        self.conv1 = nn.Conv1d(128, 128, 1)
+        self.conv2 = nn.Conv1d(128, num_classes, 1)
+        self.bn1 = nn.BatchNorm1d(128)
+        self.drop1 = nn.Dropout(0.5)
+
+    def forward(self, xyz):
+        l0_points, l0_xyz = xyz, xyz[:, :3, :]
+        l1_xyz, l1_points = self.sa1(l0_xyz, l0_points)
+        l2_xyz, l2_points = self.sa2(l1_xyz, l1_points)
+        l3_xyz, l3_points = self.sa3(l2_xyz, l2_points)
+        l4_xyz, l4_points = self.sa4(l3_xyz, l3_points)
+        l3_points = self.fp4(l3_xyz, l4_xyz, l3_points, l4_points)
+        l2_points = self.fp3(l2_xyz, l3_xyz, l2_points, l3_points)
+        l1_points = self.fp2(l1_xyz, l2_xyz, l1_points, l2_points)
+        l0_points = self.fp1(l0_xyz, l1_xyz, None, l1_points)
+        return _seg_head(self, l0_points), l4_points
+
+
+def _seg_head(net, feats_bcn):
+    """conv1 -> bn1 -> ReLU -> dropout -> conv2 -> log_softmax over classes -> [B,N,classes]
+    (pointnet2_sem_seg.py:43-47), evaluated on point-major rows."""
+    x = _rows(feats_bcn)
+    B, N, C = x.shape
+    x = F.linear(x.reshape(B * N, C), net.conv1.weight.flatten(1), net.conv1.bias)
+    x = net.drop1(F.relu(_bn_rows(net.bn1, x), inplace=True))
+    x = F.linear(x, net.conv2.weight.flatten(1), net.conv2.bias)
+    return F.log_softmax(x.float(), dim=-1).view(B, N, -1)
+
+
+class get_loss(nn.Module):
+    """pointnet2_sem_seg.py:51-57."""
+
+    def forward(self, pred, target, trans_feat, weight):
+        return F.nll_loss(pred, target, weight=weight)

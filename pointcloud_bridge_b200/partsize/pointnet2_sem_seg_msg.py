@@ -1,0 +1,49 @@
+"""PointNet++ multi-scale-grouping semantic segmentation network, drop-in for
+Partsize-identical/models/pointnet2_sem_seg_msg.py (`get_model(num_classes)`: [B,9,N] ->
+([B,N,num_classes] log-probabilities, l4_points)).  The reference file's "structure-oriented"
+get_loss hard-codes batch 64 and .cuda() (pointnet2_sem_seg_msg.py:45-181) and is outside the
+hot path; `get_loss` here is the plain NLL loss the training step of BASELINE config 2 uses.
+"""
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .pointnet2_sem_seg import _seg_head
+from .pointnet_util import PointNetFeaturePropagation, PointNetSetAbstractionMsg
+
+
+class get_model(nn.Module):
+    # layer table: pointnet2_sem_seg_msg.py:11-21
+    SA = [(1024, [0.05, 0.1], [16, 32], 9, [[16, 16, 32], [32, 32, 64]]),
+          (256, [0.1, 0.2], [16, 32], 32 + 64, [[64, 64, 128], [64, 96, 128]]),
+          (64, [0.2, 0.4], [16, 32], 128 + 128, [[128, 196, 256], [128, 196, 256]]),
+          (16, [0.4, 0.8], [16, 32], 256 + 256, [[256, 256, 512], [256, 384, 512]])]
+    FP = [(512 + 512 + 256 + 256, [256, 256]), (128 + 128 + 256, [256, 256]), (32 + 64 + 256, [256, 128]),
+          (128, [128, 128, 128])]
+
+    def __init__(self, num_classes):
+        super().__init__()
+        for i, (npoint, radii, nsamples, cin, mlps) in enumerate(self.SA, 1):
+            setattr(self, f"sa{i}", PointNetSetAbstractionMsg(npoint, radii, nsamples, cin, mlps))
+        for i, (cin, mlp) in zip((4, 3, 2, 1), self.FP):
+            setattr(self, f"fp{i}", PointNetFeaturePropagation(cin, mlp))
+        self.conv1 = nn.Conv1d(128, 128, 1)
+        self.bn1 = nn.BatchNorm1d(128)
+        self.drop1 = nn.Dropout(0.5)
+        self.conv2 = nn.Conv1d(128, num_classes, 1)
+
+    def forward(self, xyz):
+        l0_points, l0_xyz = xyz, xyz[:, :3, :]
+        l1_xyz, l1_points = self.sa1(l0_xyz, l0_points)
+        l2_xyz, l2_points = self.sa2(l1_xyz, l1_points)
+        l3_xyz, l3_points = self.sa3(l2_xyz, l2_points)
+        l4_xyz, l4_points = self.sa4(l3_xyz, l3_points)
+        l3_points = self.fp4(l3_xyz, l4_xyz, l3_points, l4_points)
+        l2_points = self.fp3(l2_xyz, l3_xyz, l2_points, l3_points)
+        l1_points = self.fp2(l1_xyz, l2_xyz, l1_points, l2_points)
+        l0_points = self.fp1(l0_xyz, l1_xyz, None, l1_points)
+        return _seg_head(self, l0_points), l4_points
+
+
+class get_loss(nn.Module):
+    def forward(self, pred, target, trans_feat=None, weight=None):
+        return F.nll_loss(pred.reshape(-1, pred.shape[-1]), target.reshape(-1), weight=weight)

@@ -1,0 +1,221 @@
+"""Drop-in for Partsize-identical/models/pointnet_util.py on the B200 kernels.
+
+Same public names, argument order, tensor layouts, int64 index outputs, error behaviour and
+nn.Module parameter names (`mlp_convs.i`, `mlp_bns.i`, `conv_blocks.i.j`, `bn_blocks.i.j`) as
+the reference, so its checkpoints load and its networks can import this module instead.
+Behind the names: farthest_point_sample / query_ball_point / index_points / three-NN are the
+CUDA kernels of libpcbridge (no distance matrices, no sorts), and the shared MLPs run on
+point-major rows ([B*S*K, C] @ W^T) instead of permuted NCHW tensors.
+
+Two additions that the reference only has inline (pointnet_util.py:325-334):
+`three_nn` and `three_interpolate`.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import ops
+
+__all__ = [
+    "square_distance", "index_points", "farthest_point_sample", "query_ball_point", "sample_and_group",
+    "sample_and_group_all", "three_nn", "three_interpolate", "PointNetSetAbstraction",
+    "PointNetSetAbstractionMsg", "PointNetFeaturePropagation",
+]
+
+
+# --------------------------------------------------------------------------------------------
+# L1 primitives (reference: pointnet_util.py:22-174)
+# --------------------------------------------------------------------------------------------
+def square_distance(src, dst):
+    """src [B,N,C], dst [B,M,C] -> [B,N,M]; -2*src.dst^T + |src|^2 + |dst|^2 in the reference's
+    fp32 operation order (pointnet_util.py:22-43)."""
+    return ops.square_distance(src, dst)
+
+
+def index_points(points, idx):
+    """points [B,N,C], idx [B,S] or [B,S,K] -> [B,S,C] / [B,S,K,C] (pointnet_util.py:46-63).
+    An index outside [-N, N) is an IndexError in the reference; here it is recorded on the
+    device and raised by ops.check_index_errors() (or at once with PCB_STRICT_INDEX=1)."""
+    return ops.gather(points, idx, clamp=False)
+
+
+def farthest_point_sample(xyz, npoint):
+    """xyz [B,N,3] -> LongTensor [B,npoint] (pointnet_util.py:66-88).  The start index is drawn
+    from the CPU default generator exactly as the reference does."""
+    return ops.furthest_point_sample(xyz, npoint)
+
+
+def query_ball_point(radius, nsample, xyz, new_xyz):
+    """-> LongTensor [B,S,nsample] (pointnet_util.py:91-112)."""
+    return ops.ball_query(radius, nsample, xyz, new_xyz)
+
+
+def sample_and_group(npoint, radius, nsample, xyz, points, returnfps=False):
+    """FPS -> centroids -> ball query -> grouped [dxyz | features]  (pointnet_util.py:116-152).
+    xyz [B,N,3], points [B,N,D] or None -> new_xyz [B,S,3], new_points [B,S,nsample,3+D]."""
+    fps_idx = farthest_point_sample(xyz, npoint)
+    new_xyz = index_points(xyz, fps_idx)
+    idx = query_ball_point(radius, nsample, xyz, new_xyz)
+    new_points = ops.group_points(xyz, points, new_xyz, idx, xyz_first=True)
+    if returnfps:
+        return new_xyz, new_points, index_points(xyz, idx), fps_idx
+    return new_xyz, new_points
+
+
+def sample_and_group_all(xyz, points):
+    """One group holding every point, centroid at the origin (pointnet_util.py:157-174)."""
+    B, N, d = xyz.shape
+    new_xyz = torch.zeros(B, 1, d, device=xyz.device, dtype=xyz.dtype)
+    grouped = xyz.view(B, 1, N, d)
+    if points is not None:
+        grouped = torch.cat([grouped, points.view(B, 1, N, -1)], dim=-1)
+    return new_xyz, grouped
+
+
+def three_nn(xyz1, xyz2, k=3):
+    """(dist, idx) of the k nearest xyz2 [B,S,3] points for each xyz1 [B,N,3] point, ascending,
+    ties by index -- what `square_distance(...).sort()[:, :, :k]` yields (pointnet_util.py:325-328)."""
+    dist, idx, _ = ops.three_nn(xyz1, xyz2, k)
+    return dist, idx
+
+
+def three_interpolate(points2, idx, dist):
+    """Inverse-distance interpolation of points2 [B,S,D] at the neighbours (idx, dist) [B,N,k]
+    -> [B,N,D]  (pointnet_util.py:330-334)."""
+    rec = 1.0 / (dist + 1e-8)
+    weight = rec / torch.sum(rec, dim=2, keepdim=True)
+    return ops.three_interpolate(points2, idx, weight, channels_first=False)
+
+
+# --------------------------------------------------------------------------------------------
+# shared MLP on rows
+# --------------------------------------------------------------------------------------------
+def _rows(t_bcn):
+    """[B,C,N] (any strides) -> point-major [B,N,C] contiguous; free when the tensor already is a
+    permuted view of point-major memory, which is what these modules hand to each other."""
+    t = t_bcn.permute(0, 2, 1)
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _bn_rows(bn, x):
+    """BatchNorm{1,2}d over every row of x [M,C]: the same statistics as the reference's
+    BatchNorm2d over (B, K, S) / BatchNorm1d over (B, N)."""
+    if bn.training and bn.track_running_stats and bn.num_batches_tracked is not None:
+        bn.num_batches_tracked.add_(1)
+    use_batch = bn.training or not bn.track_running_stats
+    mom = 0.0 if bn.momentum is None else bn.momentum
+    return F.batch_norm(x, bn.running_mean if bn.track_running_stats else None,
+                        bn.running_var if bn.track_running_stats else None, bn.weight, bn.bias,
+                        use_batch, mom, bn.eps)
+
+
+def mlp_rows(x, convs, bns):
+    """x [M,Cin] -> [M,Cout]: (1x1 conv -> BN -> ReLU) per layer, as pointnet_util.py:213-215."""
+    for conv, bn in zip(convs, bns):
+        x = F.linear(x, conv.weight.flatten(1), conv.bias)
+        x = F.relu(_bn_rows(bn, x), inplace=True)
+    return x
+
+
+def _cf_view(rows, B, S):
+    """[B*S, C] rows -> the reference's channels-first [B,C,S] shape, as a view."""
+    return rows.view(B, S, -1).permute(0, 2, 1)
+
+
+# --------------------------------------------------------------------------------------------
+# L2 modules (reference: pointnet_util.py:179-348)
+# --------------------------------------------------------------------------------------------
+class PointNetSetAbstraction(nn.Module):
+    """pointnet_util.py:179-219.  forward(xyz [B,3,N], points [B,D,N] | None)
+    -> new_xyz [B,3,S], new_points [B,mlp[-1],S]."""
+
+    def __init__(self, npoint, radius, nsample, in_channel, mlp, group_all):
+        super().__init__()
+        self.npoint, self.radius, self.nsample, self.group_all = npoint, radius, nsample, group_all
+        self.mlp_convs = nn.ModuleList()
+        self.mlp_bns = nn.ModuleList()
+        last = in_channel
+        for out in mlp:
+            self.mlp_convs.append(nn.Conv2d(last, out, 1))
+            self.mlp_bns.append(nn.BatchNorm2d(out))
+            last = out
+
+    def forward(self, xyz, points):
+        xyz_r = _rows(xyz)
+        pts_r = _rows(points) if points is not None else None
+        B = xyz_r.shape[0]
+        if self.group_all:
+            new_xyz, grouped = sample_and_group_all(xyz_r, pts_r)
+        else:
+            new_xyz, grouped = sample_and_group(self.npoint, self.radius, self.nsample, xyz_r, pts_r)
+        S, K, C = grouped.shape[1:]
+        y = mlp_rows(grouped.reshape(B * S * K, C), self.mlp_convs, self.mlp_bns)
+        y = y.view(B * S, K, -1).max(dim=1)[0]                       # max over the neighbours
+        return new_xyz.permute(0, 2, 1), _cf_view(y, B, S)
+
+
+class PointNetSetAbstractionMsg(nn.Module):
+    """pointnet_util.py:222-284: one FPS, then per radius ball query -> [features | dxyz] ->
+    shared MLP -> max; scales concatenated on channels."""
+
+    def __init__(self, npoint, radius_list, nsample_list, in_channel, mlp_list):
+        super().__init__()
+        self.npoint, self.radius_list, self.nsample_list = npoint, radius_list, nsample_list
+        self.conv_blocks = nn.ModuleList()
+        self.bn_blocks = nn.ModuleList()
+        for mlp in mlp_list:
+            convs, bns = nn.ModuleList(), nn.ModuleList()
+            last = in_channel + 3
+            for out in mlp:
+                convs.append(nn.Conv2d(last, out, 1))
+                bns.append(nn.BatchNorm2d(out))
+                last = out
+            self.conv_blocks.append(convs)
+            self.bn_blocks.append(bns)
+
+    def forward(self, xyz, points):
+        xyz_r = _rows(xyz)
+        pts_r = _rows(points) if points is not None else None
+        B = xyz_r.shape[0]
+        S = self.npoint
+        new_xyz = index_points(xyz_r, farthest_point_sample(xyz_r, S))
+        outs = []
+        for i, radius in enumerate(self.radius_list):
+            K = self.nsample_list[i]
+            idx = query_ball_point(radius, K, xyz_r, new_xyz)
+            grouped = ops.group_points(xyz_r, pts_r, new_xyz, idx, xyz_first=False)   # [feat | dxyz]
+            y = mlp_rows(grouped.view(B * S * K, -1), self.conv_blocks[i], self.bn_blocks[i])
+            outs.append(y.view(B * S, K, -1).max(dim=1)[0])
+        y = torch.cat(outs, dim=1)
+        return new_xyz.permute(0, 2, 1), _cf_view(y, B, S)
+
+
+class PointNetFeaturePropagation(nn.Module):
+    """pointnet_util.py:287-348: three-NN inverse-distance interpolation of points2 onto xyz1,
+    concat with points1, Conv1d/BN/ReLU stack.  All tensors channels-first as in the reference."""
+
+    def __init__(self, in_channel, mlp):
+        super().__init__()
+        self.mlp_convs = nn.ModuleList()
+        self.mlp_bns = nn.ModuleList()
+        last = in_channel
+        for out in mlp:
+            self.mlp_convs.append(nn.Conv1d(last, out, 1))
+            self.mlp_bns.append(nn.BatchNorm1d(out))
+            last = out
+
+    def forward(self, xyz1, xyz2, points1, points2):
+        x1, x2, p2 = _rows(xyz1), _rows(xyz2), _rows(points2)
+        B, N, _ = x1.shape
+        S = x2.shape[1]
+        if S == 1:
+            interp = p2.repeat(1, N, 1)
+        else:
+            _, idx, weight = ops.three_nn(x1, x2, 3)
+            interp = ops.three_interpolate(p2, idx, weight, channels_first=False)
+        if points1 is not None:
+            interp = torch.cat([_rows(points1).to(interp.dtype), interp], dim=-1)
+        y = mlp_rows(interp.view(B * N, -1), self.mlp_convs, self.mlp_bns)
+        return _cf_view(y, B, N)

@@ -72,3 +72,30 @@ def assert_topk_equivalent(idx_ours, idx_ref, dist_of, what="", ulp_tol=0):
     mism = (idx_ours != idx_ref) & ~tied
     assert not mism.any(), f"{what}: {int(mism.sum())} untied indices differ"
     return float((idx_ours != idx_ref).mean())
+
+
+def seeded_fill_(model, seed=0):
+    """Deterministic, construction-order-independent weights: every parameter / buffer is filled
+    from a numpy generator keyed by its *name*, so the reference network and the B200 network
+    (same state_dict keys) get bit-identical values on any host."""
+    import zlib
+
+    import torch
+    with torch.no_grad():
+        for name, t in list(model.named_parameters()) + list(model.named_buffers()):
+            rng = np.random.default_rng((zlib.crc32(name.encode()) + 7919 * seed) & 0x7FFFFFFF)
+            if name.endswith("num_batches_tracked") or name.endswith("freqs") or "base_weights" in name:
+                continue
+            if name.endswith("running_var"):
+                v = rng.uniform(0.5, 1.5, t.shape)
+            elif name.endswith("running_mean"):
+                v = rng.standard_normal(t.shape) * 0.1
+            elif t.dim() > 1:
+                fan_in = int(np.prod(t.shape[1:]))
+                v = rng.standard_normal(t.shape) / np.sqrt(fan_in)
+            elif name.endswith("weight"):                     # norm-layer scale
+                v = rng.uniform(0.5, 1.5, t.shape)
+            else:                                             # biases
+                v = rng.standard_normal(t.shape) * 0.1
+            t.copy_(torch.from_numpy(np.asarray(v, np.float32)))
+    return model
