@@ -7,12 +7,15 @@ Tolerances (fp32 mode; north_star asks 1e-5 relative for fp32, 1e-2 for bf16):
     remaining difference is GEMM/BN summation order: |delta| <= 2e-5 * max|ref| + 2e-5 is asserted
     for PointNet++ SSG/MSG and the Highway PointNet2;
   * DGCNN layers 2-4 run kNN on learned features, where a 1-ulp upstream difference can swap
-    two near-tied neighbours; asserted: 99.9 % of logits within 1e-4 relative and argmax
-    agreement >= 99.9 %;
+    two near-tied neighbours.  The reference itself, run on CPU with 1 thread instead of 8, moves
+    its logits by p50 3e-7 / p99.9 4.2e-4 / max 1.7e-3 (relative to max|logit|), and by max 3.7e-3
+    under a 3e-7 relative weight perturbation (measured in the authoring container).  Asserted:
+    p50 < 1e-5, p99.9 < 2e-3, max < 2e-2, argmax agreement >= 99.9 %; the kNN itself is checked
+    bit-exact at op level on the oracle's own features (tests/test_gpu_prims.py);
   * BriStruNet feeds eigenvalue ratios (e0 - e1) / (e0 + 1e-8) of near-singular 3x3 covariances
-    into the net (attention_modules.py:631-633): chaotic in fp32, different between LAPACK (CPU)
-    and cuSOLVER (GPU) for the reference itself.  Asserted: FPS indices bit-exact, and the
-    logits' median error small.
+    into the net (attention_modules.py:631-633), ill-conditioned in fp32 (LAPACK on CPU vs
+    cuSOLVER on GPU).  Measured 6e-6 max on the fixture; asserted: FPS indices bit-exact,
+    median < 1e-5, p99 < 1e-3.
   * bf16 autocast: 1e-2 relative to max|ref| on the log-probabilities (mean) for MSG.
 """
 import contextlib
@@ -91,7 +94,11 @@ def test_msg_forward_and_train_step_config2(g):
                     ("rv_sa1", net.sa1.bn_blocks[0][0].running_var)):
         e = rel_err(p, g[f"msg_train_{name}"])
         print("msg train", name, e)
-        assert e < 2e-4, name
+        # Weight gradients below a BatchNorm cancel heavily in fp32: the reference's own CPU result
+        # for g_sa1 / g_fp1 moves by 5e-3 between 1 and 8 threads and sits 5e-3..1e-2 away from an
+        # fp64 evaluation (measured in the authoring container), so 2e-2 is the parity bar there;
+        # quantities without that cancellation must agree to 2e-4.
+        assert e < (2e-2 if name in ("g_sa1", "g_fp1") else 2e-4), name
 
 
 def test_msg_bf16_autocast_within_1e2(g):
@@ -117,7 +124,7 @@ def test_dgcnn_forward_config3(g):
     assert y.shape == ref.shape
     err = np.abs(y - ref) / (np.abs(ref).max() + 1e-12)
     print("dgcnn rel err: p50 %.2e p99.9 %.2e max %.2e" % (np.median(err), np.quantile(err, 0.999), err.max()))
-    assert np.quantile(err, 0.999) < 1e-4
+    assert np.median(err) < 1e-5 and np.quantile(err, 0.999) < 2e-3 and err.max() < 2e-2
     assert (y.argmax(-1) == ref.argmax(-1)).mean() >= 0.999
 
 
@@ -146,7 +153,7 @@ def test_bristrunet_forward_config4(g):
     err = np.abs(y.float().cpu().numpy() - ref) / (np.abs(ref).max() + 1e-12)
     print("bristrunet rel err: p50 %.2e p99 %.2e max %.2e" % (np.median(err), np.quantile(err, 0.99), err.max()))
     assert np.isfinite(y.float().cpu().numpy()).all()
-    assert np.median(err) < 5e-2
+    assert np.median(err) < 1e-5 and np.quantile(err, 0.99) < 1e-3
     crit = hb_model.BridgeStructureLoss(num_classes=5, alpha=80, rel_margin=0.3).to(DEV)
     loss = crit(torch.from_numpy(ref).to(DEV), lab[:1], xyz[:1])
     assert abs(loss.item() - float(g["bri_loss"])) < 1e-4 * max(1.0, abs(float(g["bri_loss"])))
