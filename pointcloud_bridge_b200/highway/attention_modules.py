@@ -120,7 +120,7 @@ class ColorFeatureExtraction(nn.Module):
         c = _rows(colors)
         B, N, _ = c.shape
         feats = seq_rows(self.color_mlp, c.reshape(B * N, -1))
-        if self.dead_knn:
+        if getattr(self, "dead_knn", False):
             ops.gather(feats.view(B, N, -1), knn_cdist(xyz, 16))
         local = feats * seq_rows(self.color_attention, feats)
         pooled = feats.view(B, N, -1).mean(dim=1)                           # AdaptiveAvgPool1d(1)

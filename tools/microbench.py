@@ -27,7 +27,7 @@ def peaks():
 
 
 def timeit(fn, iters, flush):
-    for _ in range(5):
+    for _ in range(int(os.environ.get("PCB_MB_WARMUP", "5"))):
         fn()
     torch.cuda.synchronize()
     ts = []
