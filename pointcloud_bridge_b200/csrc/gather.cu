@@ -13,6 +13,24 @@ namespace pcb {
 
 constexpr int kThreads = 256;
 
+// Division by a runtime-constant 32-bit divisor in two instructions (mul.hi + shift); the
+// element index -> (row, channel) -> (cloud, ...) decompositions of these kernels were the
+// instruction-issue bottleneck with native 64-bit division (round-1 ncu: 70 % issue, 2 % DRAM).
+struct FastDiv {
+    unsigned d, magic, shift;
+    __device__ __forceinline__ unsigned div(unsigned n) const { return (__umulhi(n, magic) + n) >> shift; }   // n < 2^31
+};
+static FastDiv make_fastdiv(unsigned d)
+{
+    FastDiv f;
+    f.d = d;
+    unsigned l = 0;
+    while ((1ull << l) < d) ++l;
+    f.shift = l;
+    f.magic = (unsigned)(((1ull << 32) * ((1ull << l) - d)) / d + 1);
+    return f;
+}
+
 __device__ __forceinline__ bool resolve_index(long long &i, int N, int clamp)
 {
     if (clamp) {
@@ -25,51 +43,49 @@ __device__ __forceinline__ bool resolve_index(long long &i, int N, int clamp)
 
 // ------------------------------------------------------------------------------------------
 // index_points.  VEC = 4: C % 4 == 0 and 16-byte aligned rows; VEC = 1: anything.
-// One thread per VEC consecutive output floats -> coalesced stores.
+// One thread per VEC consecutive output floats -> coalesced stores.  total < 2^31.
 // ------------------------------------------------------------------------------------------
 template <int VEC>
 __global__ void __launch_bounds__(kThreads)
-gather_kernel(const float *__restrict__ points, const int64_t *__restrict__ idx, int N, int C,
-              int64_t M, int64_t total, int clamp, float *__restrict__ out, int *__restrict__ err)
+gather_kernel(const float *__restrict__ points, const int64_t *__restrict__ idx, int N, int C, FastDiv dCV,
+              FastDiv dM, unsigned total, int clamp, float *__restrict__ out, int *__restrict__ err)
 {
-    const int CV = C / VEC;
-    for (int64_t t = (int64_t)blockIdx.x * kThreads + threadIdx.x; t < total; t += (int64_t)gridDim.x * kThreads) {
-        const int64_t rowg = t / CV;                   // b * M + m
-        const int c = (int)(t - rowg * CV) * VEC;
-        const int64_t b = rowg / M;
-        long long i = idx[rowg];
-        const bool ok = resolve_index(i, N, clamp);
-        if (VEC == 4) {
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (ok) v = __ldg(reinterpret_cast<const float4 *>(points + ((size_t)b * N + i) * C + c));
-            st_stream_f4(reinterpret_cast<float4 *>(out + (size_t)rowg * C + c), v);
-        } else {
-            float v = ok ? __ldg(points + ((size_t)b * N + i) * C + c) : 0.f;
-            st_stream_f1(out + (size_t)rowg * C + c, v);
-        }
-        if (!ok && err && c == 0) atomicAdd(err, 1);
+    const unsigned t = blockIdx.x * kThreads + threadIdx.x;
+    if (t >= total) return;
+    const unsigned rowg = dCV.div(t);                  // b * M + m
+    const int c = (int)(t - rowg * dCV.d) * VEC;
+    const unsigned b = dM.div(rowg);
+    long long i = idx[rowg];
+    const bool ok = resolve_index(i, N, clamp);
+    if (VEC == 4) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ok) v = __ldg(reinterpret_cast<const float4 *>(points + ((size_t)b * N + i) * C + c));
+        st_stream_f4(reinterpret_cast<float4 *>(out + (size_t)rowg * C + c), v);
+    } else {
+        float v = ok ? __ldg(points + ((size_t)b * N + i) * C + c) : 0.f;
+        st_stream_f1(out + (size_t)rowg * C + c, v);
     }
+    if (!ok && err && c == 0) atomicAdd(err, 1);
 }
 
 template <int VEC>
 __global__ void __launch_bounds__(kThreads)
-gather_bwd_kernel(const float *__restrict__ gout, const int64_t *__restrict__ idx, int N, int C,
-                  int64_t M, int64_t total, int clamp, float *__restrict__ gpoints)
+gather_bwd_kernel(const float *__restrict__ gout, const int64_t *__restrict__ idx, int N, int C, FastDiv dCV,
+                  FastDiv dM, unsigned total, int clamp, float *__restrict__ gpoints)
 {
-    const int CV = C / VEC;
-    for (int64_t t = (int64_t)blockIdx.x * kThreads + threadIdx.x; t < total; t += (int64_t)gridDim.x * kThreads) {
-        const int64_t rowg = t / CV;
-        const int c = (int)(t - rowg * CV) * VEC;
-        const int64_t b = rowg / M;
-        long long i = idx[rowg];
-        if (!resolve_index(i, N, clamp)) continue;
-        float *dst = gpoints + ((size_t)b * N + i) * C + c;
-        if (VEC == 4) {
-            float4 g = ld_stream_f4(reinterpret_cast<const float4 *>(gout + (size_t)rowg * C + c));
-            atomicAdd(reinterpret_cast<float4 *>(dst), g);
-        } else {
-            atomicAdd(dst, __ldg(gout + (size_t)rowg * C + c));
-        }
+    const unsigned t = blockIdx.x * kThreads + threadIdx.x;
+    if (t >= total) return;
+    const unsigned rowg = dCV.div(t);
+    const int c = (int)(t - rowg * dCV.d) * VEC;
+    const unsigned b = dM.div(rowg);
+    long long i = idx[rowg];
+    if (!resolve_index(i, N, clamp)) return;
+    float *dst = gpoints + ((size_t)b * N + i) * C + c;
+    if (VEC == 4) {
+        float4 g = ld_stream_f4(reinterpret_cast<const float4 *>(gout + (size_t)rowg * C + c));
+        atomicAdd(reinterpret_cast<float4 *>(dst), g);
+    } else {
+        atomicAdd(dst, __ldg(gout + (size_t)rowg * C + c));
     }
 }
 
@@ -79,94 +95,109 @@ gather_bwd_kernel(const float *__restrict__ gout, const int64_t *__restrict__ id
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads)
 group_points_kernel(const float *__restrict__ xyz, const float *__restrict__ points,
-                    const float *__restrict__ new_xyz, const int64_t *__restrict__ idx, int N, int S, int K,
-                    int D, int xyz_first, int points_cf, int clamp, int64_t total, float *__restrict__ out)
+                    const float *__restrict__ new_xyz, const int64_t *__restrict__ idx, int N, int D, FastDiv dC,
+                    FastDiv dK, FastDiv dS, int xyz_first, int points_cf, int clamp, unsigned total,
+                    float *__restrict__ out)
 {
-    const int C = 3 + D;
-    for (int64_t t = (int64_t)blockIdx.x * kThreads + threadIdx.x; t < total; t += (int64_t)gridDim.x * kThreads) {
-        const int64_t rowg = t / C;                    // (b*S + s)*K + k
-        const int c = (int)(t - rowg * C);
-        const int64_t bs = rowg / K;                   // b*S + s
-        const int64_t b = bs / S;
-        long long i = idx[rowg];
-        const bool ok = resolve_index(i, N, clamp);
-        const int cx = xyz_first ? c : c - D;          // coordinate channel if in [0,3)
-        float v = 0.f;
-        if (ok) {
-            if (cx >= 0 && cx < 3) {
-                v = __fsub_rn(__ldg(xyz + ((size_t)b * N + i) * 3 + cx), __ldg(new_xyz + (size_t)bs * 3 + cx));
-            } else {
-                const int cf = xyz_first ? c - 3 : c;
-                v = points_cf ? __ldg(points + ((size_t)b * D + cf) * N + i)
-                              : __ldg(points + ((size_t)b * N + i) * D + cf);
-            }
+    const unsigned t = blockIdx.x * kThreads + threadIdx.x;
+    if (t >= total) return;
+    const unsigned rowg = dC.div(t);                   // (b*S + s)*K + k
+    const int c = (int)(t - rowg * dC.d);
+    const unsigned bs = dK.div(rowg);                  // b*S + s
+    const unsigned b = dS.div(bs);
+    long long i = idx[rowg];
+    const bool ok = resolve_index(i, N, clamp);
+    const int cx = xyz_first ? c : c - D;              // coordinate channel if in [0,3)
+    float v = 0.f;
+    if (ok) {
+        if (cx >= 0 && cx < 3) {
+            v = __fsub_rn(__ldg(xyz + ((size_t)b * N + i) * 3 + cx), __ldg(new_xyz + (size_t)bs * 3 + cx));
+        } else {
+            const int cf = xyz_first ? c - 3 : c;
+            v = points_cf ? __ldg(points + ((size_t)b * D + cf) * N + i)
+                          : __ldg(points + ((size_t)b * N + i) * D + cf);
         }
-        st_stream_f1(out + t, v);
     }
+    st_stream_f1(out + t, v);
 }
 
 __global__ void __launch_bounds__(kThreads)
-group_points_bwd_kernel(const float *__restrict__ gout, const int64_t *__restrict__ idx, int N, int S, int K,
-                        int D, int xyz_first, int points_cf, int clamp, int64_t total,
+group_points_bwd_kernel(const float *__restrict__ gout, const int64_t *__restrict__ idx, int N, int D, FastDiv dD,
+                        FastDiv dSK, int xyz_first, int points_cf, int clamp, unsigned total,
                         float *__restrict__ gpoints)
 {
     const int C = 3 + D;
     // one thread per (row, feature channel)
-    for (int64_t t = (int64_t)blockIdx.x * kThreads + threadIdx.x; t < total; t += (int64_t)gridDim.x * kThreads) {
-        const int64_t rowg = t / D;
-        const int cf = (int)(t - rowg * D);
-        const int64_t b = rowg / ((int64_t)S * K);
-        long long i = idx[rowg];
-        if (!resolve_index(i, N, clamp)) continue;
-        const float g = __ldg(gout + (size_t)rowg * C + (xyz_first ? 3 + cf : cf));
-        float *dst = points_cf ? gpoints + ((size_t)b * D + cf) * N + i : gpoints + ((size_t)b * N + i) * D + cf;
-        atomicAdd(dst, g);
-    }
+    const unsigned t = blockIdx.x * kThreads + threadIdx.x;
+    if (t >= total) return;
+    const unsigned rowg = dD.div(t);
+    const int cf = (int)(t - rowg * dD.d);
+    const unsigned b = dSK.div(rowg);
+    long long i = idx[rowg];
+    if (!resolve_index(i, N, clamp)) return;
+    const float g = __ldg(gout + (size_t)rowg * C + (xyz_first ? 3 + cf : cf));
+    float *dst = points_cf ? gpoints + ((size_t)b * D + cf) * N + i : gpoints + ((size_t)b * N + i) * D + cf;
+    atomicAdd(dst, g);
 }
 
 // ------------------------------------------------------------------------------------------
 // get_graph_feature.  x [B,D,N], idx [B,N,k] -> out [B,2D,N,k].
-// A thread owns one (n, j) edge and walks CPT channels: the index is read once per CPT
-// channels, stores are coalesced along (n, j), gathers hit one 4*N-byte row per channel.
+// A thread owns EPT consecutive (n, j) edges and walks CPT channels: indices are read once per
+// CPT channels, both output planes get 128-bit streaming stores, gathers hit one 4*N-byte
+// row of x per channel (L1/L2 resident).
 // ------------------------------------------------------------------------------------------
 constexpr int kGfCPT = 8;
 
+template <int EPT>
 __global__ void __launch_bounds__(kThreads)
-graph_feature_kernel(const float *__restrict__ x, const int64_t *__restrict__ idx, int D, int N, int k,
-                     float *__restrict__ out)
+graph_feature_kernel(const float *__restrict__ x, const int64_t *__restrict__ idx, int D, int N, FastDiv dk,
+                     unsigned NK, float *__restrict__ out)
 {
     const int b = blockIdx.z;
     const int c0 = blockIdx.y * kGfCPT;
-    const int64_t NK = (int64_t)N * k;
-    const int64_t e = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    const unsigned e = (blockIdx.x * kThreads + threadIdx.x) * EPT;
     if (e >= NK) return;
-    const int n = (int)(e / k);
-    long long nb = idx[(size_t)b * NK + e];
-    nb = nb < 0 ? 0 : (nb > N - 1 ? N - 1 : nb);
+    int n[EPT], nb[EPT];
+#pragma unroll
+    for (int u = 0; u < EPT; ++u) {
+        n[u] = (int)dk.div(e + u);
+        long long v = idx[(size_t)b * NK + e + u];
+        nb[u] = (int)(v < 0 ? 0 : (v > N - 1 ? N - 1 : v));
+    }
 #pragma unroll
     for (int cc = 0; cc < kGfCPT; ++cc) {
         const int c = c0 + cc;
         if (c < D) {
             const float *row = x + ((size_t)b * D + c) * N;
-            const float ctr = __ldg(row + n);
-            const float nbr = __ldg(row + nb);
-            st_stream_f1(out + ((size_t)b * 2 * D + c) * NK + e, __fsub_rn(nbr, ctr));
-            st_stream_f1(out + ((size_t)b * 2 * D + D + c) * NK + e, ctr);
+            float ctr[EPT], dif[EPT];
+#pragma unroll
+            for (int u = 0; u < EPT; ++u) {
+                ctr[u] = __ldg(row + n[u]);
+                dif[u] = __fsub_rn(__ldg(row + nb[u]), ctr[u]);
+            }
+            float *o1 = out + ((size_t)b * 2 * D + c) * NK + e;
+            float *o2 = out + ((size_t)b * 2 * D + D + c) * NK + e;
+            if (EPT == 4) {
+                st_stream_f4(reinterpret_cast<float4 *>(o1), make_float4(dif[0], dif[1], dif[2], dif[3]));
+                st_stream_f4(reinterpret_cast<float4 *>(o2), make_float4(ctr[0], ctr[1], ctr[2], ctr[3]));
+            } else {
+                st_stream_f1(o1, dif[0]);
+                st_stream_f1(o2, ctr[0]);
+            }
         }
     }
 }
 
 // grad_x[b,c,n] += sum_j g2[b,c,n,j] - sum_j g1[b,c,n,j];  grad_x[b,c,idx[n,j]] += g1[b,c,n,j]
 __global__ void __launch_bounds__(kThreads)
-graph_feature_bwd_kernel(const float *__restrict__ gout, const int64_t *__restrict__ idx, int D, int N, int k,
-                         float *__restrict__ gx)
+graph_feature_bwd_kernel(const float *__restrict__ gout, const int64_t *__restrict__ idx, int D, int N, FastDiv dk,
+                         unsigned NK, float *__restrict__ gx)
 {
     const int b = blockIdx.z;
     const int c0 = blockIdx.y * kGfCPT;
-    const int64_t NK = (int64_t)N * k;
-    const int64_t e = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    const unsigned e = blockIdx.x * kThreads + threadIdx.x;
     if (e >= NK) return;
-    const int n = (int)(e / k);
+    const int n = (int)dk.div(e);
     long long nb = idx[(size_t)b * NK + e];
     nb = nb < 0 ? 0 : (nb > N - 1 ? N - 1 : nb);
 #pragma unroll
@@ -189,37 +220,36 @@ graph_feature_bwd_kernel(const float *__restrict__ gout, const int64_t *__restri
 template <int VEC>
 __global__ void __launch_bounds__(kThreads)
 interp_rows_kernel(const float *__restrict__ p2, const int64_t *__restrict__ idx, const float *__restrict__ w,
-                   int N, int S, int D, int k, int64_t total, float *__restrict__ out)
+                   int S, int D, int k, FastDiv dDV, FastDiv dN, unsigned total, float *__restrict__ out)
 {
-    const int DV = D / VEC;
-    for (int64_t t = (int64_t)blockIdx.x * kThreads + threadIdx.x; t < total; t += (int64_t)gridDim.x * kThreads) {
-        const int64_t rowg = t / DV;                   // b*N + n
-        const int c = (int)(t - rowg * DV) * VEC;
-        const int64_t b = rowg / N;
-        float acc[VEC];
+    const unsigned t = blockIdx.x * kThreads + threadIdx.x;
+    if (t >= total) return;
+    const unsigned rowg = dDV.div(t);                  // b*N + n
+    const int c = (int)(t - rowg * dDV.d) * VEC;
+    const unsigned b = dN.div(rowg);
+    float acc[VEC];
 #pragma unroll
-        for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
-        for (int j = 0; j < k; ++j) {
-            long long i = idx[rowg * k + j];
-            i = i < 0 ? 0 : (i > S - 1 ? S - 1 : i);
-            const float wj = __ldg(w + rowg * k + j);
-            const float *src = p2 + ((size_t)b * S + i) * D + c;
-            if (VEC == 4) {
-                float4 f = __ldg(reinterpret_cast<const float4 *>(src));
-                float pr[4] = {__fmul_rn(f.x, wj), __fmul_rn(f.y, wj), __fmul_rn(f.z, wj), __fmul_rn(f.w, wj)};
+    for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
+    for (int j = 0; j < k; ++j) {
+        long long i = idx[(size_t)rowg * k + j];
+        i = i < 0 ? 0 : (i > S - 1 ? S - 1 : i);
+        const float wj = __ldg(w + (size_t)rowg * k + j);
+        const float *src = p2 + ((size_t)b * S + i) * D + c;
+        if (VEC == 4) {
+            float4 f = __ldg(reinterpret_cast<const float4 *>(src));
+            float pr[4] = {__fmul_rn(f.x, wj), __fmul_rn(f.y, wj), __fmul_rn(f.z, wj), __fmul_rn(f.w, wj)};
 #pragma unroll
-                for (int v = 0; v < 4; ++v) acc[v] = j == 0 ? pr[v] : __fadd_rn(acc[v], pr[v]);
-            } else {
-                float pr = __fmul_rn(__ldg(src), wj);
-                acc[0] = j == 0 ? pr : __fadd_rn(acc[0], pr);
-            }
+            for (int v = 0; v < 4; ++v) acc[v] = j == 0 ? pr[v] : __fadd_rn(acc[v], pr[v]);
+        } else {
+            float pr = __fmul_rn(__ldg(src), wj);
+            acc[0] = j == 0 ? pr : __fadd_rn(acc[0], pr);
         }
-        if (VEC == 4)
-            st_stream_f4(reinterpret_cast<float4 *>(out + (size_t)rowg * D + c),
-                         make_float4(acc[0], acc[1], acc[2], acc[3]));
-        else
-            st_stream_f1(out + (size_t)rowg * D + c, acc[0]);
     }
+    if (VEC == 4)
+        st_stream_f4(reinterpret_cast<float4 *>(out + (size_t)rowg * D + c),
+                     make_float4(acc[0], acc[1], acc[2], acc[3]));
+    else
+        st_stream_f1(out + (size_t)rowg * D + c, acc[0]);
 }
 
 // channels-first: p2 [B,D,S] -> out [B,D,N]; a thread owns one n and walks CPT channels
@@ -262,33 +292,28 @@ interp_cf_kernel(const float *__restrict__ p2, const int64_t *__restrict__ idx, 
     }
 }
 
+// backward, one thread per element of gout in its own layout (coalesced read), k atomics each.
+// cf == 0: gout [B,N,D] (inner = D, mid = N); cf != 0: gout [B,D,N] (inner = N, mid = D).
 __global__ void __launch_bounds__(kThreads)
 interp_bwd_kernel(const float *__restrict__ gout, const int64_t *__restrict__ idx, const float *__restrict__ w,
-                  int N, int S, int D, int k, int cf, int64_t total, float *__restrict__ gp2)
+                  int N, int S, int D, int k, int cf, FastDiv dInner, FastDiv dMid, unsigned total,
+                  float *__restrict__ gp2)
 {
-    // one thread per (b, n, c) in the layout of gout (coalesced read), k atomics each
-    for (int64_t t = (int64_t)blockIdx.x * kThreads + threadIdx.x; t < total; t += (int64_t)gridDim.x * kThreads) {
-        int64_t b, n;
-        int c;
-        if (cf) {                                       // gout [B,D,N]
-            n = t % N;
-            int64_t bc = t / N;
-            c = (int)(bc % D);
-            b = bc / D;
-        } else {                                        // gout [B,N,D]
-            c = (int)(t % D);
-            int64_t bn = t / D;
-            n = bn % N;
-            b = bn / N;
-        }
-        const float g = __ldg(gout + t);
-        for (int j = 0; j < k; ++j) {
-            long long i = idx[((size_t)b * N + n) * k + j];
-            i = i < 0 ? 0 : (i > S - 1 ? S - 1 : i);
-            const float wj = __ldg(w + ((size_t)b * N + n) * k + j);
-            float *dst = cf ? gp2 + ((size_t)b * D + c) * S + i : gp2 + ((size_t)b * S + i) * D + c;
-            atomicAdd(dst, g * wj);
-        }
+    const unsigned t = blockIdx.x * kThreads + threadIdx.x;
+    if (t >= total) return;
+    const unsigned outer = dInner.div(t);
+    const unsigned inner = t - outer * dInner.d;
+    const unsigned b = dMid.div(outer);
+    const unsigned mid = outer - b * dMid.d;
+    const unsigned n = cf ? inner : mid;
+    const unsigned c = cf ? mid : inner;
+    const float g = __ldg(gout + t);
+    for (int j = 0; j < k; ++j) {
+        long long i = idx[((size_t)b * N + n) * k + j];
+        i = i < 0 ? 0 : (i > S - 1 ? S - 1 : i);
+        const float wj = __ldg(w + ((size_t)b * N + n) * k + j);
+        float *dst = cf ? gp2 + ((size_t)b * D + c) * S + i : gp2 + ((size_t)b * S + i) * D + c;
+        atomicAdd(dst, g * wj);
     }
 }
 
@@ -328,14 +353,19 @@ square_distance_kernel(const float *__restrict__ src, const float *__restrict__ 
     }
 }
 
-static inline unsigned grid_for(int64_t total)
-{
-    int64_t blocks = ceil_div(total, kThreads);
-    int64_t cap = (int64_t)PCB_NUM_SMS * 32;           // grid-stride beyond 32 CTAs per SM
-    return (unsigned)(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
-}
+static inline unsigned blocks_for(int64_t total) { return (unsigned)ceil_div(total, kThreads); }
 
 static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// Largest number of clouds per launch such that per-launch element counts stay below 2^31
+// (32-bit index arithmetic in the kernels); 0 if a single cloud is already too large.
+static inline int clouds_per_launch(int B, int64_t elems_per_cloud)
+{
+    const int64_t lim = (1ll << 31) - 1;
+    if (elems_per_cloud <= 0 || elems_per_cloud > lim) return 0;
+    int64_t n = lim / elems_per_cloud;
+    return (int)(n < B ? n : B);
+}
 
 int row_sumsq_launch(const float *x, int64_t rows, int C, int64_t row_stride, int elem_stride,
                      int64_t rows_per_batch, int64_t batch_stride, float *out, cudaStream_t st)
@@ -355,12 +385,22 @@ PCB_API int pcb_gather_f32(const float *points, const int64_t *idx, int B, int N
     PCB_REQUIRE(points && idx && out, PCB_EINVAL);
     PCB_REQUIRE(B > 0 && N > 0 && C > 0 && M > 0, PCB_EINVAL);
     cudaStream_t st = (cudaStream_t)stream;
-    if (C % 4 == 0 && aligned16(points) && aligned16(out)) {
-        int64_t total = (int64_t)B * M * (C / 4);
-        gather_kernel<4><<<grid_for(total), kThreads, 0, st>>>(points, idx, N, C, M, total, clamp, out, err_count);
-    } else {
-        int64_t total = (int64_t)B * M * C;
-        gather_kernel<1><<<grid_for(total), kThreads, 0, st>>>(points, idx, N, C, M, total, clamp, out, err_count);
+    const bool vec = C % 4 == 0 && aligned16(points) && aligned16(out);
+    const int CV = vec ? C / 4 : C;
+    const int step = clouds_per_launch(B, M * (int64_t)C);
+    PCB_REQUIRE(step > 0, PCB_ERANGE);
+    for (int b0 = 0; b0 < B; b0 += step) {
+        const int nb = B - b0 < step ? B - b0 : step;
+        const unsigned total = (unsigned)((int64_t)nb * M * CV);
+        const float *p = points + (size_t)b0 * N * C;
+        const int64_t *ix = idx + (size_t)b0 * M;
+        float *o = out + (size_t)b0 * M * C;
+        if (vec)
+            gather_kernel<4><<<blocks_for(total), kThreads, 0, st>>>(p, ix, N, C, make_fastdiv(CV), make_fastdiv((unsigned)M),
+                                                                    total, clamp, o, err_count);
+        else
+            gather_kernel<1><<<blocks_for(total), kThreads, 0, st>>>(p, ix, N, C, make_fastdiv(CV), make_fastdiv((unsigned)M),
+                                                                    total, clamp, o, err_count);
     }
     PCB_RETURN_LAUNCH_STATUS();
 }
@@ -371,12 +411,22 @@ PCB_API int pcb_gather_bwd_f32(const float *grad_out, const int64_t *idx, int B,
     PCB_REQUIRE(grad_out && idx && grad_points, PCB_EINVAL);
     PCB_REQUIRE(B > 0 && N > 0 && C > 0 && M > 0, PCB_EINVAL);
     cudaStream_t st = (cudaStream_t)stream;
-    if (C % 4 == 0 && aligned16(grad_out) && aligned16(grad_points)) {
-        int64_t total = (int64_t)B * M * (C / 4);
-        gather_bwd_kernel<4><<<grid_for(total), kThreads, 0, st>>>(grad_out, idx, N, C, M, total, clamp, grad_points);
-    } else {
-        int64_t total = (int64_t)B * M * C;
-        gather_bwd_kernel<1><<<grid_for(total), kThreads, 0, st>>>(grad_out, idx, N, C, M, total, clamp, grad_points);
+    const bool vec = C % 4 == 0 && aligned16(grad_out) && aligned16(grad_points);
+    const int CV = vec ? C / 4 : C;
+    const int step = clouds_per_launch(B, M * (int64_t)C);
+    PCB_REQUIRE(step > 0, PCB_ERANGE);
+    for (int b0 = 0; b0 < B; b0 += step) {
+        const int nb = B - b0 < step ? B - b0 : step;
+        const unsigned total = (unsigned)((int64_t)nb * M * CV);
+        const float *g = grad_out + (size_t)b0 * M * C;
+        const int64_t *ix = idx + (size_t)b0 * M;
+        float *gp = grad_points + (size_t)b0 * N * C;
+        if (vec)
+            gather_bwd_kernel<4><<<blocks_for(total), kThreads, 0, st>>>(g, ix, N, C, make_fastdiv(CV),
+                                                                        make_fastdiv((unsigned)M), total, clamp, gp);
+        else
+            gather_bwd_kernel<1><<<blocks_for(total), kThreads, 0, st>>>(g, ix, N, C, make_fastdiv(CV),
+                                                                        make_fastdiv((unsigned)M), total, clamp, gp);
     }
     PCB_RETURN_LAUNCH_STATUS();
 }
@@ -388,9 +438,17 @@ PCB_API int pcb_group_points_f32(const float *xyz, const float *points, const fl
     PCB_REQUIRE(xyz && new_xyz && idx && out, PCB_EINVAL);
     PCB_REQUIRE(B > 0 && N > 0 && S > 0 && K > 0 && D >= 0, PCB_EINVAL);
     PCB_REQUIRE(points || D == 0, PCB_EINVAL);
-    int64_t total = (int64_t)B * S * K * (3 + D);
-    group_points_kernel<<<grid_for(total), kThreads, 0, (cudaStream_t)stream>>>(
-        xyz, points, new_xyz, idx, N, S, K, D, xyz_first, points_cf, clamp, total, out);
+    const int C = 3 + D;
+    const int step = clouds_per_launch(B, (int64_t)S * K * C);
+    PCB_REQUIRE(step > 0, PCB_ERANGE);
+    for (int b0 = 0; b0 < B; b0 += step) {
+        const int nb = B - b0 < step ? B - b0 : step;
+        const unsigned total = (unsigned)((int64_t)nb * S * K * C);
+        group_points_kernel<<<blocks_for(total), kThreads, 0, (cudaStream_t)stream>>>(
+            xyz + (size_t)b0 * N * 3, points ? points + (size_t)b0 * N * D : nullptr, new_xyz + (size_t)b0 * S * 3,
+            idx + (size_t)b0 * S * K, N, D, make_fastdiv(C), make_fastdiv(K), make_fastdiv(S), xyz_first, points_cf,
+            clamp, total, out + (size_t)b0 * S * K * C);
+    }
     PCB_RETURN_LAUNCH_STATUS();
 }
 
@@ -400,9 +458,15 @@ PCB_API int pcb_group_points_bwd_f32(const float *grad_out, const int64_t *idx, 
 {
     PCB_REQUIRE(grad_out && idx && grad_points, PCB_EINVAL);
     PCB_REQUIRE(B > 0 && N > 0 && S > 0 && K > 0 && D > 0, PCB_EINVAL);
-    int64_t total = (int64_t)B * S * K * D;
-    group_points_bwd_kernel<<<grid_for(total), kThreads, 0, (cudaStream_t)stream>>>(
-        grad_out, idx, N, S, K, D, xyz_first, points_cf, clamp, total, grad_points);
+    const int step = clouds_per_launch(B, (int64_t)S * K * (3 + D));
+    PCB_REQUIRE(step > 0, PCB_ERANGE);
+    for (int b0 = 0; b0 < B; b0 += step) {
+        const int nb = B - b0 < step ? B - b0 : step;
+        const unsigned total = (unsigned)((int64_t)nb * S * K * D);
+        group_points_bwd_kernel<<<blocks_for(total), kThreads, 0, (cudaStream_t)stream>>>(
+            grad_out + (size_t)b0 * S * K * (3 + D), idx + (size_t)b0 * S * K, N, D, make_fastdiv(D),
+            make_fastdiv((unsigned)(S * K)), xyz_first, points_cf, clamp, total, grad_points + (size_t)b0 * N * D);
+    }
     PCB_RETURN_LAUNCH_STATUS();
 }
 
@@ -411,9 +475,15 @@ PCB_API int pcb_graph_feature_f32(const float *x, const int64_t *idx, int B, int
 {
     PCB_REQUIRE(x && idx && out, PCB_EINVAL);
     PCB_REQUIRE(B > 0 && D > 0 && N > 0 && k > 0, PCB_EINVAL);
-    PCB_REQUIRE(B <= 65535 && ceil_div(D, kGfCPT) <= 65535, PCB_ERANGE);
-    dim3 grid((unsigned)ceil_div((int64_t)N * k, kThreads), (unsigned)ceil_div(D, kGfCPT), (unsigned)B);
-    graph_feature_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(x, idx, D, N, k, out);
+    PCB_REQUIRE(B <= 65535 && ceil_div(D, kGfCPT) <= 65535 && (int64_t)N * k < (1ll << 31), PCB_ERANGE);
+    const unsigned NK = (unsigned)N * (unsigned)k;
+    if (NK % 4 == 0 && aligned16(out)) {
+        dim3 grid((unsigned)ceil_div(NK / 4, kThreads), (unsigned)ceil_div(D, kGfCPT), (unsigned)B);
+        graph_feature_kernel<4><<<grid, kThreads, 0, (cudaStream_t)stream>>>(x, idx, D, N, make_fastdiv(k), NK, out);
+    } else {
+        dim3 grid((unsigned)ceil_div(NK, kThreads), (unsigned)ceil_div(D, kGfCPT), (unsigned)B);
+        graph_feature_kernel<1><<<grid, kThreads, 0, (cudaStream_t)stream>>>(x, idx, D, N, make_fastdiv(k), NK, out);
+    }
     PCB_RETURN_LAUNCH_STATUS();
 }
 
@@ -422,9 +492,10 @@ PCB_API int pcb_graph_feature_bwd_f32(const float *grad_out, const int64_t *idx,
 {
     PCB_REQUIRE(grad_out && idx && grad_x, PCB_EINVAL);
     PCB_REQUIRE(B > 0 && D > 0 && N > 0 && k > 0, PCB_EINVAL);
-    PCB_REQUIRE(B <= 65535 && ceil_div(D, kGfCPT) <= 65535, PCB_ERANGE);
-    dim3 grid((unsigned)ceil_div((int64_t)N * k, kThreads), (unsigned)ceil_div(D, kGfCPT), (unsigned)B);
-    graph_feature_bwd_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(grad_out, idx, D, N, k, grad_x);
+    PCB_REQUIRE(B <= 65535 && ceil_div(D, kGfCPT) <= 65535 && (int64_t)N * k < (1ll << 31), PCB_ERANGE);
+    const unsigned NK = (unsigned)N * (unsigned)k;
+    dim3 grid((unsigned)ceil_div(NK, kThreads), (unsigned)ceil_div(D, kGfCPT), (unsigned)B);
+    graph_feature_bwd_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(grad_out, idx, D, N, make_fastdiv(k), NK, grad_x);
     PCB_RETURN_LAUNCH_STATUS();
 }
 
@@ -438,12 +509,25 @@ PCB_API int pcb_interpolate_f32(const float *points2, const int64_t *idx, const 
     if (channels_first) {
         dim3 grid((unsigned)ceil_div(N, kThreads), (unsigned)ceil_div(D, kIpCPT), (unsigned)B);
         interp_cf_kernel<<<grid, kThreads, 0, st>>>(points2, idx, weight, N, S, D, k, out);
-    } else if (D % 4 == 0 && aligned16(points2) && aligned16(out)) {
-        int64_t total = (int64_t)B * N * (D / 4);
-        interp_rows_kernel<4><<<grid_for(total), kThreads, 0, st>>>(points2, idx, weight, N, S, D, k, total, out);
-    } else {
-        int64_t total = (int64_t)B * N * D;
-        interp_rows_kernel<1><<<grid_for(total), kThreads, 0, st>>>(points2, idx, weight, N, S, D, k, total, out);
+        PCB_RETURN_LAUNCH_STATUS();
+    }
+    const bool vec = D % 4 == 0 && aligned16(points2) && aligned16(out);
+    const int DV = vec ? D / 4 : D;
+    const int step = clouds_per_launch(B, (int64_t)N * D);
+    PCB_REQUIRE(step > 0, PCB_ERANGE);
+    for (int b0 = 0; b0 < B; b0 += step) {
+        const int nb = B - b0 < step ? B - b0 : step;
+        const unsigned total = (unsigned)((int64_t)nb * N * DV);
+        const float *p = points2 + (size_t)b0 * S * D;
+        const int64_t *ix = idx + (size_t)b0 * N * k;
+        const float *w = weight + (size_t)b0 * N * k;
+        float *o = out + (size_t)b0 * N * D;
+        if (vec)
+            interp_rows_kernel<4><<<blocks_for(total), kThreads, 0, st>>>(p, ix, w, S, D, k, make_fastdiv(DV),
+                                                                         make_fastdiv(N), total, o);
+        else
+            interp_rows_kernel<1><<<blocks_for(total), kThreads, 0, st>>>(p, ix, w, S, D, k, make_fastdiv(DV),
+                                                                         make_fastdiv(N), total, o);
     }
     PCB_RETURN_LAUNCH_STATUS();
 }
@@ -454,9 +538,16 @@ PCB_API int pcb_interpolate_bwd_f32(const float *grad_out, const int64_t *idx, c
 {
     PCB_REQUIRE(grad_out && idx && weight && grad_points2, PCB_EINVAL);
     PCB_REQUIRE(B > 0 && N > 0 && S > 0 && D > 0 && k > 0, PCB_EINVAL);
-    int64_t total = (int64_t)B * N * D;
-    interp_bwd_kernel<<<grid_for(total), kThreads, 0, (cudaStream_t)stream>>>(grad_out, idx, weight, N, S, D, k,
-                                                                            channels_first, total, grad_points2);
+    const int step = clouds_per_launch(B, (int64_t)N * D);
+    PCB_REQUIRE(step > 0, PCB_ERANGE);
+    for (int b0 = 0; b0 < B; b0 += step) {
+        const int nb = B - b0 < step ? B - b0 : step;
+        const unsigned total = (unsigned)((int64_t)nb * N * D);
+        interp_bwd_kernel<<<blocks_for(total), kThreads, 0, (cudaStream_t)stream>>>(
+            grad_out + (size_t)b0 * N * D, idx + (size_t)b0 * N * k, weight + (size_t)b0 * N * k, N, S, D, k,
+            channels_first, make_fastdiv(channels_first ? N : D), make_fastdiv(channels_first ? D : N), total,
+            grad_points2 + (size_t)b0 * S * D);
+    }
     PCB_RETURN_LAUNCH_STATUS();
 }
 

@@ -120,169 +120,136 @@ static int launch_three_nn(const float *xyz1, const float *xyz2, int B, int N, i
 }
 
 // ------------------------------------------------------------------------------------------
-// kNN with k up to 64: one warp per query, sorted top list distributed over the lanes
-// (NPL entries per lane), threshold filter + ballot, warp-wide shuffle insertion.
+// kNN with k up to 64 in coordinate space: one THREAD per query.
+// Candidates are staged chunk by chunk in shared memory as float4 (x, y, z, |p|^2) and read by
+// broadcast; a thread tests 64 candidates against its running k-th distance (a register) into
+// a 64-bit mask, then drains the mask into its sorted top-K list, which lives in registers
+// (K = k rounded up to a compiled size; the first k entries of a top-K list are the top-k).  An
+// insertion is a branch-free compare-exchange pass.  Deferring the (rare, divergent) insertions
+// to the drain keeps the scan loop branch-free; the round-1 warp-per-query version spent most
+// of its issue slots in shuffle insertions (profiles/r1_*).
 // ------------------------------------------------------------------------------------------
 enum { MODE_PD = 0, MODE_CDIST = 1 };
 
-constexpr int kKnnWarps = 16;
-constexpr int kKnnChunk = 8192;              // 128 KB of float4
+constexpr int kKnnThreads = 128;
+constexpr int kKnnChunk = 1024;              // candidates per staging pass (16 KB)
 
-template <int NPL>
-struct WarpList {
-    float d[NPL];
-    int i[NPL];
-    __device__ __forceinline__ void init()
-    {
-#pragma unroll
-        for (int r = 0; r < NPL; ++r) {
-            d[r] = __int_as_float(0x7f800000);
-            i[r] = 0x7fffffff;
-        }
-    }
-    // value at list position pos (warp-uniform pos)
-    __device__ __forceinline__ float dist_at(int pos) const
-    {
-        float v = 0.f;
-#pragma unroll
-        for (int r = 0; r < NPL; ++r) {
-            float t = __shfl_sync(PCB_FULL_MASK, d[r], pos & 31);
-            if ((pos >> 5) == r) v = t;
-        }
-        return v;
-    }
-    // insert (v, vi) keeping (distance, index) ascending order; the last entry falls off
-    __device__ __forceinline__ void insert(float v, int vi, int lane)
-    {
-        float carry_d = 0.f;
-        int carry_i = 0;
-        bool carry_gt = false;
-#pragma unroll
-        for (int r = 0; r < NPL; ++r) {
-            const bool gt = (d[r] > v) || (d[r] == v && i[r] > vi);
-            float up_d = __shfl_up_sync(PCB_FULL_MASK, d[r], 1);
-            int up_i = __shfl_up_sync(PCB_FULL_MASK, i[r], 1);
-            bool up_gt = __shfl_up_sync(PCB_FULL_MASK, (int)gt, 1) != 0;
-            // what lane 31 of this register row hands to lane 0 of the next one
-            const float last_d = __shfl_sync(PCB_FULL_MASK, d[r], 31);
-            const int last_i = __shfl_sync(PCB_FULL_MASK, i[r], 31);
-            const bool last_gt = __shfl_sync(PCB_FULL_MASK, (int)gt, 31) != 0;
-            if (lane == 0) {
-                up_d = carry_d;
-                up_i = carry_i;
-                up_gt = (r == 0) ? false : carry_gt;
-            }
-            if (gt) {
-                d[r] = up_gt ? up_d : v;
-                i[r] = up_gt ? up_i : vi;
-            }
-            carry_d = last_d;
-            carry_i = last_i;
-            carry_gt = last_gt;
-        }
-    }
-};
-
-template <int MODE, int NPL>
-__global__ void __launch_bounds__(kKnnWarps * 32)
-knn_xyz_kernel(const float *__restrict__ xyz, int N, int k, int qpw,
-               int64_t *__restrict__ out_idx, float *__restrict__ out_dist, int chunk, int cf)
+template <int MODE>
+__device__ __forceinline__ float knn_pair(float qx, float qy, float qz, float qn, float ax, float ay, float az,
+                                          const float4 p)
 {
-    extern __shared__ __align__(16) float4 s_pts[];
-    const int b = blockIdx.y;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const float *cloud = xyz + (size_t)b * N * 3;
-    const int nchunks = (N + chunk - 1) / chunk;
-    const int q_begin = blockIdx.x * (kKnnWarps * qpw);
+    if (MODE == MODE_PD) return sqdist3(qx, qy, qz, qn, p.x, p.y, p.z, p.w);
+    float t = cdist3_pre(ax, ay, az, qn, p.x, p.y, p.z, p.w);
+    t = t < 0.0f ? 0.0f : t;                 // clamp_min_(0)
+    return __fsqrt_rn(t);
+}
 
-    for (int pass = 0; pass < qpw; ++pass) {
-        const int q = q_begin + pass * kKnnWarps + warp;
-        const bool active = q < N;                       // warp-uniform
-        float qx = 0.f, qy = 0.f, qz = 0.f, qn = 0.f;
-        if (active) {
-            float3 v = load_point(cloud, q, N, cf);
-            qx = v.x, qy = v.y, qz = v.z;
-            qn = norm3(qx, qy, qz);
-        }
-        float ax = qx, ay = qy, az = qz;
-        if (MODE == MODE_CDIST) {                        // x1_ = cat(-2 * x1, |x1|^2, 1)
-            ax = __fmul_rn(qx, -2.0f);
-            ay = __fmul_rn(qy, -2.0f);
-            az = __fmul_rn(qz, -2.0f);
-        }
-        WarpList<NPL> list;
-        list.init();
-        float thr = __int_as_float(0x7f800000);
-        for (int c = 0; c < nchunks; ++c) {
-            const int c0 = c * chunk;
-            const int len = min(chunk, N - c0);
-            if (nchunks > 1 || pass == 0) {
-                if (c > 0 || pass > 0) __syncthreads();
-                stage_points(s_pts, cloud, c0, len, N, cf);
-                __syncthreads();
-            }
-            if (!active) continue;
-            for (int base = 0; base < len; base += 32) {
-                const int j = base + lane;
-                float d = __int_as_float(0x7f800000);
-                if (j < len) {
-                    float4 p = s_pts[j];
-                    if (MODE == MODE_PD) {
-                        d = sqdist3(qx, qy, qz, qn, p.x, p.y, p.z, p.w);
-                    } else {
-                        float t = cdist3_pre(ax, ay, az, qn, p.x, p.y, p.z, p.w);
-                        t = t < 0.0f ? 0.0f : t;             // clamp_min_(0)
-                        d = __fsqrt_rn(t);
-                    }
-                }
-                unsigned m = __ballot_sync(PCB_FULL_MASK, d < thr);
-                while (m) {
-                    const int src = __ffs(m) - 1;
-                    m &= m - 1;
-                    const float v = __shfl_sync(PCB_FULL_MASK, d, src);
-                    if (v < thr) {                           // thr may have dropped within this batch
-                        list.insert(v, c0 + base + src, lane);
-                        thr = list.dist_at(k - 1);
-                    }
-                }
-            }
-        }
-        if (active) {
+template <int MODE, int K>
+__global__ void __launch_bounds__(kKnnThreads, (K <= 20 ? 4 : (K <= 32 ? 3 : 2)))
+knn_xyz_kernel(const float *__restrict__ xyz, int N, int k, int64_t *__restrict__ out_idx,
+               float *__restrict__ out_dist, int cf)
+{
+    __shared__ __align__(16) float4 s_pts[kKnnChunk];  // candidates of the current chunk
+    const int b = blockIdx.y, tid = threadIdx.x;
+    const int q = blockIdx.x * kKnnThreads + tid;
+    const bool active = q < N;
+    const float *cloud = xyz + (size_t)b * N * 3;
+
+    float qx = 0.f, qy = 0.f, qz = 0.f, qn = 0.f;
+    if (active) {
+        float3 v = load_point(cloud, q, N, cf);
+        qx = v.x, qy = v.y, qz = v.z;
+        qn = norm3(qx, qy, qz);
+    }
+    float ax = qx, ay = qy, az = qz;
+    if (MODE == MODE_CDIST) {                          // x1_ = cat(-2 * x1, |x1|^2, 1)
+        ax = __fmul_rn(qx, -2.0f);
+        ay = __fmul_rn(qy, -2.0f);
+        az = __fmul_rn(qz, -2.0f);
+    }
+    float ld[K];
+    int li[K];
 #pragma unroll
-            for (int r = 0; r < NPL; ++r) {
-                const int pos = r * 32 + lane;
-                if (pos < k) {
-                    out_idx[((size_t)b * N + q) * k + pos] = (int64_t)list.i[r];
-                    if (out_dist) out_dist[((size_t)b * N + q) * k + pos] = list.d[r];
+    for (int p = 0; p < K; ++p) {
+        ld[p] = __int_as_float(0x7f800000);
+        li[p] = 0x7fffffff;
+    }
+    float thr = __int_as_float(0x7f800000);                // K-th smallest distance so far
+    const float4 pad = make_float4(0.f, 0.f, 0.f, __int_as_float(0x7f800000));   // distance = +inf
+
+    for (int c0 = 0; c0 < N; c0 += kKnnChunk) {
+        const int len = min(kKnnChunk, N - c0);
+        const int len64 = (len + 63) & ~63;
+        if (c0 > 0) __syncthreads();
+        stage_points(s_pts, cloud, c0, len, N, cf);
+        for (int i = len + tid; i < len64; i += blockDim.x) s_pts[i] = pad;
+        __syncthreads();
+        if (!active) continue;
+        for (int s0 = 0; s0 < len64; s0 += 64) {
+            unsigned lo = 0u, hi = 0u;
+#pragma unroll
+            for (int c = 0; c < 32; ++c)
+                if (knn_pair<MODE>(qx, qy, qz, qn, ax, ay, az, s_pts[s0 + c]) < thr) lo |= 1u << c;
+#pragma unroll
+            for (int c = 0; c < 32; ++c)
+                if (knn_pair<MODE>(qx, qy, qz, qn, ax, ay, az, s_pts[s0 + 32 + c]) < thr) hi |= 1u << c;
+            unsigned long long mask = ((unsigned long long)hi << 32) | lo;
+            while (mask) {
+                const int c = __ffsll((long long)mask) - 1;           // ascending candidate index
+                mask &= mask - 1;
+                const float v = knn_pair<MODE>(qx, qy, qz, qn, ax, ay, az, s_pts[s0 + c]);
+                if (v < thr) {
+                    float cv = v;
+                    int ci = c0 + s0 + c;
+                    bool placed = false;
+#pragma unroll
+                    for (int p = 0; p < K; ++p) {                      // compare-exchange down the list
+                        // new element: strict < (equal distance -> the earlier index stays first);
+                        // once it is placed we carry old entries, which simply shift down one slot
+                        const bool sw = placed || (cv < ld[p]);
+                        placed = sw;
+                        const float nd = sw ? cv : ld[p], nc = sw ? ld[p] : cv;
+                        const int ni = sw ? ci : li[p], nci = sw ? li[p] : ci;
+                        ld[p] = nd;
+                        li[p] = ni;
+                        cv = nc;
+                        ci = nci;
+                    }
+                    thr = ld[K - 1];
                 }
             }
         }
     }
+    if (active) {
+        int64_t *oi = out_idx + ((size_t)b * N + q) * k;
+        float *od = out_dist ? out_dist + ((size_t)b * N + q) * k : nullptr;
+#pragma unroll
+        for (int p = 0; p < K; ++p) {
+            if (p < k) {
+                oi[p] = (int64_t)li[p];
+                if (od) od[p] = ld[p];
+            }
+        }
+    }
+}
+
+template <int MODE, int K>
+static int launch_knn_xyz_k(const float *xyz, int B, int N, int k, int cf, int64_t *oi, float *od, cudaStream_t st)
+{
+    dim3 grid((unsigned)ceil_div(N, kKnnThreads), (unsigned)B);
+    knn_xyz_kernel<MODE, K><<<grid, kKnnThreads, 0, st>>>(xyz, N, k, oi, od, cf);
+    PCB_RETURN_LAUNCH_STATUS();
 }
 
 template <int MODE>
 static int launch_knn_xyz(const float *xyz, int B, int N, int k, int cf, int64_t *oi, float *od,
                           cudaStream_t st)
 {
-    int chunk = N < kKnnChunk ? N : kKnnChunk;
-    size_t smem = (size_t)chunk * sizeof(float4);
-    // enough CTAs for >= 2 waves of 148 SMs, but amortise the staging over several queries per warp
-    int qpw = 8;
-    while (qpw > 1 && (int64_t)B * ceil_div(N, kKnnWarps * qpw) < 2 * PCB_NUM_SMS) qpw >>= 1;
-    dim3 grid((unsigned)ceil_div(N, kKnnWarps * qpw), (unsigned)B);
-    cudaError_t e;
-    if (k <= 32) {
-        e = cudaFuncSetAttribute(knn_xyz_kernel<MODE, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 kKnnChunk * (int)sizeof(float4));
-        if (e != cudaSuccess) return (int)e;
-        knn_xyz_kernel<MODE, 1><<<grid, kKnnWarps * 32, smem, st>>>(xyz, N, k, qpw, oi, od, chunk, cf);
-    } else {
-        e = cudaFuncSetAttribute(knn_xyz_kernel<MODE, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 kKnnChunk * (int)sizeof(float4));
-        if (e != cudaSuccess) return (int)e;
-        knn_xyz_kernel<MODE, 2><<<grid, kKnnWarps * 32, smem, st>>>(xyz, N, k, qpw, oi, od, chunk, cf);
-    }
-    PCB_RETURN_LAUNCH_STATUS();
+    if (k <= 8) return launch_knn_xyz_k<MODE, 8>(xyz, B, N, k, cf, oi, od, st);
+    if (k <= 16) return launch_knn_xyz_k<MODE, 16>(xyz, B, N, k, cf, oi, od, st);
+    if (k <= 20) return launch_knn_xyz_k<MODE, 20>(xyz, B, N, k, cf, oi, od, st);
+    if (k <= 32) return launch_knn_xyz_k<MODE, 32>(xyz, B, N, k, cf, oi, od, st);
+    return launch_knn_xyz_k<MODE, 64>(xyz, B, N, k, cf, oi, od, st);
 }
 
 int knn_xyz_pd(const float *xyz, int B, int N, int k, int cf, int64_t *oi, float *od, cudaStream_t st)
