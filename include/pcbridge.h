@@ -120,6 +120,29 @@ int pcb_graph_feature_f32(const float *x, const int64_t *idx, int B, int D, int 
 int pcb_graph_feature_bwd_f32(const float *grad_out, const int64_t *idx, int B, int D, int N, int k,
                               float *grad_x, pcb_stream_t stream);
 
+/* ---- a6/a11 (elementwise half)  BatchNorm(train) + ReLU (+ max over nsample) on point-major rows
+ *          pointnet_util.py:213-217, 273-279, 343-345; pointnet2_utils.py:150-154, 353-356
+ * Activations y [M,C] are fp32 (dtype 0) or bf16 (dtype 1); C % 4 == 0; statistics fp32.
+ * The 1x1-conv bias is NOT added to y: BN(y + b) == BN(y) for batch statistics, b only enters
+ * the running mean (pcb_bn_finalize) -- so no bias-add / bias-gradient pass exists.
+ *   pcb_bn_stats_rows : sums[0:C] = sum_r (y[r]-y[0]), sums[C:2C] = sum_r (y[r]-y[0])^2  (1 read of y)
+ *   pcb_bn_finalize   : mean/invstd [C] of y from the sums; running_mean/var update (may be NULL)
+ *   pcb_bn_apply_rows : out[r] = max_{k<pool_k} act((y[r*pool_k+k]-mean)*invstd*gamma+beta), argmax
+ *                       [Mout,C] uint8 (may be NULL when pool_k == 1)        (1 read of y, 1 write)
+ *   pcb_bn_bwd_rows   : sums[0:C] = sum dy, [C:2C] = sum dy*yhat, [2C:3C] = sum yhat, then
+ *                       gy = gamma*invstd*(dy - sum_dy/M - yhat*sum_dy_yhat/M); gz is [M/pool_k, C]
+ *                       (2 reads of gz and y, 1 write) */
+int pcb_bn_stats_rows(const void *y, int dtype, int64_t M, int C, float *sums, pcb_stream_t stream);
+int pcb_bn_finalize(const float *sums, const void *y, int dtype, const float *bias, int64_t M, int C, float eps,
+                    float momentum, float *running_mean, float *running_var, float *mean, float *invstd,
+                    pcb_stream_t stream);
+int pcb_bn_apply_rows(const void *y, int dtype, int64_t Mout, int C, int pool_k, const float *mean,
+                      const float *invstd, const float *gamma, const float *beta, int relu, void *out,
+                      unsigned char *argmax, pcb_stream_t stream);
+int pcb_bn_bwd_rows(const void *gz, const void *y, const unsigned char *argmax, int dtype, int64_t M, int C,
+                    int pool_k, const float *mean, const float *invstd, const float *gamma, const float *beta,
+                    int relu, float *sums, void *gy, pcb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

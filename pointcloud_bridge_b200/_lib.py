@@ -35,6 +35,10 @@ _SIGNATURES = {
     "pcb_knn_cdist_f32": [_vp, _i, _i, _i, _vp, _vp, _vp],
     "pcb_graph_feature_f32": [_vp, _vp, _i, _i, _i, _i, _vp, _vp],
     "pcb_graph_feature_bwd_f32": [_vp, _vp, _i, _i, _i, _i, _vp, _vp],
+    "pcb_bn_stats_rows": [_vp, _i, _i64, _i, _vp, _vp],
+    "pcb_bn_finalize": [_vp, _vp, _i, _vp, _i64, _i, _f, _f, _vp, _vp, _vp, _vp, _vp],
+    "pcb_bn_apply_rows": [_vp, _i, _i64, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp],
+    "pcb_bn_bwd_rows": [_vp, _vp, _vp, _i, _i64, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp],
 }
 
 EXPORTS = ["pcb_version", "pcb_error_string", *_SIGNATURES]

@@ -10,8 +10,49 @@ import torch
 import torch.nn.functional as F
 
 from . import distributed as pdist
+from . import ops
 
-__all__ = ["Trainer", "BlockInference"]
+__all__ = ["Trainer", "BlockInference", "FpsStartBuffers"]
+
+
+class FpsStartBuffers:
+    """Static device buffers for the FPS start indices of a captured step.
+
+    `discover` mode (one eager warm-up step) records the (B, N) of every farthest_point_sample
+    call while drawing normally; static LongTensors are then allocated OUTSIDE the capture (a
+    tensor created inside it would be re-initialised by the captured fill kernel on every
+    replay) and handed out in call order while the graph is recorded.  `refill()` repeats,
+    before each replay, exactly the draws the eager code would make -- `torch.randint(0, N, (B,))`
+    on the CPU default generator, in call order (pointnet_util.py:79) -- into pinned staging
+    memory and copies them over.  torch.manual_seed therefore reproduces the reference's samples
+    in graph mode too.
+    """
+
+    def __init__(self):
+        self.shapes = []           # (B, N) per call, from the discovery step
+        self.calls = []            # (N, device buffer, pinned staging buffer)
+        self.mode = "off"          # off | discover | record
+        self._next = 0
+
+    def provider(self, B, N, device):
+        if self.mode == "record":
+            n, buf, _ = self.calls[self._next]
+            assert n == N and buf.shape[0] == B, "captured step differs from the discovery step"
+            self._next += 1
+            return buf
+        if self.mode == "discover":
+            self.shapes.append((B, N, device))
+        return torch.randint(0, N, (B,), dtype=torch.long).to(device)
+
+    def allocate(self):
+        self.calls = [(N, torch.zeros(B, dtype=torch.long, device=dev), torch.zeros(B, dtype=torch.long).pin_memory())
+                      for (B, N, dev) in self.shapes]
+        self._next = 0
+
+    def refill(self):
+        for N, buf, stage in self.calls:
+            stage.copy_(torch.randint(0, N, (stage.shape[0],), dtype=torch.long))
+            buf.copy_(stage, non_blocking=True)
 
 
 class Trainer:
@@ -21,15 +62,22 @@ class Trainer:
     must be bit-exact); parameters, gradients and optimizer state stay fp32.
     """
 
-    def __init__(self, net, loss_fn=None, lr=1e-3, weight_decay=1e-4, amp=True):
+    def __init__(self, net, loss_fn=None, lr=1e-3, weight_decay=1e-4, amp=True, graph=False, capturable=None):
         self.net = net
         self.loss_fn = loss_fn
         self.amp = amp
+        self.graph = graph
         self.bucket = pdist.FlatGradBucket(net)
-        self.opt = torch.optim.Adam(self.bucket.params, lr=lr, weight_decay=weight_decay, fused=True)
+        self.opt = torch.optim.Adam(self.bucket.params, lr=lr, weight_decay=weight_decay, fused=True,
+                                    capturable=graph if capturable is None else capturable)
+        self._g = None                 # captured (zero, forward, loss, backward[, Adam]) graph
+        self._static = None
+        self._starts = FpsStartBuffers()
+        self._warm = 0
+        self._opt_in_graph = False
 
-    def step(self, *inputs, labels, loss_inputs=()):
-        """One optimisation step on this rank's batch; returns the (device) loss tensor."""
+    # -- eager pieces ---------------------------------------------------------------------
+    def _fwd_bwd(self, inputs, labels, loss_inputs):
         self.bucket.zero()
         with torch.autocast("cuda", dtype=torch.bfloat16, enabled=self.amp):
             out = self.net(*inputs)
@@ -39,9 +87,74 @@ class Trainer:
         else:
             loss = self.loss_fn(logits.float(), labels, *loss_inputs)
         loss.backward()
+        return loss.detach()
+
+    def _step_eager(self, inputs, labels, loss_inputs):
+        loss = self._fwd_bwd(inputs, labels, loss_inputs)
         self.bucket.allreduce_mean()
         self.opt.step()
-        return loss.detach()
+        return loss
+
+    # -- CUDA-graph path --------------------------------------------------------------------
+    def _capture(self, inputs, labels, loss_inputs):
+        """Capture one step with static input buffers.  With several ranks the NCCL all-reduce and
+        the optimizer stay outside the graph (zero + forward + loss + backward are captured)."""
+        self._static = ([t.clone() for t in inputs], labels.clone(), [t.clone() for t in loss_inputs])
+        self._opt_in_graph = not (pdist.is_dist() and torch.distributed.get_world_size() > 1)
+        self._starts.allocate()
+        ops.set_fps_start_provider(self._starts.provider)
+        self._starts.mode = "record"
+        self._g = torch.cuda.CUDAGraph()
+        from . import _lib
+        n0 = _lib.launches()
+        try:
+            with torch.cuda.graph(self._g):
+                loss = self._fwd_bwd(self._static[0], self._static[1], self._static[2])
+                if self._opt_in_graph:
+                    self.opt.step()
+            self._static_loss = loss
+            self.kernel_launches_per_replay = _lib.launches() - n0   # libpcbridge kernels inside the graph
+        finally:
+            self._starts.mode = "off"
+            ops.set_fps_start_provider(None)
+
+    def step(self, *inputs, labels, loss_inputs=()):
+        """One optimisation step on this rank's batch; returns the (device) loss tensor."""
+        if not self.graph:
+            return self._step_eager(inputs, labels, loss_inputs)
+        if self._warm < 3:                                  # eager warm-up steps on a side stream
+            self._warm += 1
+            discover = self._warm == 3                      # the last one also records the FPS call list
+            if discover:
+                self._starts.shapes = []
+                self._starts.mode = "discover"
+                ops.set_fps_start_provider(self._starts.provider)
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            try:
+                with torch.cuda.stream(s):
+                    loss = self._step_eager(inputs, labels, loss_inputs)
+            finally:
+                if discover:
+                    self._starts.mode = "off"
+                    ops.set_fps_start_provider(None)
+            torch.cuda.current_stream().wait_stream(s)
+            return loss
+        if self._g is None:
+            self._capture(inputs, labels, loss_inputs)
+        for dst, src in zip(self._static[0], inputs):
+            dst.copy_(src, non_blocking=True)
+        self._static[1].copy_(labels, non_blocking=True)
+        for dst, src in zip(self._static[2], loss_inputs):
+            dst.copy_(src, non_blocking=True)
+        self._starts.refill()
+        self._g.replay()
+        from . import _lib
+        _lib.count_launches(self.kernel_launches_per_replay)
+        if not self._opt_in_graph:
+            self.bucket.allreduce_mean()
+            self.opt.step()
+        return self._static_loss
 
 
 class BlockInference:

@@ -111,8 +111,8 @@ class SetAbstraction(nn.Module):
         pts = _rows(points) if points is not None else None
         new_xyz, grouped = sample_and_group(self.npoint, self.radius, self.nsample, xyz, pts)
         B, S, K, C = grouped.shape
-        y = mlp_rows(grouped.view(B * S * K, C), self.mlp_convs, self.mlp_bns)
-        return new_xyz, _cf_view(y.view(B * S, K, -1).max(dim=1)[0], B, S)
+        y = mlp_rows(grouped.view(B * S * K, C), self.mlp_convs, self.mlp_bns, pool_k=K)
+        return new_xyz, _cf_view(y, B, S)
 
 
 class MultiScaleSetAbstraction(nn.Module):
@@ -144,8 +144,7 @@ class MultiScaleSetAbstraction(nn.Module):
         for i, (radius, K) in enumerate(zip(self.radius_list, self.nsample_list)):
             idx = query_ball_point(radius, K, xyz, new_xyz)
             grouped = ops.group_points(xyz, pts, new_xyz, idx, xyz_first=True, clamp=True)
-            y = mlp_rows(grouped.view(B * S * K, -1), self.conv_blocks[i], self.bn_blocks[i])
-            outs.append(y.view(B * S, K, -1).max(dim=1)[0])
+            outs.append(mlp_rows(grouped.view(B * S * K, -1), self.conv_blocks[i], self.bn_blocks[i], pool_k=K))
         return new_xyz, _cf_view(torch.cat(outs, dim=1), B, S)
 
 

@@ -70,6 +70,18 @@ def _call(name: str, dev: torch.device, *args, launches: int = 1, alg_bytes: int
     _lib.count_launches(launches)
 
 
+# Source of the FPS start indices.  None: the reference's own draw, torch.randint on the CPU
+# default generator followed by a host->device copy (pointnet_util.py:79).  A callable
+# (B, N, device) -> LongTensor[B] lets a CUDA-graph runner substitute static device buffers that
+# it refills with that same CPU draw before every replay (engine.GraphedStep).
+_fps_start_provider = None
+
+
+def set_fps_start_provider(fn) -> None:
+    global _fps_start_provider
+    _fps_start_provider = fn
+
+
 def _err_counter(dev: torch.device) -> torch.Tensor:
     key = dev.index if dev.index is not None else torch.cuda.current_device()
     t = _err_counters.get(key)
@@ -104,7 +116,10 @@ def furthest_point_sample(xyz: torch.Tensor, npoint: int, start: torch.Tensor | 
     if C != 3:
         raise ValueError("farthest point sampling expects 3-D coordinates")
     if start is None:
-        start = torch.randint(0, N, (B,), dtype=torch.long).to(xyz.device)
+        if _fps_start_provider is not None:
+            start = _fps_start_provider(B, N, xyz.device)
+        else:
+            start = torch.randint(0, N, (B,), dtype=torch.long).to(xyz.device)
     start = _i64(start.to(xyz.device), "start")
     out = torch.empty(B, npoint, dtype=torch.long, device=xyz.device)
     _call("pcb_fps_f32", xyz.device, xyz.data_ptr(), B, N, start.data_ptr(), int(npoint), out.data_ptr(),
@@ -337,3 +352,80 @@ def three_interpolate(points2: torch.Tensor, idx: torch.Tensor, weight: torch.Te
     """sum_j weight[b,n,j] * points2[b, idx[b,n,j]]: points2 [B,S,D] -> [B,N,D], or with
     channels_first [B,D,S] -> [B,D,N]."""
     return _Interpolate.apply(points2, idx, weight, bool(channels_first))
+
+
+# ---------------------------------------------------------------------------------------------
+# BatchNorm (batch statistics) + ReLU (+ max over the neighbour axis) on point-major rows
+# ---------------------------------------------------------------------------------------------
+def _act_dtype(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return 0
+    if t.dtype == torch.bfloat16:
+        return 1
+    raise _lib.PcbError(f"bn_relu_rows supports fp32 / bf16 activations, got {t.dtype}")
+
+
+class _BnReluRows(torch.autograd.Function):
+    """z = max_k relu(BN_train(y + bias)) on rows.  y [M,C] is the bias-free GEMM output."""
+
+    @staticmethod
+    def forward(ctx, y, bias, gamma, beta, running_mean, running_var, momentum, eps, relu, pool_k):
+        if not y.is_contiguous():
+            y = y.contiguous()
+        M, C = y.shape
+        dt = _act_dtype(y)
+        dev = y.device
+        sums = torch.empty(3 * C, dtype=torch.float32, device=dev)
+        stats = torch.empty(2, C, dtype=torch.float32, device=dev)          # mean, invstd of bias-free y
+        mean, invstd = stats[0], stats[1]
+        _call("pcb_bn_stats_rows", dev, y.data_ptr(), dt, M, C, sums.data_ptr(), alg_bytes=y.numel() * y.element_size())
+        _call("pcb_bn_finalize", dev, sums.data_ptr(), y.data_ptr(), dt, bias.data_ptr() if bias is not None else None,
+              M, C, float(eps), float(momentum), running_mean.data_ptr() if running_mean is not None else None,
+              running_var.data_ptr() if running_var is not None else None, mean.data_ptr(), invstd.data_ptr(),
+              alg_bytes=12 * C)
+        Mout = M // pool_k
+        out = torch.empty(Mout, C, dtype=y.dtype, device=dev)
+        argmax = torch.empty(Mout, C, dtype=torch.uint8, device=dev) if pool_k > 1 else None
+        g32, b32 = gamma.float(), beta.float()
+        _call("pcb_bn_apply_rows", dev, y.data_ptr(), dt, Mout, C, int(pool_k), mean.data_ptr(), invstd.data_ptr(),
+              g32.data_ptr(), b32.data_ptr(), int(relu), out.data_ptr(),
+              argmax.data_ptr() if argmax is not None else None,
+              alg_bytes=(y.numel() + out.numel()) * y.element_size())
+        ctx.save_for_backward(y, stats, g32, b32, argmax, sums)
+        ctx.meta = (M, C, dt, int(relu), int(pool_k), bias is not None)
+        return out
+
+    @staticmethod
+    def backward(ctx, gz):
+        y, stats, g32, b32, argmax, sums = ctx.saved_tensors
+        M, C, dt, relu, pool_k, has_bias = ctx.meta
+        gz = gz.contiguous()
+        if gz.dtype != y.dtype:
+            gz = gz.to(y.dtype)
+        gy = torch.empty_like(y)
+        _call("pcb_bn_bwd_rows", y.device, gz.data_ptr(), y.data_ptr(), argmax.data_ptr() if argmax is not None else None,
+              dt, M, C, pool_k, stats[0].data_ptr(), stats[1].data_ptr(), g32.data_ptr(), b32.data_ptr(), relu,
+              sums.data_ptr(), gy.data_ptr(), launches=2,
+              alg_bytes=(3 * y.numel() + 2 * gz.numel()) * y.element_size())
+        s = sums.view(3, C)
+        ggamma, gbeta = s[1], s[0]
+        # d/d(bias) = sum_rows gy = -gamma * invstd * (sum yhat) * (sum dy*yhat) / M: zero up to rounding,
+        # as in the reference, where the bias of a conv that feeds a training-mode BN gets a noise gradient
+        gbias = (-(g32 * stats[1]) * s[2] * s[1] / M) if has_bias else None
+        return gy, gbias, ggamma, gbeta, None, None, None, None, None, None
+
+
+def bn_relu_rows(y, bias, bn, relu=True, pool_k=1):
+    """BatchNorm with batch statistics (+ReLU, + max over groups of `pool_k` consecutive rows) of
+    the bias-free GEMM output y [M,C]; updates bn's running statistics like nn.BatchNorm does."""
+    if bn.track_running_stats and bn.num_batches_tracked is not None:
+        bn.num_batches_tracked.add_(1)
+    rm = bn.running_mean if bn.track_running_stats else None
+    rv = bn.running_var if bn.track_running_stats else None
+    return _BnReluRows.apply(y, bias, bn.weight, bn.bias, rm, rv, bn.momentum, bn.eps, bool(relu), int(pool_k))
+
+
+def bn_rows_supported(y, bn, pool_k=1) -> bool:
+    return (y.is_cuda and y.dim() == 2 and y.shape[1] % 4 == 0 and y.dtype in (torch.float32, torch.bfloat16)
+            and bn.training and bn.momentum is not None and bn.affine and y.shape[0] % pool_k == 0
+            and y.shape[0] > 1 and pool_k <= 255 and y.numel() // 4 < 2 ** 31)

@@ -5,7 +5,7 @@ same parameter names, same [B,9,N] -> ([B,N,num_classes] log-probabilities, l4_p
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .pointnet_util import PointNetFeaturePropagation, PointNetSetAbstraction, _bn_rows, _rows
+from .pointnet_util import PointNetFeaturePropagation, PointNetSetAbstraction, _rows, conv_bn_relu_rows
 
 
 class get_model(nn.Module):
@@ -43,8 +43,7 @@ def _seg_head(net, feats_bcn):
     (pointnet2_sem_seg.py:43-47), evaluated on point-major rows."""
     x = _rows(feats_bcn)
     B, N, C = x.shape
-    x = F.linear(x.reshape(B * N, C), net.conv1.weight.flatten(1), net.conv1.bias)
-    x = net.drop1(F.relu(_bn_rows(net.bn1, x), inplace=True))
+    x = net.drop1(conv_bn_relu_rows(x.reshape(B * N, C), net.conv1, net.bn1))
     x = F.linear(x, net.conv2.weight.flatten(1), net.conv2.bias)
     return F.log_softmax(x.float(), dim=-1).view(B, N, -1)
 

@@ -111,11 +111,32 @@ def _bn_rows(bn, x):
                         use_batch, mom, bn.eps)
 
 
-def mlp_rows(x, convs, bns):
-    """x [M,Cin] -> [M,Cout]: (1x1 conv -> BN -> ReLU) per layer, as pointnet_util.py:213-215."""
-    for conv, bn in zip(convs, bns):
-        x = F.linear(x, conv.weight.flatten(1), conv.bias)
-        x = F.relu(_bn_rows(bn, x), inplace=True)
+def conv_bn_relu_rows(x, conv, bn, pool_k=1):
+    """One shared-MLP layer on rows: 1x1 conv -> BN -> ReLU, optionally followed by the max over
+    groups of `pool_k` consecutive rows (the neighbour axis).  In training mode the elementwise
+    half runs in libpcbridge's fused row kernels (csrc/bn_rows.cu): the conv bias is folded into
+    the normalisation and ReLU / max-pool happen in the same pass."""
+    w = conv.weight.flatten(1)
+    if bn.training and x.is_cuda and w.shape[0] % 4 == 0 and bn.momentum is not None and bn.affine \
+            and x.shape[0] % pool_k == 0 and 1 < pool_k + 1 <= 256 and x.shape[0] > 1:
+        y = F.linear(x, w)                                   # bias-free: BN(xW + b) == BN(xW) + running-mean shift
+        if ops.bn_rows_supported(y, bn, pool_k):
+            return ops.bn_relu_rows(y, conv.bias, bn, relu=True, pool_k=pool_k)
+        x = y if conv.bias is None else y + conv.bias
+    else:
+        x = F.linear(x, w, conv.bias)
+    x = F.relu(_bn_rows(bn, x), inplace=True)
+    if pool_k > 1:
+        x = x.view(-1, pool_k, x.shape[-1]).max(dim=1)[0]
+    return x
+
+
+def mlp_rows(x, convs, bns, pool_k=1):
+    """x [M,Cin] -> [M/pool_k,Cout]: (1x1 conv -> BN -> ReLU) per layer (pointnet_util.py:213-215), the
+    last layer followed by the max over `pool_k` neighbours (:217)."""
+    n = len(convs)
+    for i, (conv, bn) in enumerate(zip(convs, bns)):
+        x = conv_bn_relu_rows(x, conv, bn, pool_k if i == n - 1 else 1)
     return x
 
 
@@ -151,8 +172,7 @@ class PointNetSetAbstraction(nn.Module):
         else:
             new_xyz, grouped = sample_and_group(self.npoint, self.radius, self.nsample, xyz_r, pts_r)
         S, K, C = grouped.shape[1:]
-        y = mlp_rows(grouped.reshape(B * S * K, C), self.mlp_convs, self.mlp_bns)
-        y = y.view(B * S, K, -1).max(dim=1)[0]                       # max over the neighbours
+        y = mlp_rows(grouped.reshape(B * S * K, C), self.mlp_convs, self.mlp_bns, pool_k=K)   # max over neighbours
         return new_xyz.permute(0, 2, 1), _cf_view(y, B, S)
 
 
@@ -186,8 +206,7 @@ class PointNetSetAbstractionMsg(nn.Module):
             K = self.nsample_list[i]
             idx = query_ball_point(radius, K, xyz_r, new_xyz)
             grouped = ops.group_points(xyz_r, pts_r, new_xyz, idx, xyz_first=False)   # [feat | dxyz]
-            y = mlp_rows(grouped.view(B * S * K, -1), self.conv_blocks[i], self.bn_blocks[i])
-            outs.append(y.view(B * S, K, -1).max(dim=1)[0])
+            outs.append(mlp_rows(grouped.view(B * S * K, -1), self.conv_blocks[i], self.bn_blocks[i], pool_k=K))
         y = torch.cat(outs, dim=1)
         return new_xyz.permute(0, 2, 1), _cf_view(y, B, S)
 
