@@ -86,8 +86,10 @@ __device__ __forceinline__ void column_reduce(int64_t M, int C, int64_t rows_per
         for (int a = 0; a < NACC; ++a)
 #pragma unroll
             for (int v = 0; v < 4; ++v) acc[a][v] = 0.f;
-        if (t.ty < t.TY)
+        if (t.ty < t.TY) {
+#pragma unroll 4
             for (int64_t r = r0 + t.ty; r < r1; r += t.TY) f(r, cq * 4, acc);
+        }
 #pragma unroll
         for (int a = 0; a < NACC; ++a)
 #pragma unroll

@@ -159,12 +159,52 @@ class Trainer:
 
 class BlockInference:
     """Evaluates independent 4096-point blocks in fixed-size batches on this rank's shard of the
-    block list.  No collective on the data path; every rank keeps its own label slice."""
+    block list.  No collective on the data path; every rank keeps its own label slice.
+    With `graph=True` the forward of a full batch is captured once into a CUDA graph (FPS start
+    indices refilled from the CPU generator before every replay, as in training)."""
 
-    def __init__(self, net, batch_blocks=32, amp=True):
+    def __init__(self, net, batch_blocks=32, amp=True, graph=True):
         self.net = net.eval()
         self.batch_blocks = batch_blocks
         self.amp = amp
+        self.graph = graph
+        self._g = None
+        self._starts = FpsStartBuffers()
+        self._seen = 0
+
+    def _forward(self, x):
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=self.amp):
+            logp, _ = self.net(x)
+        return logp.argmax(dim=-1).to(torch.uint8)
+
+    def _forward_graphed(self, x):
+        if self._seen < 2:                                   # two eager batches; the second records the FPS calls
+            self._seen += 1
+            if self._seen == 2:
+                self._starts.shapes, self._starts.mode = [], "discover"
+                ops.set_fps_start_provider(self._starts.provider)
+            try:
+                return self._forward(x)
+            finally:
+                self._starts.mode = "off"
+                ops.set_fps_start_provider(None)
+        if self._g is None:
+            self._static_x = x.clone()
+            self._starts.allocate()
+            self._starts.mode = "record"
+            ops.set_fps_start_provider(self._starts.provider)
+            torch.cuda.synchronize()
+            self._g = torch.cuda.CUDAGraph()
+            try:
+                with torch.cuda.graph(self._g):
+                    self._static_out = self._forward(self._static_x)
+            finally:
+                self._starts.mode = "off"
+                ops.set_fps_start_provider(None)
+        self._static_x.copy_(x, non_blocking=True)
+        self._starts.refill()
+        self._g.replay()
+        return self._static_out
 
     @torch.no_grad()
     def run(self, blocks_x, out_labels=None):
@@ -174,7 +214,45 @@ class BlockInference:
             out_labels = torch.empty(nb, blocks_x.shape[2], dtype=torch.uint8, device=blocks_x.device)
         for lo in range(0, nb, self.batch_blocks):
             x = blocks_x[lo:lo + self.batch_blocks]
-            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=self.amp):
-                logp, _ = self.net(x)
-            out_labels[lo:lo + x.shape[0]] = logp.argmax(dim=-1).to(torch.uint8)
+            full = x.shape[0] == self.batch_blocks
+            lab = self._forward_graphed(x) if (self.graph and full) else self._forward(x)
+            out_labels[lo:lo + x.shape[0]] = lab
         return out_labels
+
+
+def run_sharded_scene(net, blocks_x_host, rank, world, device, batch_blocks=32, amp=True, chunk_blocks=512,
+                      infer=None):
+    """Config 5: evaluate a scene that was tiled into independent blocks.  `blocks_x_host` is the
+    whole scene's pinned host tensor [nb,9,N]; this rank takes its contiguous shard
+    (distributed.shard_range), streams it through the GPU in chunks (H2D on a side stream
+    overlapped with compute) and returns (range, uint8 labels [n_local,N] on the host).
+    No collective: ranks never exchange data."""
+    rng = pdist.shard_range(blocks_x_host.shape[0], rank, world)
+    n_local = len(rng)
+    out = torch.empty(n_local, blocks_x_host.shape[2], dtype=torch.uint8).pin_memory()
+    if n_local == 0:
+        return rng, out
+    infer = infer or BlockInference(net, batch_blocks=batch_blocks, amp=amp)
+    copy_stream = torch.cuda.Stream(device=device)
+    main = torch.cuda.current_stream(device)
+    chunks = [(lo, min(lo + chunk_blocks, n_local)) for lo in range(0, n_local, chunk_blocks)]
+
+    def upload(i):
+        lo, hi = chunks[i]
+        with torch.cuda.stream(copy_stream):
+            x = blocks_x_host[rng.start + lo:rng.start + hi].to(device, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        return x, ev
+
+    nxt = upload(0)
+    for i, (lo, hi) in enumerate(chunks):
+        x, ev = nxt
+        if i + 1 < len(chunks):
+            nxt = upload(i + 1)
+        main.wait_event(ev)
+        lab = infer.run(x)
+        out[lo:hi].copy_(lab, non_blocking=True)
+        x.record_stream(main)
+    main.synchronize()
+    return rng, out

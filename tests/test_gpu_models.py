@@ -193,3 +193,17 @@ def test_cuda_graph_training_matches_eager(g):
     assert len(set(round(v, 4) for v in losses[False])) > 3       # the starts really vary per step
     for a, b in zip(losses[False], losses[True]):
         assert abs(a - b) <= 2e-5 * max(1.0, abs(a))
+
+
+def test_block_inference_graph_matches_eager(g):
+    """engine.BlockInference: captured forward == eager forward (same FPS draws), labels identical."""
+    from pointcloud_bridge_b200.engine import BlockInference
+    x9, *_ = inputs(g)
+    x = x9.repeat(4, 1, 1)                                   # 8 blocks -> 4 batches of 2
+    net = parity.seeded_fill_(ssg.get_model(13), 1).to(DEV)
+    outs = {}
+    for mode in (False, True):
+        torch.manual_seed(5)
+        outs[mode] = BlockInference(net, batch_blocks=2, amp=False, graph=mode).run(x).cpu()
+    agree = (outs[False] == outs[True]).float().mean().item()
+    assert agree > 0.999, agree
