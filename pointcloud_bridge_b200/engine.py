@@ -114,6 +114,10 @@ class Trainer:
                     self.opt.step()
             self._static_loss = loss
             self.kernel_launches_per_replay = _lib.launches() - n0   # libpcbridge kernels inside the graph
+            if not self._opt_in_graph:                               # second graph: the optimizer alone
+                self._g_opt = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self._g_opt):
+                    self.opt.step()
         finally:
             self._starts.mode = "off"
             ops.set_fps_start_provider(None)
@@ -151,9 +155,9 @@ class Trainer:
         self._g.replay()
         from . import _lib
         _lib.count_launches(self.kernel_launches_per_replay)
-        if not self._opt_in_graph:
+        if not self._opt_in_graph:                          # eager NCCL all-reduce between the two graphs
             self.bucket.allreduce_mean()
-            self.opt.step()
+            self._g_opt.replay()
         return self._static_loss
 
 
