@@ -143,6 +143,22 @@ int pcb_bn_bwd_rows(const void *gz, const void *y, const unsigned char *argmax, 
                     int pool_k, const float *mean, const float *invstd, const float *gamma, const float *beta,
                     int relu, float *sums, void *gy, pcb_stream_t stream);
 
+/* ---- a11 / section 8f rank 1: fused set-abstraction / EdgeConv block for inference
+ *          pointnet_util.py:137-147, 203-217, 258-279; pointnet2_utils.py:140-154, 341-356;
+ *          DGCNN.py:72-109, 134-148
+ * gather -> [dxyz|feat] rows (mode 0; [feat|dxyz] when xyz_first == 0) or EdgeConv rows
+ * [x_nbr - x_ctr | x_ctr] (mode 1, points [B,N,D], centre = point s, S == N) -> nlayers x
+ * (1x1 conv with folded BatchNorm + max(x, slope*x)) on tcgen05 tensor cores (bf16 operands,
+ * fp32 accumulation in TMEM) -> max over the K neighbours -> out [B*S, cout] (bf16 or fp32).
+ * kdim (HOST array, nlayers+1 entries): padded widths, multiples of 16, <= 256; wblob: bf16
+ * weights packed per layer as [kdim[l]/8][kdim[l+1]][8] (zero padded), 16-byte aligned, padded
+ * to a multiple of 128 bytes; bias: fp32, concatenated padded widths.  K <= 128.
+ * Returns PCB_ERANGE when the weights + activation tiles do not fit in shared memory. */
+int pcb_sa_fused_bf16(const float *xyz, const float *points, const float *new_xyz, const int64_t *idx, int B,
+                      int N, int S, int K, int D, int mode, int xyz_first, int nlayers, const int *kdim, int cout,
+                      const void *wblob, const float *bias, float slope, void *out, int out_bf16,
+                      pcb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -38,6 +38,7 @@ _SIGNATURES = {
     "pcb_bn_stats_rows": [_vp, _i, _i64, _i, _vp, _vp],
     "pcb_bn_finalize": [_vp, _vp, _i, _vp, _i64, _i, _f, _f, _vp, _vp, _vp, _vp, _vp],
     "pcb_bn_apply_rows": [_vp, _i, _i64, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp],
+    "pcb_sa_fused_bf16": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp, _f, _vp, _i, _vp],
     "pcb_bn_bwd_rows": [_vp, _vp, _vp, _i, _i64, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp],
 }
 

@@ -55,8 +55,18 @@ class DGCNN(nn.Module):
         x = xyz.transpose(2, 1)[:, :3, :].contiguous()
         k = min(self.k, N - 1)
         feats = []
-        for conv in (self.conv1, self.conv2, self.conv3, self.conv4):
-            x = conv(self.get_graph_feature(x.float(), k=k)).max(dim=-1)[0]
+        for li, conv in enumerate((self.conv1, self.conv2, self.conv3, self.conv4)):
+            x = x.float()
+            if ops.fused_inference_enabled() and not conv[1].training and k <= 128:
+                # EdgeConv fused on the tensor cores: the [B,2D,N,k] edge tensor never exists
+                pk = ops.packed_mlp(self, li, [conv[0]], [conv[1]], 2 * x.shape[1])
+                if pk.ok:
+                    idx = self.knn(x, k)
+                    y = ops.sa_fused(None, x.transpose(1, 2).contiguous(), None, idx, pk, mode=1, slope=0.2)
+                    x = y.view(B, N, -1).permute(0, 2, 1)
+                    feats.append(x)
+                    continue
+            x = conv(self.get_graph_feature(x, k=k)).max(dim=-1)[0]
             feats.append(x)
         local = torch.cat(feats, dim=1)                                  # [B,320,N]
         local_n = F.leaky_relu(self.local_bn(local), negative_slope=0.2)

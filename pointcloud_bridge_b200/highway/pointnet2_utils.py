@@ -109,6 +109,13 @@ class SetAbstraction(nn.Module):
     def forward(self, xyz, points):
         xyz = xyz.contiguous()
         pts = _rows(points) if points is not None else None
+        if ops.fused_inference_enabled() and not self.mlp_bns[0].training and self.nsample <= 128:
+            pk = ops.packed_mlp(self, 0, self.mlp_convs, self.mlp_bns, 3 + (pts.shape[2] if pts is not None else 0))
+            if pk.ok:
+                new_xyz = index_points(xyz, farthest_point_sample(xyz, self.npoint))
+                idx = query_ball_point(self.radius, self.nsample, xyz, new_xyz)
+                y = ops.sa_fused(xyz, pts, new_xyz, idx, pk, xyz_first=True)
+                return new_xyz, _cf_view(y, xyz.shape[0], self.npoint)
         new_xyz, grouped = sample_and_group(self.npoint, self.radius, self.nsample, xyz, pts)
         B, S, K, C = grouped.shape
         y = mlp_rows(grouped.view(B * S * K, C), self.mlp_convs, self.mlp_bns, pool_k=K)
@@ -143,6 +150,12 @@ class MultiScaleSetAbstraction(nn.Module):
         outs = []
         for i, (radius, K) in enumerate(zip(self.radius_list, self.nsample_list)):
             idx = query_ball_point(radius, K, xyz, new_xyz)
+            if ops.fused_inference_enabled() and not self.bn_blocks[i][0].training and K <= 128:
+                pk = ops.packed_mlp(self, i, self.conv_blocks[i], self.bn_blocks[i],
+                                    3 + (pts.shape[2] if pts is not None else 0))
+                if pk.ok:
+                    outs.append(ops.sa_fused(xyz, pts, new_xyz, idx, pk, xyz_first=True))
+                    continue
             grouped = ops.group_points(xyz, pts, new_xyz, idx, xyz_first=True, clamp=True)
             outs.append(mlp_rows(grouped.view(B * S * K, -1), self.conv_blocks[i], self.bn_blocks[i], pool_k=K))
         return new_xyz, _cf_view(torch.cat(outs, dim=1), B, S)

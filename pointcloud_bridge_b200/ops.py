@@ -429,3 +429,96 @@ def bn_rows_supported(y, bn, pool_k=1) -> bool:
     return (y.is_cuda and y.dim() == 2 and y.shape[1] % 4 == 0 and y.dtype in (torch.float32, torch.bfloat16)
             and bn.training and bn.momentum is not None and bn.affine and y.shape[0] % pool_k == 0
             and y.shape[0] > 1 and pool_k <= 255 and y.numel() // 4 < 2 ** 31)
+
+
+# ---------------------------------------------------------------------------------------------
+# fused set-abstraction / EdgeConv block for inference (tcgen05 tensor cores)
+# ---------------------------------------------------------------------------------------------
+def _ru16(n: int) -> int:
+    return (n + 15) // 16 * 16
+
+
+class PackedMLP:
+    """Eval-mode (conv 1x1 -> BatchNorm -> activation) stack folded to W', b' per layer and packed
+    into the shared-memory image the fused kernel expects: bf16, [K/8][N][8], zero padded."""
+
+    def __init__(self, convs, bns, c_in: int):
+        import ctypes
+        dev = convs[0].weight.device
+        kdim = [_ru16(c_in)]
+        blobs, biases = [], []
+        width = c_in
+        with torch.no_grad():
+            for conv, bn in zip(convs, bns):
+                w = conv.weight.flatten(1).float()                      # [out, in]
+                assert w.shape[1] == width
+                b = conv.bias.float() if conv.bias is not None else torch.zeros(w.shape[0], device=dev)
+                scale = bn.weight.float() / torch.sqrt(bn.running_var.float() + bn.eps)
+                w = w * scale[:, None]
+                b = (b - bn.running_mean.float()) * scale + bn.bias.float()
+                n_pad, k_pad = _ru16(w.shape[0]), kdim[-1]
+                wp = torch.zeros(n_pad, k_pad, device=dev)
+                wp[:w.shape[0], :w.shape[1]] = w
+                blobs.append(wp.view(n_pad, k_pad // 8, 8).permute(1, 0, 2).contiguous().to(torch.bfloat16).reshape(-1))
+                bp = torch.zeros(n_pad, device=dev)
+                bp[:w.shape[0]] = b
+                biases.append(bp)
+                kdim.append(n_pad)
+                width = w.shape[0]
+        blob = torch.cat(blobs)
+        pad = (-blob.numel() * 2) % 128
+        if pad:
+            blob = torch.cat([blob, torch.zeros(pad // 2, dtype=torch.bfloat16, device=dev)])
+        self.wblob = blob.contiguous()
+        self.bias = torch.cat(biases).contiguous()
+        self.kdim = kdim
+        self.kdim_c = (ctypes.c_int * len(kdim))(*kdim)
+        self.cout = width
+        self.nlayers = len(convs)
+        maxw = max(kdim)
+        a_bytes = (128 * (maxw + 8) * 2 + 127) // 128 * 128
+        self.smem = self.wblob.numel() * 2 + 2 * a_bytes + self.bias.numel() * 4 + 128
+        self.ok = self.smem <= 200 * 1024 and maxw <= 256 and self.nlayers <= 3
+
+
+def packed_mlp(owner, key, convs, bns, c_in):
+    """Cache of PackedMLP per module, invalidated when a parameter / running statistic changes."""
+    ver = tuple(t._version for m in list(convs) + list(bns) for t in list(m.parameters()) + list(m.buffers()))
+    cache = owner.__dict__.setdefault("_pcb_packed", {})
+    hit = cache.get(key)
+    if hit is None or hit[0] != ver:
+        hit = (ver, PackedMLP(convs, bns, c_in))
+        cache[key] = hit
+    return hit[1]
+
+
+def fused_inference_enabled() -> bool:
+    """The fused tcgen05 block computes in bf16: it is used only for eval-mode forwards under
+    bf16 autocast without autograd (fp32 parity runs keep the exact unfused path)."""
+    return (not torch.is_grad_enabled()) and torch.is_autocast_enabled() and \
+        torch.get_autocast_dtype('cuda') == torch.bfloat16 and os.environ.get("PCB_NO_FUSED", "0") != "1"
+
+
+@torch.no_grad()
+def sa_fused(xyz, points, new_xyz, idx, packed: PackedMLP, xyz_first=True, mode=0, slope=0.0, out_bf16=True):
+    """Fused gather -> shared MLP (folded BN) -> max over neighbours.  mode 0: xyz [B,N,3], points [B,N,D] | None,
+    new_xyz [B,S,3], idx [B,S,K]; mode 1 (EdgeConv): points [B,N,D], idx [B,N,K].  -> [B*S, cout]."""
+    idx = _i64(idx, "idx")
+    B, S, K = idx.shape
+    if points is not None:
+        points = _f32(points, "points")
+        N, D = points.shape[1], points.shape[2]
+    else:
+        N, D = xyz.shape[1], 0
+    dev = idx.device
+    if mode == 0:
+        xyz = _f32(xyz, "xyz")
+        new_xyz = _f32(new_xyz, "new_xyz")
+    out = torch.empty(B * S, packed.cout, dtype=torch.bfloat16 if out_bf16 else torch.float32, device=dev)
+    flops = 2 * B * S * K * sum(a * b for a, b in zip(packed.kdim[:-1], packed.kdim[1:]))
+    _call("pcb_sa_fused_bf16", dev, xyz.data_ptr() if mode == 0 else None, points.data_ptr() if D else None,
+          new_xyz.data_ptr() if mode == 0 else None, idx.data_ptr(), B, N, S, K, D, int(mode), int(xyz_first),
+          packed.nlayers, packed.kdim_c, packed.cout, packed.wblob.data_ptr(), packed.bias.data_ptr(), float(slope),
+          out.data_ptr(), int(out_bf16),
+          alg_bytes=B * (4 * N * (3 + D) + 8 * S * K + 12 * S) + out.numel() * out.element_size())
+    return out

@@ -167,6 +167,13 @@ class PointNetSetAbstraction(nn.Module):
         xyz_r = _rows(xyz)
         pts_r = _rows(points) if points is not None else None
         B = xyz_r.shape[0]
+        if not self.group_all and ops.fused_inference_enabled() and not self.mlp_bns[0].training:
+            pk = ops.packed_mlp(self, 0, self.mlp_convs, self.mlp_bns, 3 + (pts_r.shape[2] if pts_r is not None else 0))
+            if pk.ok and self.nsample <= 128:
+                new_xyz = index_points(xyz_r, farthest_point_sample(xyz_r, self.npoint))
+                idx = query_ball_point(self.radius, self.nsample, xyz_r, new_xyz)
+                y = ops.sa_fused(xyz_r, pts_r, new_xyz, idx, pk, xyz_first=True)
+                return new_xyz.permute(0, 2, 1), _cf_view(y, B, self.npoint)
         if self.group_all:
             new_xyz, grouped = sample_and_group_all(xyz_r, pts_r)
         else:
@@ -205,6 +212,12 @@ class PointNetSetAbstractionMsg(nn.Module):
         for i, radius in enumerate(self.radius_list):
             K = self.nsample_list[i]
             idx = query_ball_point(radius, K, xyz_r, new_xyz)
+            if ops.fused_inference_enabled() and not self.bn_blocks[i][0].training and K <= 128:
+                pk = ops.packed_mlp(self, i, self.conv_blocks[i], self.bn_blocks[i],
+                                    3 + (pts_r.shape[2] if pts_r is not None else 0))
+                if pk.ok:
+                    outs.append(ops.sa_fused(xyz_r, pts_r, new_xyz, idx, pk, xyz_first=False))
+                    continue
             grouped = ops.group_points(xyz_r, pts_r, new_xyz, idx, xyz_first=False)   # [feat | dxyz]
             outs.append(mlp_rows(grouped.view(B * S * K, -1), self.conv_blocks[i], self.bn_blocks[i], pool_k=K))
         y = torch.cat(outs, dim=1)
