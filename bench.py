@@ -259,7 +259,13 @@ def run_ours(a):
     for i in range(n_inst):
         flush.fill_(0.0)
         x, y = resident[i % len(resident)]
-        trainer._step_eager((x,), y, ())                 # eager launches so that each kernel can be bracketed
+        # Eager launches so that each kernel can be bracketed by events.  The host needs ~15 ms to
+        # enqueue an eager step, the GPU ~8 ms to run it: a 40 ms spin kernel in front lets the host
+        # run ahead, so events and kernels execute back to back and an event pair measures the kernel,
+        # not the launch gap.
+        torch.cuda._sleep(int(8e7))
+        trainer._step_eager((x,), y, ())
+        torch.cuda.synchronize()
     ei1.record()
     torch.cuda.synchronize()
     ops.set_kernel_timer(None)

@@ -125,6 +125,8 @@ int pcb_graph_feature_bwd_f32(const float *grad_out, const int64_t *idx, int B, 
  * Activations y [M,C] are fp32 (dtype 0) or bf16 (dtype 1); C % 4 == 0; statistics fp32.
  * The 1x1-conv bias is NOT added to y: BN(y + b) == BN(y) for batch statistics, b only enters
  * the running mean (pcb_bn_finalize) -- so no bias-add / bias-gradient pass exists.
+ * `sums` is a caller-provided fp32 scratch of 3*C*(1 + P) floats, P = ceil(M / max(64, ceil(M/592))):
+ * the first 3*C floats receive the column sums, the rest holds per-CTA partials (two-stage reduction).
  *   pcb_bn_stats_rows : sums[0:C] = sum_r (y[r]-y[0]), sums[C:2C] = sum_r (y[r]-y[0])^2  (1 read of y)
  *   pcb_bn_finalize   : mean/invstd [C] of y from the sums; running_mean/var update (may be NULL)
  *   pcb_bn_apply_rows : out[r] = max_{k<pool_k} act((y[r*pool_k+k]-mean)*invstd*gamma+beta), argmax

@@ -365,6 +365,9 @@ def _act_dtype(t: torch.Tensor) -> int:
     raise _lib.PcbError(f"bn_relu_rows supports fp32 / bf16 activations, got {t.dtype}")
 
 
+_BN_MAX_PARTS = 148 * 4      # kBnMaxParts in csrc/bn_rows.cu
+
+
 class _BnReluRows(torch.autograd.Function):
     """z = max_k relu(BN_train(y + bias)) on rows.  y [M,C] is the bias-free GEMM output."""
 
@@ -375,7 +378,9 @@ class _BnReluRows(torch.autograd.Function):
         M, C = y.shape
         dt = _act_dtype(y)
         dev = y.device
-        sums = torch.empty(3 * C, dtype=torch.float32, device=dev)
+        # [3C result slots | per-CTA partial sums]: the column reductions are two-stage (csrc/bn_rows.cu)
+        rpc = max(64, -(-M // _BN_MAX_PARTS))
+        sums = torch.empty(3 * C * (1 + -(-M // rpc)), dtype=torch.float32, device=dev)
         stats = torch.empty(2, C, dtype=torch.float32, device=dev)          # mean, invstd of bias-free y
         mean, invstd = stats[0], stats[1]
         _call("pcb_bn_stats_rows", dev, y.data_ptr(), dt, M, C, sums.data_ptr(), alg_bytes=y.numel() * y.element_size())
@@ -407,7 +412,7 @@ class _BnReluRows(torch.autograd.Function):
               dt, M, C, pool_k, stats[0].data_ptr(), stats[1].data_ptr(), g32.data_ptr(), b32.data_ptr(), relu,
               sums.data_ptr(), gy.data_ptr(), launches=2,
               alg_bytes=(3 * y.numel() + 2 * gz.numel()) * y.element_size())
-        s = sums.view(3, C)
+        s = sums[:3 * C].view(3, C)
         ggamma, gbeta = s[1], s[0]
         # d/d(bias) = sum_rows gy = -gamma * invstd * (sum yhat) * (sum dy*yhat) / M: zero up to rounding,
         # as in the reference, where the bias of a conv that feeds a training-mode BN gets a noise gradient
