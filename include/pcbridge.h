@@ -84,6 +84,14 @@ int pcb_group_points_f32(const float *xyz, const float *points, const float *new
 int pcb_group_points_bwd_f32(const float *grad_out, const int64_t *idx, int B, int N, int S, int K,
                              int D, int xyz_first, int points_cf, int clamp, float *grad_points,
                              pcb_stream_t stream);
+/* bf16 variants: the grouped tensor (and its gradient) in bf16, as the autocast GEMM consumes it;
+ * inputs and grad_points stay fp32 */
+int pcb_group_points_bf16(const float *xyz, const float *points, const float *new_xyz,
+                          const int64_t *idx, int B, int N, int S, int K, int D, int xyz_first,
+                          int points_cf, int clamp, void *out, pcb_stream_t stream);
+int pcb_group_points_bwd_bf16(const void *grad_out, const int64_t *idx, int B, int N, int S, int K,
+                              int D, int xyz_first, int points_cf, int clamp, float *grad_points,
+                              pcb_stream_t stream);
 
 /* ---- a7  k nearest of xyz2 for each xyz1 point + inverse-distance weights
  *          pointnet_util.py:325-332; pointnet2_utils.py:183-191 (k=3), 253-262 (k=4)

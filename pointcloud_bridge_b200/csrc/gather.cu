@@ -7,11 +7,18 @@
 //   pcb_square_distance_f32        square_distance       pointnet_util.py:22-43
 // The output (the big operand) is written once with streaming stores, fully coalesced, with
 // 128-bit accesses wherever the row length allows; the gathered source stays L1/L2 resident.
+#include <cuda_bf16.h>
+
 #include "pcb_common.cuh"
 
 namespace pcb {
 
 constexpr int kThreads = 256;
+
+__device__ __forceinline__ void store_out(float *p, float v) { st_stream_f1(p, v); }
+__device__ __forceinline__ void store_out(__nv_bfloat16 *p, float v) { *p = __float2bfloat16(v); }
+__device__ __forceinline__ float load_grad(const float *p) { return __ldg(p); }
+__device__ __forceinline__ float load_grad(const __nv_bfloat16 *p) { return __bfloat162float(*p); }
 
 __device__ __forceinline__ bool resolve_index(long long &i, int N, int clamp)
 {
@@ -75,11 +82,12 @@ gather_bwd_kernel(const float *__restrict__ gout, const int64_t *__restrict__ id
 // grouping + concat.  out[b,s,k,:] = cat(xyz[idx]-new_xyz, points[idx]) (or the MSG order).
 // One thread per output float; threads of a row share the index (broadcast load).
 // ------------------------------------------------------------------------------------------
+template <typename OT>
 __global__ void __launch_bounds__(kThreads)
 group_points_kernel(const float *__restrict__ xyz, const float *__restrict__ points,
                     const float *__restrict__ new_xyz, const int64_t *__restrict__ idx, int N, int D, FastDiv dC,
                     FastDiv dK, FastDiv dS, int xyz_first, int points_cf, int clamp, unsigned total,
-                    float *__restrict__ out)
+                    OT *__restrict__ out)
 {
     const unsigned t = blockIdx.x * kThreads + threadIdx.x;
     if (t >= total) return;
@@ -100,11 +108,12 @@ group_points_kernel(const float *__restrict__ xyz, const float *__restrict__ poi
                           : __ldg(points + ((size_t)b * N + i) * D + cf);
         }
     }
-    st_stream_f1(out + t, v);
+    store_out(out + t, v);
 }
 
+template <typename GT>
 __global__ void __launch_bounds__(kThreads)
-group_points_bwd_kernel(const float *__restrict__ gout, const int64_t *__restrict__ idx, int N, int D, FastDiv dD,
+group_points_bwd_kernel(const GT *__restrict__ gout, const int64_t *__restrict__ idx, int N, int D, FastDiv dD,
                         FastDiv dSK, int xyz_first, int points_cf, int clamp, unsigned total,
                         float *__restrict__ gpoints)
 {
@@ -117,7 +126,7 @@ group_points_bwd_kernel(const float *__restrict__ gout, const int64_t *__restric
     const unsigned b = dSK.div(rowg);
     long long i = idx[rowg];
     if (!resolve_index(i, N, clamp)) return;
-    const float g = __ldg(gout + (size_t)rowg * C + (xyz_first ? 3 + cf : cf));
+    const float g = load_grad(gout + (size_t)rowg * C + (xyz_first ? 3 + cf : cf));
     float *dst = points_cf ? gpoints + ((size_t)b * D + cf) * N + i : gpoints + ((size_t)b * N + i) * D + cf;
     atomicAdd(dst, g);
 }
@@ -413,9 +422,10 @@ PCB_API int pcb_gather_bwd_f32(const float *grad_out, const int64_t *idx, int B,
     PCB_RETURN_LAUNCH_STATUS();
 }
 
-PCB_API int pcb_group_points_f32(const float *xyz, const float *points, const float *new_xyz,
-                                 const int64_t *idx, int B, int N, int S, int K, int D, int xyz_first,
-                                 int points_cf, int clamp, float *out, pcb_stream_t stream)
+template <typename OT>
+static int group_points_launch(const float *xyz, const float *points, const float *new_xyz, const int64_t *idx, int B,
+                               int N, int S, int K, int D, int xyz_first, int points_cf, int clamp, OT *out,
+                               cudaStream_t st)
 {
     PCB_REQUIRE(xyz && new_xyz && idx && out, PCB_EINVAL);
     PCB_REQUIRE(B > 0 && N > 0 && S > 0 && K > 0 && D >= 0, PCB_EINVAL);
@@ -426,7 +436,7 @@ PCB_API int pcb_group_points_f32(const float *xyz, const float *points, const fl
     for (int b0 = 0; b0 < B; b0 += step) {
         const int nb = B - b0 < step ? B - b0 : step;
         const unsigned total = (unsigned)((int64_t)nb * S * K * C);
-        group_points_kernel<<<blocks_for(total), kThreads, 0, (cudaStream_t)stream>>>(
+        group_points_kernel<OT><<<blocks_for(total), kThreads, 0, st>>>(
             xyz + (size_t)b0 * N * 3, points ? points + (size_t)b0 * N * D : nullptr, new_xyz + (size_t)b0 * S * 3,
             idx + (size_t)b0 * S * K, N, D, make_fastdiv(C), make_fastdiv(K), make_fastdiv(S), xyz_first, points_cf,
             clamp, total, out + (size_t)b0 * S * K * C);
@@ -434,9 +444,9 @@ PCB_API int pcb_group_points_f32(const float *xyz, const float *points, const fl
     PCB_RETURN_LAUNCH_STATUS();
 }
 
-PCB_API int pcb_group_points_bwd_f32(const float *grad_out, const int64_t *idx, int B, int N, int S, int K,
-                                     int D, int xyz_first, int points_cf, int clamp, float *grad_points,
-                                     pcb_stream_t stream)
+template <typename GT>
+static int group_points_bwd_launch(const GT *grad_out, const int64_t *idx, int B, int N, int S, int K, int D,
+                                   int xyz_first, int points_cf, int clamp, float *grad_points, cudaStream_t st)
 {
     PCB_REQUIRE(grad_out && idx && grad_points, PCB_EINVAL);
     PCB_REQUIRE(B > 0 && N > 0 && S > 0 && K > 0 && D > 0, PCB_EINVAL);
@@ -445,11 +455,43 @@ PCB_API int pcb_group_points_bwd_f32(const float *grad_out, const int64_t *idx, 
     for (int b0 = 0; b0 < B; b0 += step) {
         const int nb = B - b0 < step ? B - b0 : step;
         const unsigned total = (unsigned)((int64_t)nb * S * K * D);
-        group_points_bwd_kernel<<<blocks_for(total), kThreads, 0, (cudaStream_t)stream>>>(
+        group_points_bwd_kernel<GT><<<blocks_for(total), kThreads, 0, st>>>(
             grad_out + (size_t)b0 * S * K * (3 + D), idx + (size_t)b0 * S * K, N, D, make_fastdiv(D),
             make_fastdiv((unsigned)(S * K)), xyz_first, points_cf, clamp, total, grad_points + (size_t)b0 * N * D);
     }
     PCB_RETURN_LAUNCH_STATUS();
+}
+
+PCB_API int pcb_group_points_f32(const float *xyz, const float *points, const float *new_xyz,
+                                 const int64_t *idx, int B, int N, int S, int K, int D, int xyz_first,
+                                 int points_cf, int clamp, float *out, pcb_stream_t stream)
+{
+    return group_points_launch<float>(xyz, points, new_xyz, idx, B, N, S, K, D, xyz_first, points_cf, clamp, out,
+                                      (cudaStream_t)stream);
+}
+
+PCB_API int pcb_group_points_bf16(const float *xyz, const float *points, const float *new_xyz,
+                                  const int64_t *idx, int B, int N, int S, int K, int D, int xyz_first,
+                                  int points_cf, int clamp, void *out, pcb_stream_t stream)
+{
+    return group_points_launch<__nv_bfloat16>(xyz, points, new_xyz, idx, B, N, S, K, D, xyz_first, points_cf, clamp,
+                                              (__nv_bfloat16 *)out, (cudaStream_t)stream);
+}
+
+PCB_API int pcb_group_points_bwd_f32(const float *grad_out, const int64_t *idx, int B, int N, int S, int K,
+                                     int D, int xyz_first, int points_cf, int clamp, float *grad_points,
+                                     pcb_stream_t stream)
+{
+    return group_points_bwd_launch<float>(grad_out, idx, B, N, S, K, D, xyz_first, points_cf, clamp, grad_points,
+                                          (cudaStream_t)stream);
+}
+
+PCB_API int pcb_group_points_bwd_bf16(const void *grad_out, const int64_t *idx, int B, int N, int S, int K,
+                                      int D, int xyz_first, int points_cf, int clamp, float *grad_points,
+                                      pcb_stream_t stream)
+{
+    return group_points_bwd_launch<__nv_bfloat16>((const __nv_bfloat16 *)grad_out, idx, B, N, S, K, D, xyz_first,
+                                                  points_cf, clamp, grad_points, (cudaStream_t)stream);
 }
 
 PCB_API int pcb_graph_feature_f32(const float *x, const int64_t *idx, int B, int D, int N, int k, float *out,

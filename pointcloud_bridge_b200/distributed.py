@@ -61,12 +61,13 @@ def max_over_ranks(value: float, device) -> float:
 
 
 class FlatGradBucket:
-    """All parameter gradients of `module` as views into one flat buffer.
+    """One flat fp32 buffer for all parameter gradients of `module` = one collective per step.
 
-    `p.grad` of every trainable parameter is pointed at its slice before backward; autograd then
-    accumulates in place, `allreduce_mean()` is a single collective over the whole buffer, and
-    the optimizer reads the averaged gradients through the same views -- no packing copies.
-    Call `zero()` instead of `optimizer.zero_grad()` (which would drop the views).
+    Gradients are produced by autograd as ordinary per-parameter tensors (`p.grad = None` before
+    backward, so no accumulate kernels run); `pack()` gathers them into the flat buffer with one
+    batched multi-tensor copy, `allreduce_mean()` is a single NCCL all-reduce over the buffer,
+    and `unpack()` scatters the averaged values back with another batched copy.  With one rank
+    nothing is packed at all.
     """
 
     def __init__(self, module: torch.nn.Module, dtype: torch.dtype = torch.float32):
@@ -74,10 +75,11 @@ class FlatGradBucket:
         total = sum(p.numel() for p in self.params)
         device = self.params[0].device
         self.flat = torch.zeros(total, dtype=dtype, device=device)
+        self.views = []
         off = 0
         for p in self.params:
             n = p.numel()
-            p.grad = self.flat[off:off + n].view_as(p)
+            self.views.append(self.flat[off:off + n].view_as(p))
             off += n
 
     @property
@@ -85,7 +87,23 @@ class FlatGradBucket:
         return self.flat.numel() * self.flat.element_size()
 
     def zero(self) -> None:
-        self.flat.zero_()
+        for p in self.params:
+            p.grad = None
+
+    def _live(self):
+        return [(v, p.grad) for v, p in zip(self.views, self.params) if p.grad is not None]
+
+    def pack(self) -> None:
+        live = self._live()
+        if len(live) != len(self.params):
+            self.flat.zero_()                      # parameters without a gradient contribute zeros
+        if live:
+            torch._foreach_copy_([v for v, _ in live], [g for _, g in live])
+
+    def unpack(self) -> None:
+        live = self._live()
+        if live:
+            torch._foreach_copy_([g for _, g in live], [v for v, _ in live])
 
     def allreduce_mean(self) -> None:
         if not is_dist() or dist.get_world_size() == 1:

@@ -89,9 +89,15 @@ class Trainer:
         loss.backward()
         return loss.detach()
 
+    def _multi(self):
+        return pdist.is_dist() and torch.distributed.get_world_size() > 1
+
     def _step_eager(self, inputs, labels, loss_inputs):
         loss = self._fwd_bwd(inputs, labels, loss_inputs)
-        self.bucket.allreduce_mean()
+        if self._multi():
+            self.bucket.pack()
+            self.bucket.allreduce_mean()
+            self.bucket.unpack()
         self.opt.step()
         return loss
 
@@ -100,7 +106,7 @@ class Trainer:
         """Capture one step with static input buffers.  With several ranks the NCCL all-reduce and
         the optimizer stay outside the graph (zero + forward + loss + backward are captured)."""
         self._static = ([t.clone() for t in inputs], labels.clone(), [t.clone() for t in loss_inputs])
-        self._opt_in_graph = not (pdist.is_dist() and torch.distributed.get_world_size() > 1)
+        self._opt_in_graph = not self._multi()
         self._starts.allocate()
         ops.set_fps_start_provider(self._starts.provider)
         self._starts.mode = "record"
@@ -112,11 +118,14 @@ class Trainer:
                 loss = self._fwd_bwd(self._static[0], self._static[1], self._static[2])
                 if self._opt_in_graph:
                     self.opt.step()
+                else:
+                    self.bucket.pack()
             self._static_loss = loss
             self.kernel_launches_per_replay = _lib.launches() - n0   # libpcbridge kernels inside the graph
             if not self._opt_in_graph:                               # second graph: the optimizer alone
                 self._g_opt = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(self._g_opt):
+                with torch.cuda.graph(self._g_opt, pool=self._g.pool()):
+                    self.bucket.unpack()
                     self.opt.step()
         finally:
             self._starts.mode = "off"

@@ -256,10 +256,12 @@ class _GroupPoints(torch.autograd.Function):
             D = points.shape[1] if points_cf else points.shape[2]
         else:
             D = 0
-        out = torch.empty(B, S, K, 3 + D, dtype=torch.float32, device=xyz.device)
-        _call("pcb_group_points_f32", xyz.device, xyz.data_ptr(), points.data_ptr() if D else None,
+        # under bf16 autocast the consumer is a bf16 GEMM: emit the grouped tensor in bf16 directly
+        bf16 = torch.is_autocast_enabled() and torch.get_autocast_dtype("cuda") == torch.bfloat16
+        out = torch.empty(B, S, K, 3 + D, dtype=torch.bfloat16 if bf16 else torch.float32, device=xyz.device)
+        _call("pcb_group_points_bf16" if bf16 else "pcb_group_points_f32", xyz.device, xyz.data_ptr(), points.data_ptr() if D else None,
               new_xyz.data_ptr(), idx.data_ptr(), B, N, S, K, D, int(xyz_first), int(points_cf), int(clamp),
-              out.data_ptr(), alg_bytes=B * (4 * N * (3 + D) + 12 * S + 8 * S * K + 4 * S * K * (3 + D)))
+              out.data_ptr(), alg_bytes=B * (4 * N * (3 + D) + 12 * S + 8 * S * K + out.element_size() * S * K * (3 + D)))
         ctx.save_for_backward(idx)
         ctx.meta = (B, N, S, K, D, int(xyz_first), int(points_cf), int(clamp))
         return out
@@ -270,10 +272,11 @@ class _GroupPoints(torch.autograd.Function):
         B, N, S, K, D, xyz_first, points_cf, clamp = ctx.meta
         gpoints = None
         if D and ctx.needs_input_grad[1]:
-            gout = _f32(gout, "grad")
+            bf16 = gout.dtype == torch.bfloat16
+            gout = gout.contiguous() if bf16 else _f32(gout, "grad")
             shape = (B, D, N) if points_cf else (B, N, D)
             gpoints = torch.zeros(shape, dtype=torch.float32, device=gout.device)
-            _call("pcb_group_points_bwd_f32", gout.device, gout.data_ptr(), idx.data_ptr(), B, N, S, K, D,
+            _call("pcb_group_points_bwd_bf16" if bf16 else "pcb_group_points_bwd_f32", gout.device, gout.data_ptr(), idx.data_ptr(), B, N, S, K, D,
                   xyz_first, points_cf, clamp, gpoints.data_ptr(),
                   alg_bytes=B * (4 * N * D + 8 * S * K + 4 * S * K * D))
         return None, gpoints, None, None, None, None, None

@@ -33,11 +33,12 @@ def _worker(rank, world, port, q):
     x, y = torch.randn(8, 4), torch.randn(8, 2)
     sl = pdist.shard_range(8, rank, world)
     bucket.zero()
+    assert all(p.grad is None for p in net.parameters())
     loss = ((net(x[sl.start:sl.stop]) - y[sl.start:sl.stop]) ** 2).mean()
     loss.backward()
-    # grads were accumulated in place into the flat buffer (views kept)
-    assert all(p.grad.data_ptr() >= bucket.flat.data_ptr() for p in net.parameters())
-    bucket.allreduce_mean()
+    bucket.pack()                                          # one batched copy into the flat buffer
+    bucket.allreduce_mean()                                # one collective
+    bucket.unpack()
     # reference: full-batch gradient on one process (equal shard sizes -> mean of shard means)
     torch.manual_seed(0)
     ref = torch.nn.Sequential(torch.nn.Linear(4, 3), torch.nn.ReLU(), torch.nn.Linear(3, 2))
