@@ -42,7 +42,7 @@ class FpsStartBuffers:
             return buf
         if self.mode == "discover":
             self.shapes.append((B, N, device))
-        return torch.randint(0, N, (B,), dtype=torch.long).to(device)
+        return ops._draw_start(B, N, device)
 
     def allocate(self):
         self.calls = [(N, torch.zeros(B, dtype=torch.long, device=dev), torch.zeros(B, dtype=torch.long).pin_memory())

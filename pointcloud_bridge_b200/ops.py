@@ -82,6 +82,26 @@ def set_fps_start_provider(fn) -> None:
     _fps_start_provider = fn
 
 
+# Ring of pinned staging buffers for the FPS start indices: a host->device copy from pageable
+# memory makes the host wait for all earlier work of the stream; from pinned memory it is
+# asynchronous.  64 slots per batch size: a slot is reused only after 63 later FPS calls.
+_start_ring: dict[int, tuple[list, list]] = {}
+
+
+def _draw_start(B: int, N: int, device) -> torch.Tensor:
+    """The reference's draw (pointnet_util.py:79): torch.randint on the CPU default generator."""
+    host = torch.randint(0, N, (B,), dtype=torch.long)
+    ring = _start_ring.get(B)
+    if ring is None:
+        ring = ([torch.empty(B, dtype=torch.long).pin_memory() for _ in range(64)], [0])
+        _start_ring[B] = ring
+    bufs, pos = ring
+    buf = bufs[pos[0] % len(bufs)]
+    pos[0] += 1
+    buf.copy_(host)
+    return buf.to(device, non_blocking=True)
+
+
 def _err_counter(dev: torch.device) -> torch.Tensor:
     key = dev.index if dev.index is not None else torch.cuda.current_device()
     t = _err_counters.get(key)
@@ -119,7 +139,7 @@ def furthest_point_sample(xyz: torch.Tensor, npoint: int, start: torch.Tensor | 
         if _fps_start_provider is not None:
             start = _fps_start_provider(B, N, xyz.device)
         else:
-            start = torch.randint(0, N, (B,), dtype=torch.long).to(xyz.device)
+            start = _draw_start(B, N, xyz.device)
     start = _i64(start.to(xyz.device), "start")
     out = torch.empty(B, npoint, dtype=torch.long, device=xyz.device)
     _call("pcb_fps_f32", xyz.device, xyz.data_ptr(), B, N, start.data_ptr(), int(npoint), out.data_ptr(),
@@ -530,3 +550,46 @@ def sa_fused(xyz, points, new_xyz, idx, packed: PackedMLP, xyz_first=True, mode=
           out.data_ptr(), int(out_bf16),
           alg_bytes=B * (4 * N * (3 + D) + 8 * S * K + 12 * S) + out.numel() * out.element_size())
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# y = x @ W^T on rows with a weight-gradient schedule for very tall activations
+# ---------------------------------------------------------------------------------------------
+class _LinearRows(torch.autograd.Function):
+    """F.linear without bias for x [M,K], W [N,K] with M in the 10^5..10^6 range.  The weight
+    gradient gy^T x reduces over M: cuBLAS picks legacy split-K kernels for that shape (85-135 us
+    per call in the round-1 profile); reducing 148*P row chunks as one batched GEMM and summing the
+    chunk results keeps every SM busy with short reductions."""
+
+    CHUNK = 2048
+
+    @staticmethod
+    def forward(ctx, x, w):
+        ctx.save_for_backward(x, w)
+        return torch.mm(x, w.t().to(x.dtype))
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w = ctx.saved_tensors
+        gx = gw = None
+        gy = gy.contiguous()
+        if ctx.needs_input_grad[0]:
+            gx = torch.mm(gy, w.to(gy.dtype))
+        if ctx.needs_input_grad[1]:
+            M = x.shape[0]
+            c = _LinearRows.CHUNK
+            if M % c == 0 and M // c >= 8:
+                p = M // c
+                part = torch.bmm(gy.view(p, c, -1).transpose(1, 2), x.view(p, c, -1).to(gy.dtype))   # [p,N,K]
+                gw = part.float().sum(dim=0)
+            else:
+                gw = torch.mm(gy.t(), x.to(gy.dtype)).float()
+        return gx, gw
+
+
+def linear_rows(x, w):
+    """x [M,K] @ w[N,K]^T under the ambient autocast dtype."""
+    if torch.is_autocast_enabled():
+        dt = torch.get_autocast_dtype("cuda")
+        x = x if x.dtype == dt else x.to(dt)
+    return _LinearRows.apply(x, w)

@@ -12,6 +12,8 @@ Two additions that the reference only has inline (pointnet_util.py:325-334):
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -119,7 +121,8 @@ def conv_bn_relu_rows(x, conv, bn, pool_k=1):
     w = conv.weight.flatten(1)
     if bn.training and x.is_cuda and w.shape[0] % 4 == 0 and bn.momentum is not None and bn.affine \
             and x.shape[0] % pool_k == 0 and 1 < pool_k + 1 <= 256 and x.shape[0] > 1:
-        y = F.linear(x, w)                                   # bias-free: BN(xW + b) == BN(xW) + running-mean shift
+        # bias-free: BN(xW + b) == BN(xW) + running-mean shift
+        y = ops.linear_rows(x, w) if (x.shape[0] >= 32768 and os.environ.get('PCB_PLAIN_LINEAR', '0') != '1') else F.linear(x, w)
         if ops.bn_rows_supported(y, bn, pool_k):
             return ops.bn_relu_rows(y, conv.bias, bn, relu=True, pool_k=pool_k)
         x = y if conv.bias is None else y + conv.bias
