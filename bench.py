@@ -166,9 +166,8 @@ KERNEL_OF = {                                         # C-ABI entry point -> dev
     "pcb_interpolate_bwd_f32": "interp_bwd_kernel", "pcb_knn_f32": "knn_kernel",
     "pcb_knn_cdist_f32": "knn_xyz_kernel", "pcb_graph_feature_f32": "graph_feature_kernel",
     "pcb_graph_feature_bwd_f32": "graph_feature_bwd_kernel", "pcb_group_points_bf16": "group_points_kernel",
-    "pcb_group_points_bwd_bf16": "group_points_bwd_kernel", "pcb_bn_stats_rows": "bn_stats_kernel+bn_fold_parts_kernel",
-    "pcb_bn_finalize": "bn_finalize_kernel", "pcb_bn_apply_rows": "bn_apply_kernel",
-    "pcb_bn_bwd_rows": "bn_bwd_reduce_kernel+bn_fold_parts_kernel+bn_bwd_apply_kernel",
+    "pcb_group_points_bwd_bf16": "group_points_bwd_kernel", "pcb_bn_fwd_rows": "bn_fwd_fused_kernel",
+    "pcb_bn_bwd_rows": "bn_bwd_fused_kernel",
     "pcb_sa_fused_bf16": "sa_fused_kernel"}
 
 

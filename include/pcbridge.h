@@ -76,21 +76,23 @@ int pcb_gather_bwd_f32(const float *grad_out, const int64_t *idx, int B, int N, 
  * xyz [B,N,3], points [B,N,D] or NULL (D = 0), new_xyz [B,S,3], idx [B,S,K]
  * -> out [B,S,K,3+D] = cat(xyz[idx] - new_xyz, points[idx]) when xyz_first != 0
  *                      cat(points[idx], xyz[idx] - new_xyz) otherwise (MSG order).
- * points may be channels-first ([B,D,N]) when points_cf != 0, saving the caller a transpose. */
+ * points may be channels-first ([B,D,N]) when points_cf != 0, saving the caller a transpose.
+ * pitch = row pitch of out in elements: 0 or 3+D for the dense layout; a larger value (e.g. 3+D
+ * rounded up to 8) appends zero columns so that the consuming GEMM sees 16-byte aligned rows. */
 int pcb_group_points_f32(const float *xyz, const float *points, const float *new_xyz,
                          const int64_t *idx, int B, int N, int S, int K, int D, int xyz_first,
-                         int points_cf, int clamp, float *out, pcb_stream_t stream);
+                         int points_cf, int clamp, int pitch, float *out, pcb_stream_t stream);
 /* backward w.r.t. points: grad_points ([B,N,D] or [B,D,N]) += scatter(grad_out[..., feature part]) */
 int pcb_group_points_bwd_f32(const float *grad_out, const int64_t *idx, int B, int N, int S, int K,
-                             int D, int xyz_first, int points_cf, int clamp, float *grad_points,
+                             int D, int xyz_first, int points_cf, int clamp, int pitch, float *grad_points,
                              pcb_stream_t stream);
 /* bf16 variants: the grouped tensor (and its gradient) in bf16, as the autocast GEMM consumes it;
  * inputs and grad_points stay fp32 */
 int pcb_group_points_bf16(const float *xyz, const float *points, const float *new_xyz,
                           const int64_t *idx, int B, int N, int S, int K, int D, int xyz_first,
-                          int points_cf, int clamp, void *out, pcb_stream_t stream);
+                          int points_cf, int clamp, int pitch, void *out, pcb_stream_t stream);
 int pcb_group_points_bwd_bf16(const void *grad_out, const int64_t *idx, int B, int N, int S, int K,
-                              int D, int xyz_first, int points_cf, int clamp, float *grad_points,
+                              int D, int xyz_first, int points_cf, int clamp, int pitch, float *grad_points,
                               pcb_stream_t stream);
 
 /* ---- a7  k nearest of xyz2 for each xyz1 point + inverse-distance weights
@@ -132,26 +134,28 @@ int pcb_graph_feature_bwd_f32(const float *grad_out, const int64_t *idx, int B, 
  *          pointnet_util.py:213-217, 273-279, 343-345; pointnet2_utils.py:150-154, 353-356
  * Activations y [M,C] are fp32 (dtype 0) or bf16 (dtype 1); C % 4 == 0; statistics fp32.
  * The 1x1-conv bias is NOT added to y: BN(y + b) == BN(y) for batch statistics, b only enters
- * the running mean (pcb_bn_finalize) -- so no bias-add / bias-gradient pass exists.
- * `sums` is a caller-provided fp32 scratch of 3*C*(1 + P) floats, P = ceil(M / max(64, ceil(M/592))):
- * the first 3*C floats receive the column sums, the rest holds per-CTA partials (two-stage reduction).
- *   pcb_bn_stats_rows : sums[0:C] = sum_r (y[r]-y[0]), sums[C:2C] = sum_r (y[r]-y[0])^2  (1 read of y)
- *   pcb_bn_finalize   : mean/invstd [C] of y from the sums; running_mean/var update (may be NULL)
- *   pcb_bn_apply_rows : out[r] = max_{k<pool_k} act((y[r*pool_k+k]-mean)*invstd*gamma+beta), argmax
- *                       [Mout,C] uint8 (may be NULL when pool_k == 1)        (1 read of y, 1 write)
- *   pcb_bn_bwd_rows   : sums[0:C] = sum dy, [C:2C] = sum dy*yhat, [2C:3C] = sum yhat, then
- *                       gy = gamma*invstd*(dy - sum_dy/M - yhat*sum_dy_yhat/M); gz is [M/pool_k, C]
- *                       (2 reads of gz and y, 1 write) */
-int pcb_bn_stats_rows(const void *y, int dtype, int64_t M, int C, float *sums, pcb_stream_t stream);
-int pcb_bn_finalize(const float *sums, const void *y, int dtype, const float *bias, int64_t M, int C, float eps,
-                    float momentum, float *running_mean, float *running_var, float *mean, float *invstd,
-                    pcb_stream_t stream);
-int pcb_bn_apply_rows(const void *y, int dtype, int64_t Mout, int C, int pool_k, const float *mean,
-                      const float *invstd, const float *gamma, const float *beta, int relu, void *out,
-                      unsigned char *argmax, pcb_stream_t stream);
+ * the running mean -- so no bias-add / bias-gradient pass exists.
+ * Each direction is ONE persistent cooperative kernel (column sums -> grid barrier -> fold ->
+ * grid barrier -> elementwise pass; the second read of y comes from L2).
+ * `work` is a caller-provided fp32 scratch of pcb_bn_work_floats(C) = 3*C*(1+592) floats: the first
+ * 3*C floats receive results, the rest holds per-CTA partial sums (deterministic two-stage reduction).
+ *   pcb_bn_fwd_rows : mean/invstd [C] of y (batch statistics, biased variance, eps); running_mean /
+ *                     running_var update with `momentum`, unbiased variance and the conv `bias` added
+ *                     to the mean (all three may be NULL);
+ *                     out[r] = max_{k<pool_k} act((y[r*pool_k+k]-mean)*invstd*gamma+beta), out is
+ *                     [M/pool_k, C]; argmax [M/pool_k, C] uint8 = winning k, first on ties (may be
+ *                     NULL when pool_k == 1); M % pool_k == 0, pool_k <= 255
+ *   pcb_bn_bwd_rows : gy = gamma*invstd*(dy - sum_dy/M - yhat*sum_dy_yhat/M) with dy = gz masked by the
+ *                     ReLU / argmax of the forward pass, gz is [M/pool_k, C];
+ *                     work[0:C] = sum dy (grad beta), work[C:2C] = sum dy*yhat (grad gamma),
+ *                     work[2C:3C] = gradient of the folded conv bias */
+int64_t pcb_bn_work_floats(int C);
+int pcb_bn_fwd_rows(const void *y, int dtype, int64_t M, int C, int pool_k, const float *bias, const float *gamma,
+                    const float *beta, float eps, float momentum, float *running_mean, float *running_var, int relu,
+                    float *mean, float *invstd, void *out, unsigned char *argmax, float *work, pcb_stream_t stream);
 int pcb_bn_bwd_rows(const void *gz, const void *y, const unsigned char *argmax, int dtype, int64_t M, int C,
                     int pool_k, const float *mean, const float *invstd, const float *gamma, const float *beta,
-                    int relu, float *sums, void *gy, pcb_stream_t stream);
+                    int relu, float *work, void *gy, pcb_stream_t stream);
 
 /* ---- a11 / section 8f rank 1: fused set-abstraction / EdgeConv block for inference
  *          pointnet_util.py:137-147, 203-217, 258-279; pointnet2_utils.py:140-154, 341-356;

@@ -26,10 +26,10 @@ _SIGNATURES = {
     "pcb_ball_query_f32": [_vp, _vp, _i, _i, _i, _f, _i, _vp, _vp],
     "pcb_gather_f32": [_vp, _vp, _i, _i, _i, _i64, _i, _vp, _vp, _vp],
     "pcb_gather_bwd_f32": [_vp, _vp, _i, _i, _i, _i64, _i, _vp, _vp],
-    "pcb_group_points_f32": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp],
-    "pcb_group_points_bwd_f32": [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp],
-    "pcb_group_points_bf16": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp],
-    "pcb_group_points_bwd_bf16": [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp],
+    "pcb_group_points_f32": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp],
+    "pcb_group_points_bwd_f32": [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp],
+    "pcb_group_points_bf16": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp],
+    "pcb_group_points_bwd_bf16": [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp],
     "pcb_three_nn_f32": [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp],
     "pcb_interpolate_f32": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp],
     "pcb_interpolate_bwd_f32": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp],
@@ -37,14 +37,12 @@ _SIGNATURES = {
     "pcb_knn_cdist_f32": [_vp, _i, _i, _i, _vp, _vp, _vp],
     "pcb_graph_feature_f32": [_vp, _vp, _i, _i, _i, _i, _vp, _vp],
     "pcb_graph_feature_bwd_f32": [_vp, _vp, _i, _i, _i, _i, _vp, _vp],
-    "pcb_bn_stats_rows": [_vp, _i, _i64, _i, _vp, _vp],
-    "pcb_bn_finalize": [_vp, _vp, _i, _vp, _i64, _i, _f, _f, _vp, _vp, _vp, _vp, _vp],
-    "pcb_bn_apply_rows": [_vp, _i, _i64, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp],
+    "pcb_bn_fwd_rows": [_vp, _i, _i64, _i, _i, _vp, _vp, _vp, _f, _f, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp],
     "pcb_sa_fused_bf16": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp, _f, _vp, _i, _vp],
     "pcb_bn_bwd_rows": [_vp, _vp, _vp, _i, _i64, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp],
 }
 
-EXPORTS = ["pcb_version", "pcb_error_string", *_SIGNATURES]
+EXPORTS = ["pcb_version", "pcb_error_string", "pcb_bn_work_floats", *_SIGNATURES]
 
 
 class PcbError(RuntimeError):
@@ -64,6 +62,8 @@ def lib():
         l.pcb_version.argtypes = []
         l.pcb_error_string.restype = ctypes.c_char_p
         l.pcb_error_string.argtypes = [_i]
+        l.pcb_bn_work_floats.restype = _i64
+        l.pcb_bn_work_floats.argtypes = [_i]
         for name, args in _SIGNATURES.items():
             fn = getattr(l, name)
             fn.restype = _i

@@ -4,18 +4,29 @@
 //  Partsize-identical/models/pointnet_util.py:213-217, 273-279, 343-345;
 //  Highway_bridge/models/pointnet2_utils.py:150-154, 353-356).
 // The training GEMM stays a library call in round 1; these kernels replace PyTorch's separate
-// statistics / transform / ReLU / max / threshold_backward / bias-sum passes with
-//   forward : stats (1 read) -> fold -> finalize (C threads) -> apply [+ReLU] [+max over K] (1 read, 1 write)
-//   backward: reduce (2 reads) -> fold -> apply (2 reads, 1 write)
-// All HBM-bound.  Activations may be fp32 or bf16 (autocast); statistics, affine parameters and
-// all arithmetic are fp32.  The convolution bias is folded in here (BN(xW + b) only needs b for
-// the running mean), so no separate bias-add or bias-gradient pass exists.
-// Column reductions are two-stage: every CTA stores its partial sums to parts[cta][NACC*C] with
-// plain stores and a small second kernel adds the <= 592 partials per column (one atomicAdd per
-// CTA per column serialised ~1000 same-address atomics in L2 and cost more than the read).
+// statistics / transform / ReLU / max / threshold_backward / bias-sum passes with ONE persistent
+// cooperative kernel per direction:
+//   forward : column sums of y -> grid sync -> fold + mean/invstd/running stats -> grid sync
+//             -> act(BN(y)) [+ max over K]        (y read twice, the second time from L2; 1 write)
+//   backward: column sums of dy, dy*yhat, yhat -> grid sync -> fold (+ conv-bias gradient)
+//             -> grid sync -> gy                  (y and gz read twice; 1 write)
+// A layer's activations (<= 67 MB bf16 here) fit the 126 MB L2, so the second read does not go to
+// HBM; one launch instead of seven per layer matters as much as the bytes, because the layers are
+// small (13 MB on average in the MSG train step: ~2 us of HBM time against ~4 us per launch).
+// Activations may be fp32 or bf16 (autocast); statistics, affine parameters and all arithmetic
+// are fp32.  The convolution bias is folded in here (BN(xW + b) only needs b for the running
+// mean), so no separate bias-add or bias-gradient pass exists.
+// Column reductions are two-stage and deterministic: every CTA stores its partial sums to
+// parts[cta][NACC*C] with plain stores; after the grid barrier one warp per channel adds the
+// <= 592 partials in a fixed order.
+#include <cooperative_groups.h>
 #include <cuda_bf16.h>
 
+#include <cstdlib>
+
 #include "pcb_common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace pcb {
 
@@ -23,16 +34,15 @@ constexpr int kBnThreads = 256;
 constexpr int kBnMaxParts = PCB_NUM_SMS * 4;
 
 // VecIO<T, V>: V consecutive channels per thread, one 16-byte access for (float,4) and (bf16,8),
-// one 8-byte access for (bf16,4).
+// one 8-byte access for (bf16,4).  ldraw/cvt split the load from its first use so that several
+// rows can be in flight per thread.
 template <typename T, int V>
 struct VecIO;
 template <>
 struct VecIO<float, 4> {
-    static __device__ __forceinline__ void load(const float *p, float v[4])
-    {
-        float4 t = __ldg(reinterpret_cast<const float4 *>(p));
-        v[0] = t.x, v[1] = t.y, v[2] = t.z, v[3] = t.w;
-    }
+    typedef float4 Raw;
+    static __device__ __forceinline__ Raw ldraw(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
+    static __device__ __forceinline__ void cvt(const Raw &t, float v[4]) { v[0] = t.x, v[1] = t.y, v[2] = t.z, v[3] = t.w; }
     static __device__ __forceinline__ void store(float *p, const float v[4])
     {
         *reinterpret_cast<float4 *>(p) = make_float4(v[0], v[1], v[2], v[3]);
@@ -40,12 +50,13 @@ struct VecIO<float, 4> {
 };
 template <>
 struct VecIO<__nv_bfloat16, 4> {
-    static __device__ __forceinline__ void load(const __nv_bfloat16 *p, float v[4])
+    typedef uint2 Raw;
+    static __device__ __forceinline__ Raw ldraw(const __nv_bfloat16 *p) { return __ldg(reinterpret_cast<const uint2 *>(p)); }
+    static __device__ __forceinline__ void cvt(const Raw &t, float v[4])
     {
-        uint2 t = __ldg(reinterpret_cast<const uint2 *>(p));
-        float2 fa = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162 *>(&t.x));
-        float2 fb = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162 *>(&t.y));
-        v[0] = fa.x, v[1] = fa.y, v[2] = fb.x, v[3] = fb.y;
+        // bf16 -> fp32 is a 16-bit shift
+        v[0] = __uint_as_float(t.x << 16), v[1] = __uint_as_float(t.x & 0xffff0000u);
+        v[2] = __uint_as_float(t.y << 16), v[3] = __uint_as_float(t.y & 0xffff0000u);
     }
     static __device__ __forceinline__ void store(__nv_bfloat16 *p, const float v[4])
     {
@@ -58,14 +69,15 @@ struct VecIO<__nv_bfloat16, 4> {
 };
 template <>
 struct VecIO<__nv_bfloat16, 8> {
-    static __device__ __forceinline__ void load(const __nv_bfloat16 *p, float v[8])
+    typedef uint4 Raw;
+    static __device__ __forceinline__ Raw ldraw(const __nv_bfloat16 *p) { return __ldg(reinterpret_cast<const uint4 *>(p)); }
+    static __device__ __forceinline__ void cvt(const Raw &t, float v[8])
     {
-        uint4 t = __ldg(reinterpret_cast<const uint4 *>(p));
-        unsigned w[4] = {t.x, t.y, t.z, t.w};
+        const unsigned w[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            float2 f = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162 *>(&w[i]));
-            v[2 * i] = f.x, v[2 * i + 1] = f.y;
+            v[2 * i] = __uint_as_float(w[i] << 16);
+            v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
         }
     }
     static __device__ __forceinline__ void store(__nv_bfloat16 *p, const float v[8])
@@ -80,50 +92,100 @@ struct VecIO<__nv_bfloat16, 8> {
     }
 };
 
+// V one-byte argmax entries in one 4- or 8-byte access
+template <int V>
+struct AmIO;
+template <>
+struct AmIO<8> {
+    typedef uint2 Raw;
+    static __device__ __forceinline__ Raw ld(const unsigned char *p) { return *reinterpret_cast<const uint2 *>(p); }
+    static __device__ __forceinline__ int get(const Raw &t, int i) { return (int)(((i < 4 ? t.x : t.y) >> (8 * (i & 3))) & 0xffu); }
+    static __device__ __forceinline__ void st(unsigned char *p, const int bi[8])
+    {
+        unsigned w[2] = {0u, 0u};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) w[i >> 2] |= (unsigned)(bi[i] & 0xff) << (8 * (i & 3));
+        *reinterpret_cast<uint2 *>(p) = make_uint2(w[0], w[1]);
+    }
+};
+template <>
+struct AmIO<4> {
+    typedef unsigned Raw;
+    static __device__ __forceinline__ Raw ld(const unsigned char *p) { return *reinterpret_cast<const unsigned *>(p); }
+    static __device__ __forceinline__ int get(const Raw &t, int i) { return (int)((t >> (8 * i)) & 0xffu); }
+    static __device__ __forceinline__ void st(unsigned char *p, const int bi[4])
+    {
+        unsigned w = 0u;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) w |= (unsigned)(bi[i] & 0xff) << (8 * i);
+        *reinterpret_cast<unsigned *>(p) = w;
+    }
+};
+
 // ---------------------------------------------------------------------------------------------
-// Column reduction skeleton.  threadIdx.x % TX walks the C/V channel groups, threadIdx.x / TX
-// walks rows; a CTA covers `rows_per_cta` consecutive rows and stores NACC*C partial sums.
-// f(row, c, acc[NACC][V]) accumulates the V channels of one row.
+// Skeletons.  threadIdx.x % TX owns one group of V channels (per-channel constants are loaded
+// once per group by f.init), threadIdx.x / TX walks "units" (rows, or pooling groups of pool_k
+// rows).  U units are loaded (f.load -> Pack) before the first is consumed.
 // ---------------------------------------------------------------------------------------------
-template <int NACC, int V, typename F>
-__device__ __forceinline__ void column_reduce(int64_t M, int C, int64_t rows_per_cta, float *__restrict__ parts, F f)
+struct Lanes {
+    int CV, TX, TY, tx, ty;
+    __device__ __forceinline__ Lanes(int C, int V)
+    {
+        CV = C / V;
+        TX = CV < kBnThreads ? CV : kBnThreads;
+        TY = kBnThreads / TX;
+        tx = threadIdx.x % TX;
+        ty = threadIdx.x / TX;
+    }
+};
+
+// column sums over the units [blockIdx.x * upc, +upc) -> parts[blockIdx.x][NACC * C]
+template <int NACC, int V, int U, typename F>
+__device__ __forceinline__ void column_reduce(F &f, int64_t units, int C, int64_t upc, float *__restrict__ parts,
+                                              float (*s_part)[kBnThreads][V])
 {
-    __shared__ float s_part[NACC][kBnThreads][V];
-    const int CV = C / V;
-    const int TX = CV < kBnThreads ? CV : kBnThreads;
-    const int TY = kBnThreads / TX;
-    const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
-    const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta;
-    const int64_t r1 = r0 + rows_per_cta < M ? r0 + rows_per_cta : M;
+    const Lanes L(C, V);
+    const int64_t u0 = (int64_t)blockIdx.x * upc;
+    const int64_t u1 = u0 + upc < units ? u0 + upc : units;
     // channel groups of one row sit on lanes tx, tx+TX, ...: when TX is a power of two <= 32 the
     // row partials of a warp are folded with shuffles first
-    const bool warp_fold = TX <= 32 && (TX & (TX - 1)) == 0;
+    const bool warp_fold = L.TX <= 32 && (L.TX & (L.TX - 1)) == 0;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float *my_parts = parts + (size_t)blockIdx.x * NACC * C;
-    for (int cg = tx; cg < CV; cg += TX) {
+    for (int cg0 = 0; cg0 < L.CV; cg0 += L.TX) {
+        const int cgi = cg0 + L.tx;
+        const int c = cgi * V;
         float acc[NACC][V];
 #pragma unroll
         for (int a = 0; a < NACC; ++a)
 #pragma unroll
             for (int v = 0; v < V; ++v) acc[a][v] = 0.f;
-        if (ty < TY) {
-#pragma unroll 4
-            for (int64_t r = r0 + ty; r < r1; r += TY) f(r, cg * V, acc);
+        if (L.ty < L.TY && cgi < L.CV) {
+            f.init(c);
+            for (int64_t u = u0 + L.ty; u < u1; u += (int64_t)U * L.TY) {
+                typename F::Pack p[U];
+#pragma unroll
+                for (int j = 0; j < U; ++j)
+                    if (u + j * L.TY < u1) p[j] = f.load(u + j * L.TY, c);
+#pragma unroll
+                for (int j = 0; j < U; ++j)
+                    if (u + j * L.TY < u1) f.use(p[j], u + j * L.TY, c, acc);
+            }
         }
         if (warp_fold) {
-            for (int off = TX; off < 32; off <<= 1)
+            for (int off = L.TX; off < 32; off <<= 1)
 #pragma unroll
                 for (int a = 0; a < NACC; ++a)
 #pragma unroll
                     for (int v = 0; v < V; ++v) acc[a][v] += __shfl_xor_sync(PCB_FULL_MASK, acc[a][v], off);
-            if (lane < TX) {
+            if (lane < L.TX) {
 #pragma unroll
                 for (int a = 0; a < NACC; ++a)
 #pragma unroll
                     for (int v = 0; v < V; ++v) s_part[a][warp * 32 + lane][v] = acc[a][v];
             }
             __syncthreads();
-            if (threadIdx.x < TX) {
+            if (threadIdx.x < L.TX && cgi < L.CV) {
 #pragma unroll
                 for (int a = 0; a < NACC; ++a)
 #pragma unroll
@@ -131,7 +193,7 @@ __device__ __forceinline__ void column_reduce(int64_t M, int C, int64_t rows_per
                         float s = 0.f;
 #pragma unroll
                         for (int w = 0; w < kBnThreads / 32; ++w) s += s_part[a][w * 32 + threadIdx.x][v];
-                        my_parts[(size_t)a * C + cg * V + v] = s;
+                        my_parts[(size_t)a * C + c + v] = s;
                     }
             }
         } else {
@@ -140,14 +202,14 @@ __device__ __forceinline__ void column_reduce(int64_t M, int C, int64_t rows_per
 #pragma unroll
                 for (int v = 0; v < V; ++v) s_part[a][threadIdx.x][v] = acc[a][v];
             __syncthreads();
-            if (ty == 0) {
+            if (L.ty == 0 && cgi < L.CV) {
 #pragma unroll
                 for (int a = 0; a < NACC; ++a)
 #pragma unroll
                     for (int v = 0; v < V; ++v) {
                         float s = 0.f;
-                        for (int y = 0; y < TY; ++y) s += s_part[a][y * TX + tx][v];
-                        my_parts[(size_t)a * C + cg * V + v] = s;
+                        for (int y = 0; y < L.TY; ++y) s += s_part[a][y * L.TX + L.tx][v];
+                        my_parts[(size_t)a * C + c + v] = s;
                     }
             }
         }
@@ -155,319 +217,527 @@ __device__ __forceinline__ void column_reduce(int64_t M, int C, int64_t rows_per
     }
 }
 
-// sums[c] = sum over parts of parts[part][c]: 32 columns x 8 part-lanes per block (the sum over
-// <= 592 partials is latency-bound, so it is spread over 8 threads per column, 4 loads in flight)
-__global__ void __launch_bounds__(256)
-bn_fold_parts_kernel(const float *__restrict__ parts, int nparts, int ncols, float *__restrict__ sums)
+// elementwise pass over all units, grid-strided
+template <int V, int U, typename F>
+__device__ __forceinline__ void row_stream(F &f, int64_t units, int C)
 {
-    __shared__ float s_acc[8][33];
-    const int cl = threadIdx.x & 31, pl = threadIdx.x >> 5;
-    const int c = blockIdx.x * 32 + cl;
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-    if (c < ncols) {
-        int i = pl;
-        for (; i + 24 < nparts; i += 32) {
-            s0 += parts[(size_t)i * ncols + c];
-            s1 += parts[(size_t)(i + 8) * ncols + c];
-            s2 += parts[(size_t)(i + 16) * ncols + c];
-            s3 += parts[(size_t)(i + 24) * ncols + c];
-        }
-        for (; i < nparts; i += 8) s0 += parts[(size_t)i * ncols + c];
-    }
-    s_acc[pl][cl] = (s0 + s1) + (s2 + s3);
-    __syncthreads();
-    if (pl == 0 && c < ncols) {
-        float s = 0.f;
+    const Lanes L(C, V);
+    if (L.ty >= L.TY) return;
+    const int64_t stride = (int64_t)gridDim.x * L.TY;
+    for (int cgi = L.tx; cgi < L.CV; cgi += L.TX) {
+        const int c = cgi * V;
+        f.init(c);
+        for (int64_t u = (int64_t)blockIdx.x * L.TY + L.ty; u < units; u += U * stride) {
+            typename F::Pack p[U];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) s += s_acc[j][cl];
-        sums[c] = s;
+            for (int j = 0; j < U; ++j)
+                if (u + j * stride < units) p[j] = f.load(u + j * stride, c);
+#pragma unroll
+            for (int j = 0; j < U; ++j)
+                if (u + j * stride < units) f.emit(p[j], u + j * stride, c);
+        }
     }
 }
 
-// stats: parts -> sum_rows (y - y[0]) and sum_rows (y - y[0])^2 (shifted: no cancellation when
-// |mean| >> std)
-template <typename T, int V>
-__global__ void __launch_bounds__(kBnThreads)
-bn_stats_kernel(const T *__restrict__ y, int64_t M, int C, int64_t rows_per_cta, float *__restrict__ parts)
+// sum over the CTA partials of the NACC accumulators of channel c (one warp; fixed order)
+template <int NACC>
+__device__ __forceinline__ void fold_channel(const float *parts, int nparts, int C, int c, float s[NACC])
 {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int a = 0; a < NACC; ++a) s[a] = 0.f;
+#pragma unroll 4
+    for (int i = lane; i < nparts; i += 32)
+#pragma unroll
+        for (int a = 0; a < NACC; ++a) s[a] += __ldcg(parts + ((size_t)i * NACC + a) * C + c);
+#pragma unroll
+    for (int a = 0; a < NACC; ++a)
+#pragma unroll
+        for (int off = 16; off; off >>= 1) s[a] += __shfl_xor_sync(PCB_FULL_MASK, s[a], off);
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------------------------
+// sum_rows (y - y[0]) and sum_rows (y - y[0])^2 (shifted: no cancellation when |mean| >> std)
+template <typename T, int V>
+struct FwdStats {
+    typedef typename VecIO<T, V>::Raw Pack;
+    const T *y;
+    int C;
     float s[V];
-    int s_c = -1;
-    column_reduce<2, V>(M, C, rows_per_cta, parts, [&](int64_t r, int c, float acc[2][V]) {
+    __device__ __forceinline__ void init(int c) { VecIO<T, V>::cvt(VecIO<T, V>::ldraw(y + c), s); }
+    __device__ __forceinline__ Pack load(int64_t r, int c) const { return VecIO<T, V>::ldraw(y + r * C + c); }
+    __device__ __forceinline__ void use(const Pack &p, int64_t, int, float acc[2][V]) const
+    {
         float v[V];
-        VecIO<T, V>::load(y + r * C + c, v);
-        if (c != s_c) {                                   // shift = first row, loaded once per channel group
-            VecIO<T, V>::load(y + c, s);
-            s_c = c;
-        }
+        VecIO<T, V>::cvt(p, v);
 #pragma unroll
         for (int i = 0; i < V; ++i) {
             const float d = v[i] - s[i];
             acc[0][i] += d;
             acc[1][i] += d * d;
         }
-    });
-}
-
-// finalize: mean / invstd of y from the shifted sums; running statistics update (momentum,
-// unbiased variance, conv bias added to the running mean) as torch.nn.functional.batch_norm does.
-template <typename T>
-__global__ void bn_finalize_kernel(const float *__restrict__ sums, const T *__restrict__ y, const float *__restrict__ bias,
-                                   int64_t M, int C, float eps, float momentum, float *__restrict__ running_mean,
-                                   float *__restrict__ running_var, float *__restrict__ mean, float *__restrict__ invstd)
-{
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
-    const float shift = (float)y[c];
-    const float m1 = sums[c] / (float)M;
-    const float var = fmaxf(sums[C + c] / (float)M - m1 * m1, 0.f);
-    const float mu = shift + m1;                          // mean of the bias-free pre-activation
-    mean[c] = mu;
-    invstd[c] = rsqrtf(var + eps);
-    if (running_mean) {
-        const float b = bias ? bias[c] : 0.f;
-        running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (mu + b);
-        const float unbiased = M > 1 ? var * ((float)M / (float)(M - 1)) : var;
-        running_var[c] = (1.f - momentum) * running_var[c] + momentum * unbiased;
     }
-}
+};
 
-// apply: z = act((y - mean) * invstd * gamma + beta); pool_k > 1: out[r] = max_k z[r*pool_k + k]
-// with the winning k (first on ties, as torch.max) stored for the backward pass.
+// z = act(y * sc + sh), sc = invstd * gamma, sh = beta - mean * sc
 template <typename T, int V>
-__global__ void __launch_bounds__(kBnThreads)
-bn_apply_kernel(const T *__restrict__ y, unsigned total, int C, FastDiv dCV, int pool_k, const float *__restrict__ mean,
-                const float *__restrict__ invstd, const float *__restrict__ gamma, const float *__restrict__ beta,
-                int relu, T *__restrict__ out, unsigned char *__restrict__ argmax)
-{
-    const unsigned t = blockIdx.x * kBnThreads + threadIdx.x;
-    if (t >= total) return;
-    const int64_t r = dCV.div(t);
-    const int c = (int)(t - (unsigned)r * dCV.d) * V;
-    float sc[V], sh[V], best[V];
-    int bi[V];
-#pragma unroll
-    for (int i = 0; i < V; ++i) {
-        sc[i] = invstd[c + i] * gamma[c + i];
-        sh[i] = beta[c + i] - mean[c + i] * sc[i];
-        bi[i] = 0;
-        best[i] = 0.f;
-    }
-#pragma unroll 4
-    for (int k = 0; k < pool_k; ++k) {
-        float v[V];
-        VecIO<T, V>::load(y + (r * pool_k + k) * C + c, v);
+struct FwdApply {
+    typedef typename VecIO<T, V>::Raw Pack;
+    const T *y;
+    T *out;
+    const float *mean, *invstd, *gamma, *beta;
+    int C, relu;
+    float sc[V], sh[V];
+    __device__ __forceinline__ void init(int c)
+    {
 #pragma unroll
         for (int i = 0; i < V; ++i) {
-            float z = fmaf(v[i], sc[i], sh[i]);
-            if (relu) z = fmaxf(z, 0.f);
-            if (k == 0 || z > best[i]) {
-                best[i] = z;
-                bi[i] = k;
+            sc[i] = __ldcg(invstd + c + i) * gamma[c + i];
+            sh[i] = beta[c + i] - __ldcg(mean + c + i) * sc[i];
+        }
+    }
+    __device__ __forceinline__ Pack load(int64_t r, int c) const { return VecIO<T, V>::ldraw(y + r * C + c); }
+    __device__ __forceinline__ void emit(const Pack &p, int64_t r, int c) const
+    {
+        float v[V];
+        VecIO<T, V>::cvt(p, v);
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+            v[i] = fmaf(v[i], sc[i], sh[i]);
+            if (relu) v[i] = fmaxf(v[i], 0.f);
+        }
+        VecIO<T, V>::store(out + r * C + c, v);
+    }
+};
+
+// out[g] = max_k z[g * pool_k + k]; the winning k (first on ties, as torch.max) goes to argmax
+template <typename T, int V, int KB>
+struct FwdApplyPooled : FwdApply<T, V> {
+    struct Pack {};
+    unsigned char *argmax;
+    int pool_k;
+    __device__ __forceinline__ Pack load(int64_t, int) const { return Pack(); }
+    __device__ __forceinline__ void emit(const Pack &, int64_t g, int c) const
+    {
+        float best[V];
+        int bi[V];
+#pragma unroll
+        for (int i = 0; i < V; ++i) best[i] = 0.f, bi[i] = 0;
+        const T *row = this->y + (g * pool_k) * this->C + c;
+        for (int k0 = 0; k0 < pool_k; k0 += KB) {
+            typename VecIO<T, V>::Raw t[KB];
+#pragma unroll
+            for (int j = 0; j < KB; ++j)
+                if (k0 + j < pool_k) t[j] = VecIO<T, V>::ldraw(row + (size_t)(k0 + j) * this->C);
+#pragma unroll
+            for (int j = 0; j < KB; ++j)
+                if (k0 + j < pool_k) {
+                    float v[V];
+                    VecIO<T, V>::cvt(t[j], v);
+#pragma unroll
+                    for (int i = 0; i < V; ++i) {
+                        float z = fmaf(v[i], this->sc[i], this->sh[i]);
+                        if (this->relu) z = fmaxf(z, 0.f);
+                        if (k0 + j == 0 || z > best[i]) best[i] = z, bi[i] = k0 + j;
+                    }
+                }
+        }
+        VecIO<T, V>::store(this->out + g * this->C + c, best);
+        if (argmax) AmIO<V>::st(argmax + g * this->C + c, bi);
+    }
+};
+
+struct BnFwdArgs {
+    const void *y;
+    void *out;
+    unsigned char *argmax;
+    const float *bias, *gamma, *beta;
+    float *running_mean, *running_var, *mean, *invstd, *work;
+    int64_t M, upc;
+    int C, pool_k, relu, nparts;
+    float eps, momentum;
+    int dbg;
+};
+
+template <typename T, int V>
+__global__ void __launch_bounds__(kBnThreads)
+bn_fwd_fused_kernel(const BnFwdArgs a)
+{
+    cg::grid_group grid = cg::this_grid();
+    const T *y = (const T *)a.y;
+    const int C = a.C;
+    float *parts = a.work + 3 * (size_t)C;
+    __shared__ float s_part[2][kBnThreads][V];
+    if ((int)blockIdx.x < a.nparts && !(a.dbg & 2)) {
+        FwdStats<T, V> f;
+        f.y = y, f.C = C;
+        column_reduce<2, V, 4>(f, a.M, C, a.upc, parts, s_part);
+    }
+    if (!(a.dbg & 1)) grid.sync();
+    // mean / invstd of y from the shifted sums; running statistics update (momentum, unbiased
+    // variance, conv bias added to the running mean) as torch.nn.functional.batch_norm does
+    {
+        const int lane = threadIdx.x & 31;
+        const int nw = gridDim.x * (kBnThreads / 32);
+        for (int c = blockIdx.x * (kBnThreads / 32) + (threadIdx.x >> 5); c < C; c += nw) {
+            float s[2];
+            fold_channel<2>(parts, a.nparts, C, c, s);
+            if (lane == 0) {
+                const float M = (float)a.M;
+                const float shift = (float)y[c];
+                const float m1 = s[0] / M;
+                const float var = fmaxf(s[1] / M - m1 * m1, 0.f);
+                const float mu = shift + m1;                  // mean of the bias-free pre-activation
+                a.mean[c] = mu;
+                a.invstd[c] = rsqrtf(var + a.eps);
+                if (a.running_mean) {
+                    const float b = a.bias ? a.bias[c] : 0.f;
+                    a.running_mean[c] = (1.f - a.momentum) * a.running_mean[c] + a.momentum * (mu + b);
+                    const float unbiased = a.M > 1 ? var * (M / (float)(a.M - 1)) : var;
+                    a.running_var[c] = (1.f - a.momentum) * a.running_var[c] + a.momentum * unbiased;
+                }
             }
         }
     }
-    VecIO<T, V>::store(out + r * C + c, best);
-    if (argmax) {
-        unsigned w[2] = {0u, 0u};
-#pragma unroll
-        for (int i = 0; i < V; ++i) w[i >> 2] |= (unsigned)(bi[i] & 0xff) << (8 * (i & 3));
-        if (V == 8)
-            *reinterpret_cast<uint2 *>(argmax + r * C + c) = make_uint2(w[0], w[1]);
-        else
-            *reinterpret_cast<unsigned *>(argmax + r * C + c) = w[0];
+    if (!(a.dbg & 1)) grid.sync();
+    if (a.dbg & 4) return;
+    if (a.pool_k > 1) {
+        FwdApplyPooled<T, V, 8> f;
+        f.y = y, f.out = (T *)a.out, f.mean = a.mean, f.invstd = a.invstd, f.gamma = a.gamma, f.beta = a.beta;
+        f.C = C, f.relu = a.relu, f.argmax = a.argmax, f.pool_k = a.pool_k;
+        row_stream<V, 1>(f, a.M / a.pool_k, C);
+    } else {
+        FwdApply<T, V> f;
+        f.y = y, f.out = (T *)a.out, f.mean = a.mean, f.invstd = a.invstd, f.gamma = a.gamma, f.beta = a.beta;
+        f.C = C, f.relu = a.relu;
+        row_stream<V, 4>(f, a.M, C);
     }
 }
 
-// backward.  dy(row) = gz(row) * [act passes]  (pooled: gz of the group, only for the winning k)
+// ---------------------------------------------------------------------------------------------
+// backward.  dy(row) = gz(row) * [act passes]  (pooled: gz of the group, only for the winning k);
+// yhat = (y - mean) * invstd;  gy = gamma * invstd * (dy - sum_dy / M - yhat * sum_dy_yhat / M)
+// ---------------------------------------------------------------------------------------------
 template <typename T, int V>
-__device__ __forceinline__ void load_dy(const T *__restrict__ gz, const T *__restrict__ y,
-                                        const unsigned char *__restrict__ argmax, int64_t r, int c, int C, FastDiv dK,
-                                        const float *__restrict__ mean, const float *__restrict__ invstd,
-                                        const float *__restrict__ gamma, const float *__restrict__ beta, int relu,
-                                        float dy[V], float yh[V])
-{
-    float v[V], g[V];
-    VecIO<T, V>::load(y + r * C + c, v);
-    const int pool_k = (int)dK.d;
-    const int64_t rg = pool_k > 1 ? (int64_t)dK.div((unsigned)r) : r;
-    VecIO<T, V>::load(gz + rg * C + c, g);
-    const int k = (int)(r - rg * pool_k);
-    unsigned char am[V];
-    if (pool_k > 1) {                                      // V winners in one 4- or 8-byte load
-        if (V == 8) {
-            const uint2 t = __ldg(reinterpret_cast<const uint2 *>(argmax + rg * C + c));
-            const unsigned w[2] = {t.x, t.y};
+struct BwdBase {
+    const T *y, *gz;
+    const unsigned char *argmax;
+    T *gy;
+    const float *mean, *invstd, *gamma, *beta, *sums;
+    int C, relu, pool_k;
+    float invM;
+    float m[V], is[V], sc[V], sh[V], a0[V], a1[V];
+    __device__ __forceinline__ void consts(int c, bool with_sums)
+    {
 #pragma unroll
-            for (int i = 0; i < V; ++i) am[i] = (unsigned char)(w[i >> 2] >> (8 * (i & 3)));
-        } else {
-            const unsigned t = __ldg(reinterpret_cast<const unsigned *>(argmax + rg * C + c));
-#pragma unroll
-            for (int i = 0; i < V; ++i) am[i] = (unsigned char)(t >> (8 * (i & 3)));
+        for (int i = 0; i < V; ++i) {
+            m[i] = mean[c + i];
+            is[i] = invstd[c + i];
+            sc[i] = is[i] * gamma[c + i];                     // same expressions as the forward pass
+            sh[i] = beta[c + i] - m[i] * sc[i];
+            if (with_sums) {
+                a0[i] = __ldcg(sums + c + i) * invM;
+                a1[i] = __ldcg(sums + C + c + i) * invM;
+            }
         }
     }
+    // one row: dy and yhat from the raw y / gz values; k < 0: no pooling
+    __device__ __forceinline__ void row(const typename VecIO<T, V>::Raw &yr, const float g[V],
+                                        const typename AmIO<V>::Raw &am, int k, float dy[V], float yh[V]) const
+    {
+        float v[V];
+        VecIO<T, V>::cvt(yr, v);
 #pragma unroll
-    for (int i = 0; i < V; ++i) {
-        yh[i] = (v[i] - mean[c + i]) * invstd[c + i];
-        const float sc = invstd[c + i] * gamma[c + i];     // same expression as the forward pass
-        const float z = fmaf(v[i], sc, beta[c + i] - mean[c + i] * sc);
-        bool pass = !relu || z > 0.f;
-        if (pool_k > 1) pass = pass && (k == (int)am[i]);
-        dy[i] = pass ? g[i] : 0.f;
+        for (int i = 0; i < V; ++i) {
+            yh[i] = (v[i] - m[i]) * is[i];
+            const float z = fmaf(v[i], sc[i], sh[i]);
+            bool pass = !relu || z > 0.f;
+            if (k >= 0) pass = pass && (k == AmIO<V>::get(am, i));
+            dy[i] = pass ? g[i] : 0.f;
+        }
     }
-}
-
-// reduce: parts -> sum dy, sum dy * yhat, sum yhat
-template <typename T, int V>
-__global__ void __launch_bounds__(kBnThreads)
-bn_bwd_reduce_kernel(const T *__restrict__ gz, const T *__restrict__ y, const unsigned char *__restrict__ argmax,
-                     int64_t M, int C, FastDiv dK, int64_t rows_per_cta, const float *__restrict__ mean,
-                     const float *__restrict__ invstd, const float *__restrict__ gamma, const float *__restrict__ beta,
-                     int relu, float *__restrict__ parts)
-{
-    column_reduce<3, V>(M, C, rows_per_cta, parts, [&](int64_t r, int c, float acc[3][V]) {
-        float dy[V], yh[V];
-        load_dy<T, V>(gz, y, argmax, r, c, C, dK, mean, invstd, gamma, beta, relu, dy, yh);
+    __device__ __forceinline__ void accumulate(const float dy[V], const float yh[V], float acc[3][V]) const
+    {
 #pragma unroll
         for (int i = 0; i < V; ++i) {
             acc[0][i] += dy[i];
             acc[1][i] += dy[i] * yh[i];
             acc[2][i] += yh[i];
         }
-    });
+    }
+    __device__ __forceinline__ void write(int64_t r, int c, const float dy[V], const float yh[V]) const
+    {
+        float o[V];
+#pragma unroll
+        for (int i = 0; i < V; ++i) o[i] = sc[i] * (dy[i] - a0[i] - yh[i] * a1[i]);
+        VecIO<T, V>::store(gy + r * C + c, o);
+    }
+};
+
+// unit = row
+template <typename T, int V, bool APPLY>
+struct BwdRows : BwdBase<T, V> {
+    struct Pack {
+        typename VecIO<T, V>::Raw y, g;
+    };
+    __device__ __forceinline__ void init(int c) { this->consts(c, APPLY); }
+    __device__ __forceinline__ Pack load(int64_t r, int c) const
+    {
+        Pack p;
+        p.y = VecIO<T, V>::ldraw(this->y + r * this->C + c);
+        p.g = VecIO<T, V>::ldraw(this->gz + r * this->C + c);
+        return p;
+    }
+    __device__ __forceinline__ void use(const Pack &p, int64_t, int, float acc[3][V]) const
+    {
+        float g[V], dy[V], yh[V];
+        VecIO<T, V>::cvt(p.g, g);
+        this->row(p.y, g, typename AmIO<V>::Raw(), -1, dy, yh);
+        this->accumulate(dy, yh, acc);
+    }
+    __device__ __forceinline__ void emit(const Pack &p, int64_t r, int c) const
+    {
+        float g[V], dy[V], yh[V];
+        VecIO<T, V>::cvt(p.g, g);
+        this->row(p.y, g, typename AmIO<V>::Raw(), -1, dy, yh);
+        this->write(r, c, dy, yh);
+    }
+};
+
+// unit = pooling group of pool_k consecutive rows sharing one gz row and one argmax row
+template <typename T, int V, bool APPLY, int KB>
+struct BwdGroups : BwdBase<T, V> {
+    struct Pack {
+        typename VecIO<T, V>::Raw g;
+        typename AmIO<V>::Raw am;
+    };
+    __device__ __forceinline__ void init(int c) { this->consts(c, APPLY); }
+    __device__ __forceinline__ Pack load(int64_t g, int c) const
+    {
+        Pack p;
+        p.g = VecIO<T, V>::ldraw(this->gz + g * this->C + c);
+        p.am = AmIO<V>::ld(this->argmax + g * this->C + c);
+        return p;
+    }
+    template <typename Sink>
+    __device__ __forceinline__ void walk(const Pack &p, int64_t grp, int c, Sink sink) const
+    {
+        float g[V];
+        VecIO<T, V>::cvt(p.g, g);
+        const int64_t r0 = grp * this->pool_k;
+        const T *row = this->y + r0 * this->C + c;
+        for (int k0 = 0; k0 < this->pool_k; k0 += KB) {
+            typename VecIO<T, V>::Raw t[KB];
+#pragma unroll
+            for (int j = 0; j < KB; ++j)
+                if (k0 + j < this->pool_k) t[j] = VecIO<T, V>::ldraw(row + (size_t)(k0 + j) * this->C);
+#pragma unroll
+            for (int j = 0; j < KB; ++j)
+                if (k0 + j < this->pool_k) {
+                    float dy[V], yh[V];
+                    this->row(t[j], g, p.am, k0 + j, dy, yh);
+                    sink(r0 + k0 + j, dy, yh);
+                }
+        }
+    }
+    __device__ __forceinline__ void use(const Pack &p, int64_t grp, int c, float acc[3][V]) const
+    {
+        walk(p, grp, c, [&](int64_t, const float *dy, const float *yh) { this->accumulate(dy, yh, acc); });
+    }
+    __device__ __forceinline__ void emit(const Pack &p, int64_t grp, int c) const
+    {
+        walk(p, grp, c, [&](int64_t r, const float *dy, const float *yh) { this->write(r, c, dy, yh); });
+    }
+};
+
+struct BnBwdArgs {
+    const void *gz, *y;
+    const unsigned char *argmax;
+    void *gy;
+    const float *mean, *invstd, *gamma, *beta;
+    float *work;
+    int64_t M, upc;
+    int C, pool_k, relu, nparts;
+    int dbg;
+};
+
+template <typename T, int V, typename F>
+__device__ __forceinline__ void bwd_fill(F &f, const BnBwdArgs &a)
+{
+    f.y = (const T *)a.y, f.gz = (const T *)a.gz, f.argmax = a.argmax, f.gy = (T *)a.gy;
+    f.mean = a.mean, f.invstd = a.invstd, f.gamma = a.gamma, f.beta = a.beta, f.sums = a.work;
+    f.C = a.C, f.relu = a.relu, f.pool_k = a.pool_k, f.invM = 1.f / (float)a.M;
 }
 
-// apply: gy = gamma * invstd * (dy - sum_dy / M - yhat * sum_dy_yhat / M)
 template <typename T, int V>
 __global__ void __launch_bounds__(kBnThreads)
-bn_bwd_apply_kernel(const T *__restrict__ gz, const T *__restrict__ y, const unsigned char *__restrict__ argmax,
-                    int64_t M, unsigned total, int C, FastDiv dCV, FastDiv dK, const float *__restrict__ mean,
-                    const float *__restrict__ invstd, const float *__restrict__ gamma, const float *__restrict__ beta,
-                    int relu, const float *__restrict__ sums, T *__restrict__ gy)
+bn_bwd_fused_kernel(const BnBwdArgs a)
 {
-    const unsigned t = blockIdx.x * kBnThreads + threadIdx.x;
-    if (t >= total) return;
-    const int64_t r = dCV.div(t);
-    const int c = (int)(t - (unsigned)r * dCV.d) * V;
-    float dy[V], yh[V], o[V];
-    load_dy<T, V>(gz, y, argmax, r, c, C, dK, mean, invstd, gamma, beta, relu, dy, yh);
-    const float invM = 1.f / (float)M;
-#pragma unroll
-    for (int i = 0; i < V; ++i)
-        o[i] = gamma[c + i] * invstd[c + i] * (dy[i] - sums[c + i] * invM - yh[i] * sums[C + c + i] * invM);
-    VecIO<T, V>::store(gy + r * C + c, o);
+    cg::grid_group grid = cg::this_grid();
+    const int C = a.C;
+    float *parts = a.work + 3 * (size_t)C;
+    const bool pooled = a.pool_k > 1;
+    __shared__ float s_part[3][kBnThreads][V];
+    if ((int)blockIdx.x < a.nparts && !(a.dbg & 2)) {
+        if (pooled) {
+            BwdGroups<T, V, false, 4> f;
+            bwd_fill<T, V>(f, a);
+            column_reduce<3, V, 1>(f, a.M / a.pool_k, C, a.upc, parts, s_part);
+        } else {
+            BwdRows<T, V, false> f;
+            bwd_fill<T, V>(f, a);
+            column_reduce<3, V, 4>(f, a.M, C, a.upc, parts, s_part);
+        }
+    }
+    if (!(a.dbg & 1)) grid.sync();
+    // work[0:C] = sum dy (= grad beta), [C:2C] = sum dy*yhat (= grad gamma), [2C:3C] = gradient of
+    // the folded conv bias = sum_rows gy = -gamma*invstd * (sum yhat) * (sum dy*yhat) / M
+    {
+        const int lane = threadIdx.x & 31;
+        const int nw = gridDim.x * (kBnThreads / 32);
+        for (int c = blockIdx.x * (kBnThreads / 32) + (threadIdx.x >> 5); c < C; c += nw) {
+            float s[3];
+            fold_channel<3>(parts, a.nparts, C, c, s);
+            if (lane == 0) {
+                a.work[c] = s[0];
+                a.work[C + c] = s[1];
+                a.work[2 * C + c] = -(a.gamma[c] * a.invstd[c]) * s[2] * s[1] / (float)a.M;
+            }
+        }
+    }
+    if (!(a.dbg & 1)) grid.sync();
+    if (a.dbg & 4) return;
+    if (pooled) {
+        BwdGroups<T, V, true, 4> f;
+        bwd_fill<T, V>(f, a);
+        row_stream<V, 1>(f, a.M / a.pool_k, C);
+    } else {
+        BwdRows<T, V, true> f;
+        bwd_fill<T, V>(f, a);
+        row_stream<V, 4>(f, a.M, C);
+    }
 }
 
-// rows per CTA such that at most kBnMaxParts CTAs (and partial rows) exist
-static inline int64_t rows_per_cta_for(int64_t M)
+// ---------------------------------------------------------------------------------------------
+// launch
+// ---------------------------------------------------------------------------------------------
+// co-resident CTAs of `kernel` on the current device (cooperative launch limit), capped at
+// PCB_BN_CTAS_PER_SM per SM (default 4) and kBnMaxParts in total
+template <typename K>
+static int coop_capacity(K kernel)
 {
-    int64_t rpc = ceil_div(M, (int64_t)kBnMaxParts);
-    return rpc < 64 ? 64 : rpc;
+    int dev = 0, sms = 0, occ = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kBnThreads, 0);
+    const char *e = getenv("PCB_BN_CTAS_PER_SM");
+    const int cap = e ? atoi(e) : 4;
+    if (cap >= 1 && occ > cap) occ = cap;
+    int g = occ * sms;
+    if (g > kBnMaxParts) g = kBnMaxParts;
+    return g < 1 ? 1 : g;
+}
+
+struct Plan {
+    int64_t upc;      // units per CTA in the reduction phase
+    int nparts;       // CTAs that take part in it
+    int grid;
+};
+
+static Plan make_plan(int64_t units, int C, int V, int grid_cap)
+{
+    const int CV = C / V;
+    const int TX = CV < kBnThreads ? CV : kBnThreads;
+    const int TY = kBnThreads / TX;
+    Plan p;
+    p.upc = ceil_div(units, (int64_t)grid_cap);
+    if (p.upc < TY) p.upc = TY;                           // at least one unit per row lane
+    p.nparts = (int)ceil_div(units, p.upc);
+    // the elementwise phase wants every SM busy even when the reduction has few parts
+    const int64_t want = ceil_div(units, (int64_t)TY);
+    p.grid = (int)(want < grid_cap ? want : grid_cap);
+    if (p.grid < p.nparts) p.grid = p.nparts;
+    return p;
+}
+
+template <typename K, typename A>
+static int coop_launch(K kernel, int grid, const A &args, cudaStream_t st)
+{
+    void *params[] = {(void *)&args};
+    return (int)cudaLaunchCooperativeKernel((const void *)kernel, dim3((unsigned)grid), dim3(kBnThreads), params, 0, st);
 }
 
 template <typename T, int V>
-static int bn_stats_launch(const void *y, int64_t M, int C, float *sums, cudaStream_t st)
+static int bn_fwd_launch(BnFwdArgs a, cudaStream_t st)
 {
-    const int64_t rpc = rows_per_cta_for(M);
-    const int nparts = (int)ceil_div(M, rpc);
-    float *parts = sums + 3 * (size_t)C;                  // scratch after the 3C result slots
-    bn_stats_kernel<T, V><<<nparts, kBnThreads, 0, st>>>((const T *)y, M, C, rpc, parts);
-    bn_fold_parts_kernel<<<(unsigned)ceil_div(2 * C, 32), 256, 0, st>>>(parts, nparts, 2 * C, sums);
-    PCB_RETURN_LAUNCH_STATUS();
+    static const int cap = coop_capacity(bn_fwd_fused_kernel<T, V>);
+    const Plan p = make_plan(a.M, a.C, V, cap);           // statistics are over rows, pooled or not
+    a.upc = p.upc, a.nparts = p.nparts;
+    int grid = p.grid;
+    if (a.pool_k > 1) {
+        const Plan q = make_plan(a.M / a.pool_k, a.C, V, cap);
+        grid = q.grid > p.nparts ? q.grid : p.nparts;
+    }
+    return coop_launch(bn_fwd_fused_kernel<T, V>, grid, a, st);
 }
 
 template <typename T, int V>
-static int bn_apply_launch(const void *y, int64_t Mout, int C, int pool_k, const float *mean, const float *invstd,
-                           const float *gamma, const float *beta, int relu, void *out, unsigned char *argmax,
-                           cudaStream_t st)
+static int bn_bwd_launch(BnBwdArgs a, cudaStream_t st)
 {
-    const unsigned total = (unsigned)(Mout * (C / V));
-    bn_apply_kernel<T, V><<<(unsigned)ceil_div(total, kBnThreads), kBnThreads, 0, st>>>(
-        (const T *)y, total, C, make_fastdiv(C / V), pool_k, mean, invstd, gamma, beta, relu, (T *)out, argmax);
-    PCB_RETURN_LAUNCH_STATUS();
-}
-
-template <typename T, int V>
-static int bn_bwd_launch(const void *gz, const void *y, const unsigned char *argmax, int64_t M, int C, int pool_k,
-                         const float *mean, const float *invstd, const float *gamma, const float *beta, int relu,
-                         float *sums, void *gy, cudaStream_t st)
-{
-    const int64_t rpc = rows_per_cta_for(M);
-    const unsigned rblocks = (unsigned)ceil_div(M, rpc);
-    float *parts = sums + 3 * (size_t)C;
-    const unsigned total = (unsigned)(M * (C / V));
-    const FastDiv dK = make_fastdiv(pool_k), dCV = make_fastdiv(C / V);
-    bn_bwd_reduce_kernel<T, V><<<rblocks, kBnThreads, 0, st>>>((const T *)gz, (const T *)y, argmax, M, C, dK, rpc, mean,
-                                                              invstd, gamma, beta, relu, parts);
-    bn_fold_parts_kernel<<<(unsigned)ceil_div(3 * C, 32), 256, 0, st>>>(parts, (int)rblocks, 3 * C, sums);
-    bn_bwd_apply_kernel<T, V><<<(unsigned)ceil_div(total, kBnThreads), kBnThreads, 0, st>>>(
-        (const T *)gz, (const T *)y, argmax, M, total, C, dCV, dK, mean, invstd, gamma, beta, relu, sums, (T *)gy);
-    PCB_RETURN_LAUNCH_STATUS();
+    static const int cap = coop_capacity(bn_bwd_fused_kernel<T, V>);
+    const Plan p = make_plan(a.M / a.pool_k, a.C, V, cap);
+    a.upc = p.upc, a.nparts = p.nparts;
+    return coop_launch(bn_bwd_fused_kernel<T, V>, p.grid, a, st);
 }
 
 }  // namespace pcb
 
 using namespace pcb;
 
-#define PCB_BN_CHECK(M, C)                                   \
-    PCB_REQUIRE((M) > 0 && (C) > 0, PCB_EINVAL);             \
-    PCB_REQUIRE((C) % 4 == 0 && (dtype == 0 || dtype == 1), PCB_ERANGE)
+#define PCB_BN_CHECK(M, C, pool_k)                                       \
+    PCB_REQUIRE((M) > 0 && (C) > 0, PCB_EINVAL);                         \
+    PCB_REQUIRE((C) % 4 == 0 && (dtype == 0 || dtype == 1), PCB_ERANGE); \
+    PCB_REQUIRE((pool_k) >= 1 && (pool_k) <= 255 && (M) % (pool_k) == 0, PCB_ERANGE)
 
 static inline bool al16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
-PCB_API int pcb_bn_stats_rows(const void *y, int dtype, int64_t M, int C, float *sums, pcb_stream_t stream)
-{
-    PCB_REQUIRE(y && sums, PCB_EINVAL);
-    PCB_BN_CHECK(M, C);
-    cudaStream_t st = (cudaStream_t)stream;
-    if (!dtype) return bn_stats_launch<float, 4>(y, M, C, sums, st);
-    if (C % 8 == 0 && al16(y)) return bn_stats_launch<__nv_bfloat16, 8>(y, M, C, sums, st);
-    return bn_stats_launch<__nv_bfloat16, 4>(y, M, C, sums, st);
-}
+PCB_API int64_t pcb_bn_work_floats(int C) { return 3 * (int64_t)C * (1 + kBnMaxParts); }
 
-PCB_API int pcb_bn_finalize(const float *sums, const void *y, int dtype, const float *bias, int64_t M, int C,
-                            float eps, float momentum, float *running_mean, float *running_var, float *mean,
-                            float *invstd, pcb_stream_t stream)
+PCB_API int pcb_bn_fwd_rows(const void *y, int dtype, int64_t M, int C, int pool_k, const float *bias,
+                            const float *gamma, const float *beta, float eps, float momentum, float *running_mean,
+                            float *running_var, int relu, float *mean, float *invstd, void *out,
+                            unsigned char *argmax, float *work, pcb_stream_t stream)
 {
-    PCB_REQUIRE(sums && y && mean && invstd, PCB_EINVAL);
-    PCB_BN_CHECK(M, C);
+    PCB_REQUIRE(y && gamma && beta && mean && invstd && out && work, PCB_EINVAL);
+    PCB_BN_CHECK(M, C, pool_k);
+    PCB_REQUIRE(!running_mean || running_var, PCB_EINVAL);
+    BnFwdArgs a;
+    a.y = y, a.out = out, a.argmax = argmax, a.bias = bias, a.gamma = gamma, a.beta = beta;
+    a.running_mean = running_mean, a.running_var = running_var;
+    a.mean = mean, a.invstd = invstd, a.work = work, a.M = M, a.C = C, a.pool_k = pool_k, a.relu = relu;
+    a.eps = eps, a.momentum = momentum, a.upc = 0, a.nparts = 0;
+    a.dbg = getenv("PCB_BN_DBG") ? atoi(getenv("PCB_BN_DBG")) : 0;
     cudaStream_t st = (cudaStream_t)stream;
-    unsigned blocks = (unsigned)ceil_div(C, 128);
-    if (dtype)
-        bn_finalize_kernel<__nv_bfloat16><<<blocks, 128, 0, st>>>(sums, (const __nv_bfloat16 *)y, bias, M, C, eps, momentum,
-                                                                running_mean, running_var, mean, invstd);
-    else
-        bn_finalize_kernel<float><<<blocks, 128, 0, st>>>(sums, (const float *)y, bias, M, C, eps, momentum, running_mean,
-                                                        running_var, mean, invstd);
-    PCB_RETURN_LAUNCH_STATUS();
-}
-
-PCB_API int pcb_bn_apply_rows(const void *y, int dtype, int64_t Mout, int C, int pool_k, const float *mean,
-                              const float *invstd, const float *gamma, const float *beta, int relu, void *out,
-                              unsigned char *argmax, pcb_stream_t stream)
-{
-    PCB_REQUIRE(y && mean && invstd && gamma && beta && out, PCB_EINVAL);
-    PCB_BN_CHECK(Mout, C);
-    PCB_REQUIRE(pool_k >= 1 && pool_k <= 255, PCB_ERANGE);
-    PCB_REQUIRE(Mout * (C / 4) < (1ll << 31) && Mout * pool_k < (1ll << 31), PCB_ERANGE);
-    cudaStream_t st = (cudaStream_t)stream;
-    if (!dtype) return bn_apply_launch<float, 4>(y, Mout, C, pool_k, mean, invstd, gamma, beta, relu, out, argmax, st);
-    if (C % 8 == 0 && al16(y) && al16(out))
-        return bn_apply_launch<__nv_bfloat16, 8>(y, Mout, C, pool_k, mean, invstd, gamma, beta, relu, out, argmax, st);
-    return bn_apply_launch<__nv_bfloat16, 4>(y, Mout, C, pool_k, mean, invstd, gamma, beta, relu, out, argmax, st);
+    if (!dtype) return bn_fwd_launch<float, 4>(a, st);
+    if (C % 8 == 0 && al16(y) && al16(out)) return bn_fwd_launch<__nv_bfloat16, 8>(a, st);
+    return bn_fwd_launch<__nv_bfloat16, 4>(a, st);
 }
 
 PCB_API int pcb_bn_bwd_rows(const void *gz, const void *y, const unsigned char *argmax, int dtype, int64_t M, int C,
                             int pool_k, const float *mean, const float *invstd, const float *gamma, const float *beta,
-                            int relu, float *sums, void *gy, pcb_stream_t stream)
+                            int relu, float *work, void *gy, pcb_stream_t stream)
 {
-    PCB_REQUIRE(gz && y && mean && invstd && gamma && beta && sums && gy, PCB_EINVAL);
-    PCB_BN_CHECK(M, C);
-    PCB_REQUIRE(pool_k >= 1 && pool_k <= 255 && (pool_k == 1 || argmax), PCB_ERANGE);
-    PCB_REQUIRE(M * (C / 4) < (1ll << 31), PCB_ERANGE);
+    PCB_REQUIRE(gz && y && mean && invstd && gamma && beta && work && gy, PCB_EINVAL);
+    PCB_BN_CHECK(M, C, pool_k);
+    PCB_REQUIRE(pool_k == 1 || argmax, PCB_EINVAL);
+    BnBwdArgs a;
+    a.gz = gz, a.y = y, a.argmax = argmax, a.gy = gy, a.mean = mean, a.invstd = invstd, a.gamma = gamma, a.beta = beta;
+    a.work = work, a.M = M, a.C = C, a.pool_k = pool_k, a.relu = relu, a.upc = 0, a.nparts = 0;
+    a.dbg = getenv("PCB_BN_DBG") ? atoi(getenv("PCB_BN_DBG")) : 0;
     cudaStream_t st = (cudaStream_t)stream;
-    if (!dtype)
-        return bn_bwd_launch<float, 4>(gz, y, argmax, M, C, pool_k, mean, invstd, gamma, beta, relu, sums, gy, st);
-    if (C % 8 == 0 && al16(y) && al16(gz) && al16(gy))
-        return bn_bwd_launch<__nv_bfloat16, 8>(gz, y, argmax, M, C, pool_k, mean, invstd, gamma, beta, relu, sums, gy, st);
-    return bn_bwd_launch<__nv_bfloat16, 4>(gz, y, argmax, M, C, pool_k, mean, invstd, gamma, beta, relu, sums, gy, st);
+    if (!dtype) return bn_bwd_launch<float, 4>(a, st);
+    if (C % 8 == 0 && al16(y) && al16(gz) && al16(gy)) return bn_bwd_launch<__nv_bfloat16, 8>(a, st);
+    return bn_bwd_launch<__nv_bfloat16, 4>(a, st);
 }

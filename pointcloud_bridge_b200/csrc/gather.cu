@@ -89,10 +89,15 @@ group_points_kernel(const float *__restrict__ xyz, const float *__restrict__ poi
                     FastDiv dK, FastDiv dS, int xyz_first, int points_cf, int clamp, unsigned total,
                     OT *__restrict__ out)
 {
+    // dC.d = row pitch of `out` in elements (>= 3 + D; the extra columns are written as zeros)
     const unsigned t = blockIdx.x * kThreads + threadIdx.x;
     if (t >= total) return;
     const unsigned rowg = dC.div(t);                   // (b*S + s)*K + k
     const int c = (int)(t - rowg * dC.d);
+    if (c >= 3 + D) {
+        store_out(out + t, 0.f);
+        return;
+    }
     const unsigned bs = dK.div(rowg);                  // b*S + s
     const unsigned b = dS.div(bs);
     long long i = idx[rowg];
@@ -113,11 +118,11 @@ group_points_kernel(const float *__restrict__ xyz, const float *__restrict__ poi
 
 template <typename GT>
 __global__ void __launch_bounds__(kThreads)
-group_points_bwd_kernel(const GT *__restrict__ gout, const int64_t *__restrict__ idx, int N, int D, FastDiv dD,
-                        FastDiv dSK, int xyz_first, int points_cf, int clamp, unsigned total,
+group_points_bwd_kernel(const GT *__restrict__ gout, const int64_t *__restrict__ idx, int N, int D, int C,
+                        FastDiv dD, FastDiv dSK, int xyz_first, int points_cf, int clamp, unsigned total,
                         float *__restrict__ gpoints)
 {
-    const int C = 3 + D;
+    // C = row pitch of gout in elements (>= 3 + D)
     // one thread per (row, feature channel)
     const unsigned t = blockIdx.x * kThreads + threadIdx.x;
     if (t >= total) return;
@@ -424,13 +429,14 @@ PCB_API int pcb_gather_bwd_f32(const float *grad_out, const int64_t *idx, int B,
 
 template <typename OT>
 static int group_points_launch(const float *xyz, const float *points, const float *new_xyz, const int64_t *idx, int B,
-                               int N, int S, int K, int D, int xyz_first, int points_cf, int clamp, OT *out,
+                               int N, int S, int K, int D, int xyz_first, int points_cf, int clamp, int pitch, OT *out,
                                cudaStream_t st)
 {
     PCB_REQUIRE(xyz && new_xyz && idx && out, PCB_EINVAL);
     PCB_REQUIRE(B > 0 && N > 0 && S > 0 && K > 0 && D >= 0, PCB_EINVAL);
     PCB_REQUIRE(points || D == 0, PCB_EINVAL);
-    const int C = 3 + D;
+    PCB_REQUIRE(pitch == 0 || pitch >= 3 + D, PCB_EINVAL);
+    const int C = pitch ? pitch : 3 + D;
     const int step = clouds_per_launch(B, (int64_t)S * K * C);
     PCB_REQUIRE(step > 0, PCB_ERANGE);
     for (int b0 = 0; b0 < B; b0 += step) {
@@ -446,17 +452,20 @@ static int group_points_launch(const float *xyz, const float *points, const floa
 
 template <typename GT>
 static int group_points_bwd_launch(const GT *grad_out, const int64_t *idx, int B, int N, int S, int K, int D,
-                                   int xyz_first, int points_cf, int clamp, float *grad_points, cudaStream_t st)
+                                   int xyz_first, int points_cf, int clamp, int pitch, float *grad_points,
+                                   cudaStream_t st)
 {
     PCB_REQUIRE(grad_out && idx && grad_points, PCB_EINVAL);
     PCB_REQUIRE(B > 0 && N > 0 && S > 0 && K > 0 && D > 0, PCB_EINVAL);
-    const int step = clouds_per_launch(B, (int64_t)S * K * (3 + D));
+    PCB_REQUIRE(pitch == 0 || pitch >= 3 + D, PCB_EINVAL);
+    const int C = pitch ? pitch : 3 + D;
+    const int step = clouds_per_launch(B, (int64_t)S * K * C);
     PCB_REQUIRE(step > 0, PCB_ERANGE);
     for (int b0 = 0; b0 < B; b0 += step) {
         const int nb = B - b0 < step ? B - b0 : step;
         const unsigned total = (unsigned)((int64_t)nb * S * K * D);
         group_points_bwd_kernel<GT><<<blocks_for(total), kThreads, 0, st>>>(
-            grad_out + (size_t)b0 * S * K * (3 + D), idx + (size_t)b0 * S * K, N, D, make_fastdiv(D),
+            grad_out + (size_t)b0 * S * K * C, idx + (size_t)b0 * S * K, N, D, C, make_fastdiv(D),
             make_fastdiv((unsigned)(S * K)), xyz_first, points_cf, clamp, total, grad_points + (size_t)b0 * N * D);
     }
     PCB_RETURN_LAUNCH_STATUS();
@@ -464,34 +473,34 @@ static int group_points_bwd_launch(const GT *grad_out, const int64_t *idx, int B
 
 PCB_API int pcb_group_points_f32(const float *xyz, const float *points, const float *new_xyz,
                                  const int64_t *idx, int B, int N, int S, int K, int D, int xyz_first,
-                                 int points_cf, int clamp, float *out, pcb_stream_t stream)
+                                 int points_cf, int clamp, int pitch, float *out, pcb_stream_t stream)
 {
-    return group_points_launch<float>(xyz, points, new_xyz, idx, B, N, S, K, D, xyz_first, points_cf, clamp, out,
+    return group_points_launch<float>(xyz, points, new_xyz, idx, B, N, S, K, D, xyz_first, points_cf, clamp, pitch, out,
                                       (cudaStream_t)stream);
 }
 
 PCB_API int pcb_group_points_bf16(const float *xyz, const float *points, const float *new_xyz,
                                   const int64_t *idx, int B, int N, int S, int K, int D, int xyz_first,
-                                  int points_cf, int clamp, void *out, pcb_stream_t stream)
+                                  int points_cf, int clamp, int pitch, void *out, pcb_stream_t stream)
 {
     return group_points_launch<__nv_bfloat16>(xyz, points, new_xyz, idx, B, N, S, K, D, xyz_first, points_cf, clamp,
-                                              (__nv_bfloat16 *)out, (cudaStream_t)stream);
+                                              pitch, (__nv_bfloat16 *)out, (cudaStream_t)stream);
 }
 
 PCB_API int pcb_group_points_bwd_f32(const float *grad_out, const int64_t *idx, int B, int N, int S, int K,
-                                     int D, int xyz_first, int points_cf, int clamp, float *grad_points,
+                                     int D, int xyz_first, int points_cf, int clamp, int pitch, float *grad_points,
                                      pcb_stream_t stream)
 {
-    return group_points_bwd_launch<float>(grad_out, idx, B, N, S, K, D, xyz_first, points_cf, clamp, grad_points,
+    return group_points_bwd_launch<float>(grad_out, idx, B, N, S, K, D, xyz_first, points_cf, clamp, pitch, grad_points,
                                           (cudaStream_t)stream);
 }
 
 PCB_API int pcb_group_points_bwd_bf16(const void *grad_out, const int64_t *idx, int B, int N, int S, int K,
-                                      int D, int xyz_first, int points_cf, int clamp, float *grad_points,
+                                      int D, int xyz_first, int points_cf, int clamp, int pitch, float *grad_points,
                                       pcb_stream_t stream)
 {
     return group_points_bwd_launch<__nv_bfloat16>((const __nv_bfloat16 *)grad_out, idx, B, N, S, K, D, xyz_first,
-                                                  points_cf, clamp, grad_points, (cudaStream_t)stream);
+                                                  points_cf, clamp, pitch, grad_points, (cudaStream_t)stream);
 }
 
 PCB_API int pcb_graph_feature_f32(const float *x, const int64_t *idx, int B, int D, int N, int k, float *out,

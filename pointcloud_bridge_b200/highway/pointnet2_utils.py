@@ -44,12 +44,12 @@ def query_ball_point(radius, nsample, xyz, new_xyz):
     return ops.ball_query(radius, nsample, xyz, new_xyz)
 
 
-def sample_and_group(npoint, radius, nsample, xyz, points):
+def sample_and_group(npoint, radius, nsample, xyz, points, pad_to=1):
     """xyz [B,N,3], points [B,N,D] | None -> new_xyz [B,S,3], new_points [B,S,nsample,3+D]
-    (pointnet2_utils.py:42-60)."""
+    (pointnet2_utils.py:42-60).  pad_to > 1: channels rounded up with zero columns (ops.group_points)."""
     new_xyz = index_points(xyz, farthest_point_sample(xyz, npoint))
     idx = query_ball_point(radius, nsample, xyz, new_xyz)
-    return new_xyz, ops.group_points(xyz, points, new_xyz, idx, xyz_first=True, clamp=True)
+    return new_xyz, ops.group_points(xyz, points, new_xyz, idx, xyz_first=True, clamp=True, pad_to=pad_to)
 
 
 def three_nn(xyz1, xyz2, k=3):
@@ -116,7 +116,7 @@ class SetAbstraction(nn.Module):
                 idx = query_ball_point(self.radius, self.nsample, xyz, new_xyz)
                 y = ops.sa_fused(xyz, pts, new_xyz, idx, pk, xyz_first=True)
                 return new_xyz, _cf_view(y, xyz.shape[0], self.npoint)
-        new_xyz, grouped = sample_and_group(self.npoint, self.radius, self.nsample, xyz, pts)
+        new_xyz, grouped = sample_and_group(self.npoint, self.radius, self.nsample, xyz, pts, pad_to=8)
         B, S, K, C = grouped.shape
         y = mlp_rows(grouped.view(B * S * K, C), self.mlp_convs, self.mlp_bns, pool_k=K)
         return new_xyz, _cf_view(y, B, S)
@@ -156,7 +156,7 @@ class MultiScaleSetAbstraction(nn.Module):
                 if pk.ok:
                     outs.append(ops.sa_fused(xyz, pts, new_xyz, idx, pk, xyz_first=True))
                     continue
-            grouped = ops.group_points(xyz, pts, new_xyz, idx, xyz_first=True, clamp=True)
+            grouped = ops.group_points(xyz, pts, new_xyz, idx, xyz_first=True, clamp=True, pad_to=8)
             outs.append(mlp_rows(grouped.view(B * S * K, -1), self.conv_blocks[i], self.bn_blocks[i], pool_k=K))
         return new_xyz, _cf_view(torch.cat(outs, dim=1), B, S)
 

@@ -265,7 +265,7 @@ def gather(points: torch.Tensor, idx: torch.Tensor, clamp: bool = False) -> torc
 
 class _GroupPoints(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, xyz, points, new_xyz, idx, xyz_first, points_cf, clamp):
+    def forward(ctx, xyz, points, new_xyz, idx, xyz_first, points_cf, clamp, pad_to):
         xyz = _f32(xyz, "xyz")
         new_xyz = _f32(new_xyz, "new_xyz")
         idx = _i64(idx, "idx")
@@ -278,18 +278,19 @@ class _GroupPoints(torch.autograd.Function):
             D = 0
         # under bf16 autocast the consumer is a bf16 GEMM: emit the grouped tensor in bf16 directly
         bf16 = torch.is_autocast_enabled() and torch.get_autocast_dtype("cuda") == torch.bfloat16
-        out = torch.empty(B, S, K, 3 + D, dtype=torch.bfloat16 if bf16 else torch.float32, device=xyz.device)
+        pitch = -(-(3 + D) // pad_to) * pad_to
+        out = torch.empty(B, S, K, pitch, dtype=torch.bfloat16 if bf16 else torch.float32, device=xyz.device)
         _call("pcb_group_points_bf16" if bf16 else "pcb_group_points_f32", xyz.device, xyz.data_ptr(), points.data_ptr() if D else None,
-              new_xyz.data_ptr(), idx.data_ptr(), B, N, S, K, D, int(xyz_first), int(points_cf), int(clamp),
-              out.data_ptr(), alg_bytes=B * (4 * N * (3 + D) + 12 * S + 8 * S * K + out.element_size() * S * K * (3 + D)))
+              new_xyz.data_ptr(), idx.data_ptr(), B, N, S, K, D, int(xyz_first), int(points_cf), int(clamp), pitch,
+              out.data_ptr(), alg_bytes=B * (4 * N * (3 + D) + 12 * S + 8 * S * K + out.element_size() * S * K * pitch))
         ctx.save_for_backward(idx)
-        ctx.meta = (B, N, S, K, D, int(xyz_first), int(points_cf), int(clamp))
+        ctx.meta = (B, N, S, K, D, int(xyz_first), int(points_cf), int(clamp), pitch)
         return out
 
     @staticmethod
     def backward(ctx, gout):
         (idx,) = ctx.saved_tensors
-        B, N, S, K, D, xyz_first, points_cf, clamp = ctx.meta
+        B, N, S, K, D, xyz_first, points_cf, clamp, pitch = ctx.meta
         gpoints = None
         if D and ctx.needs_input_grad[1]:
             bf16 = gout.dtype == torch.bfloat16
@@ -297,16 +298,19 @@ class _GroupPoints(torch.autograd.Function):
             shape = (B, D, N) if points_cf else (B, N, D)
             gpoints = torch.zeros(shape, dtype=torch.float32, device=gout.device)
             _call("pcb_group_points_bwd_bf16" if bf16 else "pcb_group_points_bwd_f32", gout.device, gout.data_ptr(), idx.data_ptr(), B, N, S, K, D,
-                  xyz_first, points_cf, clamp, gpoints.data_ptr(),
-                  alg_bytes=B * (4 * N * D + 8 * S * K + 4 * S * K * D))
-        return None, gpoints, None, None, None, None, None
+                  xyz_first, points_cf, clamp, pitch, gpoints.data_ptr(),
+                  alg_bytes=B * (4 * N * D + 8 * S * K + gout.element_size() * S * K * D))
+        return None, gpoints, None, None, None, None, None, None
 
 
 def group_points(xyz, points, new_xyz, idx, xyz_first: bool = True, points_cf: bool = False,
-                 clamp: bool = False) -> torch.Tensor:
+                 clamp: bool = False, pad_to: int = 1) -> torch.Tensor:
     """Fused index_points(xyz, idx) - new_xyz, index_points(points, idx) and concat:
-    -> [B,S,K,3+D].  `points` is [B,N,D], or [B,D,N] with points_cf=True, or None."""
-    return _GroupPoints.apply(xyz, points, new_xyz, idx, bool(xyz_first), bool(points_cf), bool(clamp))
+    -> [B,S,K,3+D].  `points` is [B,N,D], or [B,D,N] with points_cf=True, or None.
+    pad_to > 1 rounds the channel count up to a multiple of pad_to with zero columns: 3+D is 99,
+    259, 515 in the MSG network, and rows that are not 16-byte aligned send the following GEMM to
+    cuBLAS's unaligned legacy kernels (`linear_rows` accepts the padded rows)."""
+    return _GroupPoints.apply(xyz, points, new_xyz, idx, bool(xyz_first), bool(points_cf), bool(clamp), int(pad_to))
 
 
 class _GraphFeature(torch.autograd.Function):
@@ -388,11 +392,14 @@ def _act_dtype(t: torch.Tensor) -> int:
     raise _lib.PcbError(f"bn_relu_rows supports fp32 / bf16 activations, got {t.dtype}")
 
 
-_BN_MAX_PARTS = 148 * 4      # kBnMaxParts in csrc/bn_rows.cu
+def _bn_work(C: int, dev) -> torch.Tensor:
+    """fp32 scratch of one BN launch: 3*C results + per-CTA partial sums (csrc/bn_rows.cu)."""
+    return torch.empty(_lib.lib().pcb_bn_work_floats(C), dtype=torch.float32, device=dev)
 
 
 class _BnReluRows(torch.autograd.Function):
-    """z = max_k relu(BN_train(y + bias)) on rows.  y [M,C] is the bias-free GEMM output."""
+    """z = max_k relu(BN_train(y + bias)) on rows.  y [M,C] is the bias-free GEMM output.
+    One cooperative kernel forward, one backward."""
 
     @staticmethod
     def forward(ctx, y, bias, gamma, beta, running_mean, running_var, momentum, eps, relu, pool_k):
@@ -401,46 +408,40 @@ class _BnReluRows(torch.autograd.Function):
         M, C = y.shape
         dt = _act_dtype(y)
         dev = y.device
-        # [3C result slots | per-CTA partial sums]: the column reductions are two-stage (csrc/bn_rows.cu)
-        rpc = max(64, -(-M // _BN_MAX_PARTS))
-        sums = torch.empty(3 * C * (1 + -(-M // rpc)), dtype=torch.float32, device=dev)
         stats = torch.empty(2, C, dtype=torch.float32, device=dev)          # mean, invstd of bias-free y
-        mean, invstd = stats[0], stats[1]
-        _call("pcb_bn_stats_rows", dev, y.data_ptr(), dt, M, C, sums.data_ptr(), alg_bytes=y.numel() * y.element_size())
-        _call("pcb_bn_finalize", dev, sums.data_ptr(), y.data_ptr(), dt, bias.data_ptr() if bias is not None else None,
-              M, C, float(eps), float(momentum), running_mean.data_ptr() if running_mean is not None else None,
-              running_var.data_ptr() if running_var is not None else None, mean.data_ptr(), invstd.data_ptr(),
-              alg_bytes=12 * C)
         Mout = M // pool_k
         out = torch.empty(Mout, C, dtype=y.dtype, device=dev)
         argmax = torch.empty(Mout, C, dtype=torch.uint8, device=dev) if pool_k > 1 else None
         g32, b32 = gamma.float(), beta.float()
-        _call("pcb_bn_apply_rows", dev, y.data_ptr(), dt, Mout, C, int(pool_k), mean.data_ptr(), invstd.data_ptr(),
-              g32.data_ptr(), b32.data_ptr(), int(relu), out.data_ptr(),
-              argmax.data_ptr() if argmax is not None else None,
-              alg_bytes=(y.numel() + out.numel()) * y.element_size())
-        ctx.save_for_backward(y, stats, g32, b32, argmax, sums)
+        work = _bn_work(C, dev)
+        esz = y.element_size()
+        _call("pcb_bn_fwd_rows", dev, y.data_ptr(), dt, M, C, int(pool_k),
+              bias.data_ptr() if bias is not None else None, g32.data_ptr(), b32.data_ptr(), float(eps),
+              float(momentum), running_mean.data_ptr() if running_mean is not None else None,
+              running_var.data_ptr() if running_var is not None else None, int(relu), stats[0].data_ptr(),
+              stats[1].data_ptr(), out.data_ptr(), argmax.data_ptr() if argmax is not None else None,
+              work.data_ptr(), alg_bytes=(y.numel() + out.numel()) * esz + (Mout * C if pool_k > 1 else 0))
+        ctx.save_for_backward(y, stats, g32, b32, argmax)
         ctx.meta = (M, C, dt, int(relu), int(pool_k), bias is not None)
         return out
 
     @staticmethod
     def backward(ctx, gz):
-        y, stats, g32, b32, argmax, sums = ctx.saved_tensors
+        y, stats, g32, b32, argmax = ctx.saved_tensors
         M, C, dt, relu, pool_k, has_bias = ctx.meta
         gz = gz.contiguous()
         if gz.dtype != y.dtype:
             gz = gz.to(y.dtype)
         gy = torch.empty_like(y)
+        work = _bn_work(C, y.device)
         _call("pcb_bn_bwd_rows", y.device, gz.data_ptr(), y.data_ptr(), argmax.data_ptr() if argmax is not None else None,
               dt, M, C, pool_k, stats[0].data_ptr(), stats[1].data_ptr(), g32.data_ptr(), b32.data_ptr(), relu,
-              sums.data_ptr(), gy.data_ptr(), launches=2,
-              alg_bytes=(3 * y.numel() + 2 * gz.numel()) * y.element_size())
-        s = sums[:3 * C].view(3, C)
-        ggamma, gbeta = s[1], s[0]
-        # d/d(bias) = sum_rows gy = -gamma * invstd * (sum yhat) * (sum dy*yhat) / M: zero up to rounding,
-        # as in the reference, where the bias of a conv that feeds a training-mode BN gets a noise gradient
-        gbias = (-(g32 * stats[1]) * s[2] * s[1] / M) if has_bias else None
-        return gy, gbias, ggamma, gbeta, None, None, None, None, None, None
+              work.data_ptr(), gy.data_ptr(),
+              alg_bytes=(2 * y.numel() + gz.numel()) * y.element_size() + (gz.numel() if pool_k > 1 else 0))
+        s = work[:3 * C].view(3, C)
+        # s[2] = d/d(conv bias) = sum_rows gy: zero up to rounding, as in the reference, where the bias of a
+        # conv that feeds a training-mode BN gets a noise gradient
+        return gy, (s[2] if has_bias else None), s[1], s[0], None, None, None, None, None, None
 
 
 def bn_relu_rows(y, bias, bn, relu=True, pool_k=1):
@@ -564,9 +565,14 @@ class _LinearRows(torch.autograd.Function):
     CHUNK = 2048
 
     @staticmethod
+    def _padded(w, kx, dtype):
+        w = w.to(dtype)
+        return w if w.shape[1] == kx else torch.nn.functional.pad(w, (0, kx - w.shape[1]))
+
+    @staticmethod
     def forward(ctx, x, w):
         ctx.save_for_backward(x, w)
-        return torch.mm(x, w.t().to(x.dtype))
+        return torch.mm(x, _LinearRows._padded(w, x.shape[1], x.dtype).t())
 
     @staticmethod
     def backward(ctx, gy):
@@ -574,7 +580,7 @@ class _LinearRows(torch.autograd.Function):
         gx = gw = None
         gy = gy.contiguous()
         if ctx.needs_input_grad[0]:
-            gx = torch.mm(gy, w.to(gy.dtype))
+            gx = torch.mm(gy, _LinearRows._padded(w, x.shape[1], gy.dtype))
         if ctx.needs_input_grad[1]:
             M = x.shape[0]
             c = _LinearRows.CHUNK
@@ -584,11 +590,14 @@ class _LinearRows(torch.autograd.Function):
                 gw = part.float().sum(dim=0)
             else:
                 gw = torch.mm(gy.t(), x.to(gy.dtype)).float()
+            if gw.shape[1] != w.shape[1]:
+                gw = gw[:, :w.shape[1]]
         return gx, gw
 
 
 def linear_rows(x, w):
-    """x [M,K] @ w[N,K]^T under the ambient autocast dtype."""
+    """x [M,K] @ w[N,K]^T under the ambient autocast dtype.  x may carry zero pad columns beyond
+    K (group_points(pad_to=8)); the weight is padded to match and its gradient sliced back."""
     if torch.is_autocast_enabled():
         dt = torch.get_autocast_dtype("cuda")
         x = x if x.dtype == dt else x.to(dt)

@@ -44,7 +44,13 @@ def _seg_head(net, feats_bcn):
     x = _rows(feats_bcn)
     B, N, C = x.shape
     x = net.drop1(conv_bn_relu_rows(x.reshape(B * N, C), net.conv1, net.bn1))
-    x = F.linear(x, net.conv2.weight.flatten(1), net.conv2.bias)
+    w, b = net.conv2.weight.flatten(1), net.conv2.bias
+    nc = w.shape[0]
+    pad = (-nc) % 8 if x.is_cuda else 0
+    if pad:                        # [M,5] bf16 rows are not 16-byte aligned: cuBLAS falls back to legacy kernels
+        x = F.linear(x, F.pad(w, (0, 0, 0, pad)), F.pad(b, (0, pad)) if b is not None else None)[:, :nc]
+    else:
+        x = F.linear(x, w, b)
     return F.log_softmax(x.float(), dim=-1).view(B, N, -1)
 
 

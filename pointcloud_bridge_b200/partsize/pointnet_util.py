@@ -54,13 +54,14 @@ def query_ball_point(radius, nsample, xyz, new_xyz):
     return ops.ball_query(radius, nsample, xyz, new_xyz)
 
 
-def sample_and_group(npoint, radius, nsample, xyz, points, returnfps=False):
+def sample_and_group(npoint, radius, nsample, xyz, points, returnfps=False, pad_to=1):
     """FPS -> centroids -> ball query -> grouped [dxyz | features]  (pointnet_util.py:116-152).
-    xyz [B,N,3], points [B,N,D] or None -> new_xyz [B,S,3], new_points [B,S,nsample,3+D]."""
+    xyz [B,N,3], points [B,N,D] or None -> new_xyz [B,S,3], new_points [B,S,nsample,3+D]
+    (pad_to > 1: channel count rounded up with zero columns, see ops.group_points)."""
     fps_idx = farthest_point_sample(xyz, npoint)
     new_xyz = index_points(xyz, fps_idx)
     idx = query_ball_point(radius, nsample, xyz, new_xyz)
-    new_points = ops.group_points(xyz, points, new_xyz, idx, xyz_first=True)
+    new_points = ops.group_points(xyz, points, new_xyz, idx, xyz_first=True, pad_to=pad_to)
     if returnfps:
         return new_xyz, new_points, index_points(xyz, idx), fps_idx
     return new_xyz, new_points
@@ -119,15 +120,16 @@ def conv_bn_relu_rows(x, conv, bn, pool_k=1):
     half runs in libpcbridge's fused row kernels (csrc/bn_rows.cu): the conv bias is folded into
     the normalisation and ReLU / max-pool happen in the same pass."""
     w = conv.weight.flatten(1)
+    padded = x.shape[1] != w.shape[1]                     # zero pad columns from group_points(pad_to=8)
     if bn.training and x.is_cuda and w.shape[0] % 4 == 0 and bn.momentum is not None and bn.affine \
             and x.shape[0] % pool_k == 0 and 1 < pool_k + 1 <= 256 and x.shape[0] > 1:
         # bias-free: BN(xW + b) == BN(xW) + running-mean shift
-        y = ops.linear_rows(x, w) if (x.shape[0] >= 32768 and os.environ.get('PCB_PLAIN_LINEAR', '0') != '1') else F.linear(x, w)
+        y = ops.linear_rows(x, w) if (padded or x.shape[0] >= 32768) else F.linear(x, w)
         if ops.bn_rows_supported(y, bn, pool_k):
             return ops.bn_relu_rows(y, conv.bias, bn, relu=True, pool_k=pool_k)
         x = y if conv.bias is None else y + conv.bias
     else:
-        x = F.linear(x, w, conv.bias)
+        x = F.linear(x, F.pad(w, (0, x.shape[1] - w.shape[1])) if padded else w, conv.bias)
     x = F.relu(_bn_rows(bn, x), inplace=True)
     if pool_k > 1:
         x = x.view(-1, pool_k, x.shape[-1]).max(dim=1)[0]
@@ -180,7 +182,7 @@ class PointNetSetAbstraction(nn.Module):
         if self.group_all:
             new_xyz, grouped = sample_and_group_all(xyz_r, pts_r)
         else:
-            new_xyz, grouped = sample_and_group(self.npoint, self.radius, self.nsample, xyz_r, pts_r)
+            new_xyz, grouped = sample_and_group(self.npoint, self.radius, self.nsample, xyz_r, pts_r, pad_to=8)
         S, K, C = grouped.shape[1:]
         y = mlp_rows(grouped.reshape(B * S * K, C), self.mlp_convs, self.mlp_bns, pool_k=K)   # max over neighbours
         return new_xyz.permute(0, 2, 1), _cf_view(y, B, S)
@@ -221,7 +223,7 @@ class PointNetSetAbstractionMsg(nn.Module):
                 if pk.ok:
                     outs.append(ops.sa_fused(xyz_r, pts_r, new_xyz, idx, pk, xyz_first=False))
                     continue
-            grouped = ops.group_points(xyz_r, pts_r, new_xyz, idx, xyz_first=False)   # [feat | dxyz]
+            grouped = ops.group_points(xyz_r, pts_r, new_xyz, idx, xyz_first=False, pad_to=8)   # [feat | dxyz | 0]
             outs.append(mlp_rows(grouped.view(B * S * K, -1), self.conv_blocks[i], self.bn_blocks[i], pool_k=K))
         y = torch.cat(outs, dim=1)
         return new_xyz.permute(0, 2, 1), _cf_view(y, B, S)

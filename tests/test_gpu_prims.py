@@ -243,6 +243,20 @@ def test_backward_of_gathers_matches_torch_autograd():
         (ga,) = torch.autograd.grad(out, p_in, g)
         (gb,) = torch.autograd.grad(ref, pts, g)
         torch.testing.assert_close(ga.transpose(1, 2) if cf else ga, gb, rtol=1e-5, atol=1e-5)
+        # padded rows (pad_to=8): same values, zero pad columns, pad columns ignored by the backward
+        outp = ops.group_points(xyz, p_in, new_xyz, idx, xyz_first=True, points_cf=cf, pad_to=8)
+        C = 3 + D
+        assert outp.shape[-1] == -(-C // 8) * 8
+        assert torch.equal(outp[..., :C], ref) and not outp[..., C:].any()
+        gp = torch.randn_like(outp)
+        (gc,) = torch.autograd.grad(outp, p_in, gp)
+        ref2 = torch.cat([xyz[bi, idx] - new_xyz.view(B, S, 1, 3), pts[bi, idx]], -1)
+        (gd,) = torch.autograd.grad(ref2, pts, gp[..., :C])
+        torch.testing.assert_close(gc.transpose(1, 2) if cf else gc, gd, rtol=1e-5, atol=1e-5)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            outb = ops.group_points(xyz, p_in, new_xyz, idx, xyz_first=False, points_cf=cf, pad_to=8)
+        refb = torch.cat([pts[bi, idx], xyz[bi, idx] - new_xyz.view(B, S, 1, 3)], -1).to(torch.bfloat16)
+        assert outb.dtype == torch.bfloat16 and torch.equal(outb[..., :C], refb) and not outb[..., C:].any()
 
     x = torch.randn(B, D, N, device=DEV, requires_grad=True)
     kidx = torch.randint(0, N, (B, N, 5), device=DEV)
