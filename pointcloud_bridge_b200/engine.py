@@ -70,6 +70,7 @@ class Trainer:
         self.bucket = pdist.FlatGradBucket(net)
         self.opt = torch.optim.Adam(self.bucket.params, lr=lr, weight_decay=weight_decay, fused=True,
                                     capturable=graph if capturable is None else capturable)
+        self._ctx = ops.StepContext(net, bf16=amp)
         self._g = None                 # captured (zero, forward, loss, backward[, Adam]) graph
         self._static = None
         self._starts = FpsStartBuffers()
@@ -79,14 +80,15 @@ class Trainer:
     # -- eager pieces ---------------------------------------------------------------------
     def _fwd_bwd(self, inputs, labels, loss_inputs):
         self.bucket.zero()
-        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=self.amp):
-            out = self.net(*inputs)
-        logits = out[0] if isinstance(out, tuple) else out
-        if self.loss_fn is None:       # sem-seg nets return log-probabilities [B,N,C]
-            loss = F.nll_loss(logits.float().reshape(-1, logits.shape[-1]), labels.reshape(-1))
-        else:
-            loss = self.loss_fn(logits.float(), labels, *loss_inputs)
-        loss.backward()
+        with self._ctx:
+            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=self.amp):
+                out = self.net(*inputs)
+            logits = out[0] if isinstance(out, tuple) else out
+            if self.loss_fn is None:       # sem-seg nets return log-probabilities [B,N,C]
+                loss = F.nll_loss(logits.float().reshape(-1, logits.shape[-1]), labels.reshape(-1))
+            else:
+                loss = self.loss_fn(logits.float(), labels, *loss_inputs)
+            loss.backward()
         return loss.detach()
 
     def _multi(self):

@@ -448,7 +448,10 @@ def bn_relu_rows(y, bias, bn, relu=True, pool_k=1):
     """BatchNorm with batch statistics (+ReLU, + max over groups of `pool_k` consecutive rows) of
     the bias-free GEMM output y [M,C]; updates bn's running statistics like nn.BatchNorm does."""
     if bn.track_running_stats and bn.num_batches_tracked is not None:
-        bn.num_batches_tracked.add_(1)
+        if _step_ctx is not None:
+            _step_ctx.counters.append(bn.num_batches_tracked)
+        else:
+            bn.num_batches_tracked.add_(1)
     rm = bn.running_mean if bn.track_running_stats else None
     rv = bn.running_var if bn.track_running_stats else None
     return _BnReluRows.apply(y, bias, bn.weight, bn.bias, rm, rv, bn.momentum, bn.eps, bool(relu), int(pool_k))
@@ -556,43 +559,81 @@ def sa_fused(xyz, points, new_xyz, idx, packed: PackedMLP, xyz_first=True, mode=
 # ---------------------------------------------------------------------------------------------
 # y = x @ W^T on rows with a weight-gradient schedule for very tall activations
 # ---------------------------------------------------------------------------------------------
+class StepContext:
+    """Batches the tiny per-layer bookkeeping kernels of one training step (34 BatchNorm layers in
+    the MSG network): inside `with ctx:` every `num_batches_tracked += 1` is deferred to ONE
+    multi-tensor add on exit, and with bf16 autocast the fp32 -> bf16 casts of the shared-MLP
+    weights are ONE multi-tensor copy on entry into persistent shadows that `linear_rows` picks up
+    (autocast would cast each weight on use, forward and again backward)."""
+
+    def __init__(self, module: torch.nn.Module, bf16: bool):
+        self.counters = []
+        self.params = [p for p in module.parameters() if p.dim() >= 2] if bf16 else []
+        self.shadows = [torch.empty(p.shape[0], p[0].numel(), dtype=torch.bfloat16, device=p.device) for p in self.params]
+        self.by_id = {id(p): s for p, s in zip(self.params, self.shadows)}
+
+    def __enter__(self):
+        global _step_ctx
+        self.counters = []
+        if self.params:
+            with torch.no_grad():
+                torch._foreach_copy_(self.shadows, [p.detach().flatten(1) for p in self.params])
+        _step_ctx = self
+        return self
+
+    def __exit__(self, *exc):
+        global _step_ctx
+        _step_ctx = None
+        if self.counters:
+            torch._foreach_add_(self.counters, 1)
+        return False
+
+    def shadow(self, w):
+        base = w._base if w._base is not None else w
+        return self.by_id.get(id(base))
+
+
+_step_ctx = None
+_WGRAD_CHUNK = int(os.environ.get("PCB_WGRAD_CHUNK", "2048"))
+
+
 class _LinearRows(torch.autograd.Function):
     """F.linear without bias for x [M,K], W [N,K] with M in the 10^5..10^6 range.  The weight
-    gradient gy^T x reduces over M: cuBLAS picks legacy split-K kernels for that shape (85-135 us
-    per call in the round-1 profile); reducing 148*P row chunks as one batched GEMM and summing the
-    chunk results keeps every SM busy with short reductions."""
-
-    CHUNK = 2048
+    gradient gy^T x reduces over M: reducing 2048-row chunks as one batched GEMM and summing the
+    chunk results keeps every SM busy with short reductions.  x may carry zero pad columns beyond
+    K (`group_points(pad_to=8)`): the weight is padded to match and its gradient sliced back."""
 
     @staticmethod
-    def _padded(w, kx, dtype):
-        w = w.to(dtype)
-        return w if w.shape[1] == kx else torch.nn.functional.pad(w, (0, kx - w.shape[1]))
-
-    @staticmethod
-    def forward(ctx, x, w):
-        ctx.save_for_backward(x, w)
-        return torch.mm(x, _LinearRows._padded(w, x.shape[1], x.dtype).t())
+    def forward(ctx, x, w, w_lp):
+        # w_lp: the weight already in x's dtype (StepContext shadow) or None
+        wl = w_lp if w_lp is not None else w.to(x.dtype)
+        if wl.shape[1] != x.shape[1]:
+            wl = torch.nn.functional.pad(wl, (0, x.shape[1] - wl.shape[1]))
+        ctx.save_for_backward(x, wl)
+        ctx.kw = w.shape[1]
+        return torch.mm(x, wl.t())
 
     @staticmethod
     def backward(ctx, gy):
-        x, w = ctx.saved_tensors
+        x, wl = ctx.saved_tensors
         gx = gw = None
         gy = gy.contiguous()
+        if gy.dtype != x.dtype:
+            gy = gy.to(x.dtype)
         if ctx.needs_input_grad[0]:
-            gx = torch.mm(gy, _LinearRows._padded(w, x.shape[1], gy.dtype))
+            gx = torch.mm(gy, wl)
         if ctx.needs_input_grad[1]:
             M = x.shape[0]
-            c = _LinearRows.CHUNK
-            if M % c == 0 and M // c >= 8:
+            c = _WGRAD_CHUNK
+            if c and M % c == 0 and M // c >= 8:
                 p = M // c
-                part = torch.bmm(gy.view(p, c, -1).transpose(1, 2), x.view(p, c, -1).to(gy.dtype))   # [p,N,K]
+                part = torch.bmm(gy.view(p, c, -1).transpose(1, 2), x.view(p, c, -1))   # [p,N,K]
                 gw = part.float().sum(dim=0)
             else:
-                gw = torch.mm(gy.t(), x.to(gy.dtype)).float()
-            if gw.shape[1] != w.shape[1]:
-                gw = gw[:, :w.shape[1]]
-        return gx, gw
+                gw = torch.mm(gy.t(), x).float()
+            if gw.shape[1] != ctx.kw:
+                gw = gw[:, :ctx.kw]
+        return gx, gw, None
 
 
 def linear_rows(x, w):
@@ -601,4 +642,5 @@ def linear_rows(x, w):
     if torch.is_autocast_enabled():
         dt = torch.get_autocast_dtype("cuda")
         x = x if x.dtype == dt else x.to(dt)
-    return _LinearRows.apply(x, w)
+    w_lp = _step_ctx.shadow(w) if (_step_ctx is not None and x.dtype == torch.bfloat16) else None
+    return _LinearRows.apply(x, w, w_lp)

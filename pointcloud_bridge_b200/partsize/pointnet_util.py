@@ -124,7 +124,7 @@ def conv_bn_relu_rows(x, conv, bn, pool_k=1):
     if bn.training and x.is_cuda and w.shape[0] % 4 == 0 and bn.momentum is not None and bn.affine \
             and x.shape[0] % pool_k == 0 and 1 < pool_k + 1 <= 256 and x.shape[0] > 1:
         # bias-free: BN(xW + b) == BN(xW) + running-mean shift
-        y = ops.linear_rows(x, w) if (padded or x.shape[0] >= 32768) else F.linear(x, w)
+        y = ops.linear_rows(x, w)
         if ops.bn_rows_supported(y, bn, pool_k):
             return ops.bn_relu_rows(y, conv.bias, bn, relu=True, pool_k=pool_k)
         x = y if conv.bias is None else y + conv.bias
