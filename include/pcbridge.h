@@ -137,7 +137,7 @@ int pcb_graph_feature_bwd_f32(const float *grad_out, const int64_t *idx, int B, 
  * the running mean -- so no bias-add / bias-gradient pass exists.
  * Each direction is ONE persistent cooperative kernel (column sums -> grid barrier -> fold ->
  * grid barrier -> elementwise pass; the second read of y comes from L2).
- * `work` is a caller-provided fp32 scratch of pcb_bn_work_floats(C) = 3*C*(1+592) floats: the first
+ * `work` is a caller-provided fp32 scratch of pcb_bn_work_floats(C) = 3*C*(1+296) floats: the first
  * 3*C floats receive results, the rest holds per-CTA partial sums (deterministic two-stage reduction).
  *   pcb_bn_fwd_rows : mean/invstd [C] of y (batch statistics, biased variance, eps); running_mean /
  *                     running_var update with `momentum`, unbiased variance and the conv `bias` added

@@ -10,7 +10,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpcbridge.so")
+LIB_PATH = os.environ.get("PCB_LIB_PATH") or os.path.join(_HERE, "libpcbridge.so")   # override: kernel experiments
 
 _lib = None
 

@@ -18,7 +18,7 @@
 // mean), so no separate bias-add or bias-gradient pass exists.
 // Column reductions are two-stage and deterministic: every CTA stores its partial sums to
 // parts[cta][NACC*C] with plain stores; after the grid barrier one warp per channel adds the
-// <= 592 partials in a fixed order.
+// <= 296 partials in a fixed order.
 #include <cooperative_groups.h>
 #include <cuda_bf16.h>
 
@@ -30,8 +30,30 @@ namespace cg = cooperative_groups;
 
 namespace pcb {
 
+#ifndef PCB_BN_U
+#define PCB_BN_U 4    // rows in flight per thread, forward phases
+#endif
+#ifndef PCB_BN_UB
+#define PCB_BN_UB 4   // rows in flight per thread, backward phases (two loads per row)
+#endif
+#ifndef PCB_BN_MINB
+#define PCB_BN_MINB 2 // __launch_bounds__ min CTAs per SM
+#endif
+#ifdef PCB_BN_TRACE   // kernel-tuning aid: per-CTA %globaltimer stamps at the phase boundaries
+__device__ unsigned long long g_bn_trace[8 * 1024];
+#define BN_STAMP(i)                                                                   \
+    do {                                                                              \
+        if (threadIdx.x == 0 && blockIdx.x < 1024) {                                  \
+            unsigned long long t_;                                                    \
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                    \
+            g_bn_trace[blockIdx.x * 8 + (i)] = t_;                                    \
+        }                                                                             \
+    } while (0)
+#else
+#define BN_STAMP(i)
+#endif
 constexpr int kBnThreads = 256;
-constexpr int kBnMaxParts = PCB_NUM_SMS * 4;
+constexpr int kBnMaxParts = PCB_NUM_SMS * 2;      // at most 2 CTAs per SM (register budget) -> <= 296 partials
 
 // VecIO<T, V>: V consecutive channels per thread, one 16-byte access for (float,4) and (bf16,8),
 // one 8-byte access for (bf16,4).  ldraw/cvt split the load from its first use so that several
@@ -217,7 +239,9 @@ __device__ __forceinline__ void column_reduce(F &f, int64_t units, int C, int64_
     }
 }
 
-// elementwise pass over all units, grid-strided
+// elementwise pass over all units, grid-strided.  (Handing chunks out dynamically through a
+// ticket counter balanced the SMs -- the slowest finishes this phase ~25 % after the median --
+// but the per-chunk __syncthreads and the smaller number of loads in flight cost more than that.)
 template <int V, int U, typename F>
 __device__ __forceinline__ void row_stream(F &f, int64_t units, int C)
 {
@@ -239,22 +263,34 @@ __device__ __forceinline__ void row_stream(F &f, int64_t units, int C)
     }
 }
 
-// sum over the CTA partials of the NACC accumulators of channel c (one warp; fixed order)
+// sum over the CTA partials of the NACC accumulators of channel c (one warp; fixed order).  All
+// loads are issued before the first add: the fold sits between two grid barriers, so its latency
+// (one L2 round trip instead of ten) is on every CTA's critical path.
+constexpr int kFoldJ = (kBnMaxParts + 31) / 32;
 template <int NACC>
 __device__ __forceinline__ void fold_channel(const float *parts, int nparts, int C, int c, float s[NACC])
 {
     const int lane = threadIdx.x & 31;
+    float v[kFoldJ][NACC];
 #pragma unroll
-    for (int a = 0; a < NACC; ++a) s[a] = 0.f;
-#pragma unroll 4
-    for (int i = lane; i < nparts; i += 32)
+    for (int j = 0; j < kFoldJ; ++j) {
+        const int i = lane + 32 * j;
 #pragma unroll
-        for (int a = 0; a < NACC; ++a) s[a] += __ldcg(parts + ((size_t)i * NACC + a) * C + c);
+        for (int a = 0; a < NACC; ++a) v[j][a] = i < nparts ? __ldcg(parts + ((size_t)i * NACC + a) * C + c) : 0.f;
+    }
 #pragma unroll
-    for (int a = 0; a < NACC; ++a)
+    for (int a = 0; a < NACC; ++a) {
+        s[a] = 0.f;
+#pragma unroll
+        for (int j = 0; j < kFoldJ; ++j) s[a] += v[j][a];
 #pragma unroll
         for (int off = 16; off; off >>= 1) s[a] += __shfl_xor_sync(PCB_FULL_MASK, s[a], off);
+    }
 }
+
+// channel -> warp assignment of the fold: consecutive channels go to different CTAs (SMs)
+#define PCB_FOLD_LOOP(c, C) \
+    for (int c = blockIdx.x + (threadIdx.x >> 5) * gridDim.x; c < (C); c += gridDim.x * (kBnThreads / 32))
 
 // ---------------------------------------------------------------------------------------------
 // forward
@@ -276,7 +312,7 @@ struct FwdStats {
         for (int i = 0; i < V; ++i) {
             const float d = v[i] - s[i];
             acc[0][i] += d;
-            acc[1][i] += d * d;
+            acc[1][i] = fmaf(d, d, acc[1][i]);
         }
     }
 };
@@ -358,51 +394,55 @@ struct BnFwdArgs {
     int64_t M, upc;
     int C, pool_k, relu, nparts;
     float eps, momentum;
-    int dbg;
 };
 
 template <typename T, int V>
-__global__ void __launch_bounds__(kBnThreads)
+__global__ void __launch_bounds__(kBnThreads, PCB_BN_MINB)
 bn_fwd_fused_kernel(const BnFwdArgs a)
 {
     cg::grid_group grid = cg::this_grid();
+    BN_STAMP(0);
     const T *y = (const T *)a.y;
     const int C = a.C;
     float *parts = a.work + 3 * (size_t)C;
     __shared__ float s_part[2][kBnThreads][V];
-    if ((int)blockIdx.x < a.nparts && !(a.dbg & 2)) {
+    if ((int)blockIdx.x < a.nparts) {
         FwdStats<T, V> f;
         f.y = y, f.C = C;
-        column_reduce<2, V, 4>(f, a.M, C, a.upc, parts, s_part);
+        column_reduce<2, V, PCB_BN_U>(f, a.M, C, a.upc, parts, s_part);
     }
-    if (!(a.dbg & 1)) grid.sync();
+    BN_STAMP(1);
+    grid.sync();
+    BN_STAMP(2);
     // mean / invstd of y from the shifted sums; running statistics update (momentum, unbiased
     // variance, conv bias added to the running mean) as torch.nn.functional.batch_norm does
     {
         const int lane = threadIdx.x & 31;
-        const int nw = gridDim.x * (kBnThreads / 32);
-        for (int c = blockIdx.x * (kBnThreads / 32) + (threadIdx.x >> 5); c < C; c += nw) {
+        PCB_FOLD_LOOP(c, C) {
+            // operands of the finalize step first, so that their latency overlaps the fold's
+            const float shift = (float)y[c];
+            const float b = a.bias ? a.bias[c] : 0.f;
+            const float rm = a.running_mean ? a.running_mean[c] : 0.f, rv = a.running_mean ? a.running_var[c] : 0.f;
             float s[2];
             fold_channel<2>(parts, a.nparts, C, c, s);
             if (lane == 0) {
                 const float M = (float)a.M;
-                const float shift = (float)y[c];
                 const float m1 = s[0] / M;
                 const float var = fmaxf(s[1] / M - m1 * m1, 0.f);
                 const float mu = shift + m1;                  // mean of the bias-free pre-activation
                 a.mean[c] = mu;
                 a.invstd[c] = rsqrtf(var + a.eps);
                 if (a.running_mean) {
-                    const float b = a.bias ? a.bias[c] : 0.f;
-                    a.running_mean[c] = (1.f - a.momentum) * a.running_mean[c] + a.momentum * (mu + b);
+                    a.running_mean[c] = (1.f - a.momentum) * rm + a.momentum * (mu + b);
                     const float unbiased = a.M > 1 ? var * (M / (float)(a.M - 1)) : var;
-                    a.running_var[c] = (1.f - a.momentum) * a.running_var[c] + a.momentum * unbiased;
+                    a.running_var[c] = (1.f - a.momentum) * rv + a.momentum * unbiased;
                 }
             }
         }
     }
-    if (!(a.dbg & 1)) grid.sync();
-    if (a.dbg & 4) return;
+    BN_STAMP(3);
+    grid.sync();
+    BN_STAMP(4);
     if (a.pool_k > 1) {
         FwdApplyPooled<T, V, 8> f;
         f.y = y, f.out = (T *)a.out, f.mean = a.mean, f.invstd = a.invstd, f.gamma = a.gamma, f.beta = a.beta;
@@ -412,8 +452,9 @@ bn_fwd_fused_kernel(const BnFwdArgs a)
         FwdApply<T, V> f;
         f.y = y, f.out = (T *)a.out, f.mean = a.mean, f.invstd = a.invstd, f.gamma = a.gamma, f.beta = a.beta;
         f.C = C, f.relu = a.relu;
-        row_stream<V, 4>(f, a.M, C);
+        row_stream<V, PCB_BN_U>(f, a.M, C);
     }
+    BN_STAMP(5);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -428,15 +469,16 @@ struct BwdBase {
     const float *mean, *invstd, *gamma, *beta, *sums;
     int C, relu, pool_k;
     float invM;
-    float m[V], is[V], sc[V], sh[V], a0[V], a1[V];
+    float nm[V], is[V], sc[V], sh[V], a0[V], a1[V];      // nm = -mean * invstd: yhat = fma(y, is, nm)
     __device__ __forceinline__ void consts(int c, bool with_sums)
     {
 #pragma unroll
         for (int i = 0; i < V; ++i) {
-            m[i] = mean[c + i];
+            const float m = mean[c + i];
             is[i] = invstd[c + i];
+            nm[i] = -m * is[i];
             sc[i] = is[i] * gamma[c + i];                     // same expressions as the forward pass
-            sh[i] = beta[c + i] - m[i] * sc[i];
+            sh[i] = beta[c + i] - m * sc[i];
             if (with_sums) {
                 a0[i] = __ldcg(sums + c + i) * invM;
                 a1[i] = __ldcg(sums + C + c + i) * invM;
@@ -451,7 +493,7 @@ struct BwdBase {
         VecIO<T, V>::cvt(yr, v);
 #pragma unroll
         for (int i = 0; i < V; ++i) {
-            yh[i] = (v[i] - m[i]) * is[i];
+            yh[i] = fmaf(v[i], is[i], nm[i]);
             const float z = fmaf(v[i], sc[i], sh[i]);
             bool pass = !relu || z > 0.f;
             if (k >= 0) pass = pass && (k == AmIO<V>::get(am, i));
@@ -463,7 +505,7 @@ struct BwdBase {
 #pragma unroll
         for (int i = 0; i < V; ++i) {
             acc[0][i] += dy[i];
-            acc[1][i] += dy[i] * yh[i];
+            acc[1][i] = fmaf(dy[i], yh[i], acc[1][i]);
             acc[2][i] += yh[i];
         }
     }
@@ -471,7 +513,7 @@ struct BwdBase {
     {
         float o[V];
 #pragma unroll
-        for (int i = 0; i < V; ++i) o[i] = sc[i] * (dy[i] - a0[i] - yh[i] * a1[i]);
+        for (int i = 0; i < V; ++i) o[i] = sc[i] * fmaf(-yh[i], a1[i], dy[i] - a0[i]);
         VecIO<T, V>::store(gy + r * C + c, o);
     }
 };
@@ -560,7 +602,6 @@ struct BnBwdArgs {
     float *work;
     int64_t M, upc;
     int C, pool_k, relu, nparts;
-    int dbg;
 };
 
 template <typename T, int V, typename F>
@@ -572,15 +613,16 @@ __device__ __forceinline__ void bwd_fill(F &f, const BnBwdArgs &a)
 }
 
 template <typename T, int V>
-__global__ void __launch_bounds__(kBnThreads)
+__global__ void __launch_bounds__(kBnThreads, PCB_BN_MINB)
 bn_bwd_fused_kernel(const BnBwdArgs a)
 {
     cg::grid_group grid = cg::this_grid();
+    BN_STAMP(0);
     const int C = a.C;
     float *parts = a.work + 3 * (size_t)C;
     const bool pooled = a.pool_k > 1;
     __shared__ float s_part[3][kBnThreads][V];
-    if ((int)blockIdx.x < a.nparts && !(a.dbg & 2)) {
+    if ((int)blockIdx.x < a.nparts) {
         if (pooled) {
             BwdGroups<T, V, false, 4> f;
             bwd_fill<T, V>(f, a);
@@ -588,27 +630,30 @@ bn_bwd_fused_kernel(const BnBwdArgs a)
         } else {
             BwdRows<T, V, false> f;
             bwd_fill<T, V>(f, a);
-            column_reduce<3, V, 4>(f, a.M, C, a.upc, parts, s_part);
+            column_reduce<3, V, PCB_BN_UB>(f, a.M, C, a.upc, parts, s_part);
         }
     }
-    if (!(a.dbg & 1)) grid.sync();
+    BN_STAMP(1);
+    grid.sync();
+    BN_STAMP(2);
     // work[0:C] = sum dy (= grad beta), [C:2C] = sum dy*yhat (= grad gamma), [2C:3C] = gradient of
     // the folded conv bias = sum_rows gy = -gamma*invstd * (sum yhat) * (sum dy*yhat) / M
     {
         const int lane = threadIdx.x & 31;
-        const int nw = gridDim.x * (kBnThreads / 32);
-        for (int c = blockIdx.x * (kBnThreads / 32) + (threadIdx.x >> 5); c < C; c += nw) {
+        PCB_FOLD_LOOP(c, C) {
+            const float gi = a.gamma[c] * a.invstd[c];
             float s[3];
             fold_channel<3>(parts, a.nparts, C, c, s);
             if (lane == 0) {
                 a.work[c] = s[0];
                 a.work[C + c] = s[1];
-                a.work[2 * C + c] = -(a.gamma[c] * a.invstd[c]) * s[2] * s[1] / (float)a.M;
+                a.work[2 * C + c] = -gi * s[2] * s[1] / (float)a.M;
             }
         }
     }
-    if (!(a.dbg & 1)) grid.sync();
-    if (a.dbg & 4) return;
+    BN_STAMP(3);
+    grid.sync();
+    BN_STAMP(4);
     if (pooled) {
         BwdGroups<T, V, true, 4> f;
         bwd_fill<T, V>(f, a);
@@ -616,15 +661,16 @@ bn_bwd_fused_kernel(const BnBwdArgs a)
     } else {
         BwdRows<T, V, true> f;
         bwd_fill<T, V>(f, a);
-        row_stream<V, 4>(f, a.M, C);
+        row_stream<V, PCB_BN_UB>(f, a.M, C);
     }
+    BN_STAMP(5);
 }
 
 // ---------------------------------------------------------------------------------------------
 // launch
 // ---------------------------------------------------------------------------------------------
 // co-resident CTAs of `kernel` on the current device (cooperative launch limit), capped at
-// PCB_BN_CTAS_PER_SM per SM (default 4) and kBnMaxParts in total
+// PCB_BN_CTAS_PER_SM per SM (default 2) and kBnMaxParts in total
 template <typename K>
 static int coop_capacity(K kernel)
 {
@@ -633,7 +679,7 @@ static int coop_capacity(K kernel)
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kBnThreads, 0);
     const char *e = getenv("PCB_BN_CTAS_PER_SM");
-    const int cap = e ? atoi(e) : 4;
+    const int cap = e ? atoi(e) : 2;
     if (cap >= 1 && occ > cap) occ = cap;
     int g = occ * sms;
     if (g > kBnMaxParts) g = kBnMaxParts;
@@ -703,6 +749,13 @@ using namespace pcb;
 
 static inline bool al16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
+#ifdef PCB_BN_TRACE
+PCB_API int pcb_bn_debug_trace(unsigned long long *host_out)
+{
+    return (int)cudaMemcpyFromSymbol(host_out, g_bn_trace, sizeof(g_bn_trace));
+}
+#endif
+
 PCB_API int64_t pcb_bn_work_floats(int C) { return 3 * (int64_t)C * (1 + kBnMaxParts); }
 
 PCB_API int pcb_bn_fwd_rows(const void *y, int dtype, int64_t M, int C, int pool_k, const float *bias,
@@ -718,7 +771,6 @@ PCB_API int pcb_bn_fwd_rows(const void *y, int dtype, int64_t M, int C, int pool
     a.running_mean = running_mean, a.running_var = running_var;
     a.mean = mean, a.invstd = invstd, a.work = work, a.M = M, a.C = C, a.pool_k = pool_k, a.relu = relu;
     a.eps = eps, a.momentum = momentum, a.upc = 0, a.nparts = 0;
-    a.dbg = getenv("PCB_BN_DBG") ? atoi(getenv("PCB_BN_DBG")) : 0;
     cudaStream_t st = (cudaStream_t)stream;
     if (!dtype) return bn_fwd_launch<float, 4>(a, st);
     if (C % 8 == 0 && al16(y) && al16(out)) return bn_fwd_launch<__nv_bfloat16, 8>(a, st);
@@ -735,7 +787,6 @@ PCB_API int pcb_bn_bwd_rows(const void *gz, const void *y, const unsigned char *
     BnBwdArgs a;
     a.gz = gz, a.y = y, a.argmax = argmax, a.gy = gy, a.mean = mean, a.invstd = invstd, a.gamma = gamma, a.beta = beta;
     a.work = work, a.M = M, a.C = C, a.pool_k = pool_k, a.relu = relu, a.upc = 0, a.nparts = 0;
-    a.dbg = getenv("PCB_BN_DBG") ? atoi(getenv("PCB_BN_DBG")) : 0;
     cudaStream_t st = (cudaStream_t)stream;
     if (!dtype) return bn_bwd_launch<float, 4>(a, st);
     if (C % 8 == 0 && al16(y) && al16(gz) && al16(gy)) return bn_bwd_launch<__nv_bfloat16, 8>(a, st);
