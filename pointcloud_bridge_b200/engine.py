@@ -55,6 +55,13 @@ class FpsStartBuffers:
             buf.copy_(stage, non_blocking=True)
 
 
+def _nll_mean(logp, labels):
+    """F.nll_loss(logp, labels) (mean over rows, no class weights, no ignore_index) as gather + mean:
+    ATen's 2-D nll_loss reduces 65 536 rows in a single thread block (68 us forward + 39 us
+    backward in the round-1 profile)."""
+    return -logp.gather(1, labels.view(-1, 1)).mean()
+
+
 class Trainer:
     """forward -> loss -> backward -> one flat NCCL all-reduce -> fused Adam.
 
@@ -85,7 +92,7 @@ class Trainer:
                 out = self.net(*inputs)
             logits = out[0] if isinstance(out, tuple) else out
             if self.loss_fn is None:       # sem-seg nets return log-probabilities [B,N,C]
-                loss = F.nll_loss(logits.float().reshape(-1, logits.shape[-1]), labels.reshape(-1))
+                loss = _nll_mean(logits.float().reshape(-1, logits.shape[-1]), labels.reshape(-1))
             else:
                 loss = self.loss_fn(logits.float(), labels, *loss_inputs)
             loss.backward()

@@ -568,16 +568,29 @@ class StepContext:
 
     def __init__(self, module: torch.nn.Module, bf16: bool):
         self.counters = []
-        self.params = [p for p in module.parameters() if p.dim() >= 2] if bf16 else []
-        self.shadows = [torch.empty(p.shape[0], p[0].numel(), dtype=torch.bfloat16, device=p.device) for p in self.params]
-        self.by_id = {id(p): s for p, s in zip(self.params, self.shadows)}
+        params = [p for p in module.parameters() if p.dim() >= 2] if bf16 else []
+        # shadows are [N, K rounded up to 8] with zero pad columns (written once, here): the padded
+        # ones match the zero-padded rows of group_points(pad_to=8)
+        self.dense, self.dense_shadows, self.ragged = [], [], []
+        self.by_id = {}
+        for p in params:
+            n, k = p.shape[0], p[0].numel()
+            sh = torch.zeros(n, -(-k // 8) * 8, dtype=torch.bfloat16, device=p.device)
+            self.by_id[id(p)] = sh
+            if sh.shape[1] == k:
+                self.dense.append(p)
+                self.dense_shadows.append(sh)
+            else:
+                self.ragged.append((p, sh[:, :k]))
 
     def __enter__(self):
         global _step_ctx
         self.counters = []
-        if self.params:
-            with torch.no_grad():
-                torch._foreach_copy_(self.shadows, [p.detach().flatten(1) for p in self.params])
+        with torch.no_grad():
+            if self.dense:
+                torch._foreach_copy_(self.dense_shadows, [p.detach().flatten(1) for p in self.dense])
+            for p, view in self.ragged:
+                view.copy_(p.detach().flatten(1))
         _step_ctx = self
         return self
 
@@ -607,7 +620,9 @@ class _LinearRows(torch.autograd.Function):
     def forward(ctx, x, w, w_lp):
         # w_lp: the weight already in x's dtype (StepContext shadow) or None
         wl = w_lp if w_lp is not None else w.to(x.dtype)
-        if wl.shape[1] != x.shape[1]:
+        if wl.shape[1] > x.shape[1]:                      # padded shadow, dense rows
+            wl = wl[:, :x.shape[1]]
+        elif wl.shape[1] < x.shape[1]:
             wl = torch.nn.functional.pad(wl, (0, x.shape[1] - wl.shape[1]))
         ctx.save_for_backward(x, wl)
         ctx.kw = w.shape[1]
@@ -628,7 +643,7 @@ class _LinearRows(torch.autograd.Function):
             if c and M % c == 0 and M // c >= 8:
                 p = M // c
                 part = torch.bmm(gy.view(p, c, -1).transpose(1, 2), x.view(p, c, -1))   # [p,N,K]
-                gw = part.float().sum(dim=0)
+                gw = part.sum(dim=0, dtype=torch.float32)
             else:
                 gw = torch.mm(gy.t(), x).float()
             if gw.shape[1] != ctx.kw:
