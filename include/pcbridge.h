@@ -109,6 +109,17 @@ int pcb_interpolate_bwd_f32(const float *grad_out, const int64_t *idx, const flo
                             int N, int S, int D, int k, int channels_first, float *grad_points2,
                             pcb_stream_t stream);
 
+/* a7 fused for training under bf16 autocast: the input rows of a feature-propagation MLP in one pass,
+ *          pointnet_util.py:325-340 (interpolate, torch.cat([points1, interpolated]), cast)
+ * points1 [B,N,D1] (fp32 or bf16; NULL when D1 == 0), points2 [B,S,D2] (fp32 or bf16), idx/weight [B,N,k]
+ * -> out [B,N,pitch] bf16 = [points1 | sum_j weight_j * points2[idx_j] | zeros]; D1, D2, pitch even.
+ * backward w.r.t. points2 (zero-initialised fp32 [B,S,D2]); the gradient of points1 is grad_out[..., :D1]. */
+int pcb_fp_concat_bf16(const void *points1, int p1_bf16, const void *points2, int p2_bf16, const int64_t *idx,
+                       const float *weight, int B, int N, int S, int D1, int D2, int k, int pitch, void *out,
+                       pcb_stream_t stream);
+int pcb_fp_concat_bwd_bf16(const void *grad_out, const int64_t *idx, const float *weight, int B, int N, int S,
+                           int D1, int D2, int k, int pitch, float *grad_points2, pcb_stream_t stream);
+
 /* ---- a8  DGCNN.knn                        Highway_bridge/models/DGCNN.py:49-70
  * x [B,D,N] (channels_first != 0, as DGCNN passes it) or [B,N,D]; out_idx [B,N,k] ordered by
  * (pairwise distance, index), self included; out_dist [B,N,k] may be NULL.  1 <= k <= 64,

@@ -33,6 +33,8 @@ _SIGNATURES = {
     "pcb_three_nn_f32": [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp],
     "pcb_interpolate_f32": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp],
     "pcb_interpolate_bwd_f32": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp],
+    "pcb_fp_concat_bf16": [_vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp],
+    "pcb_fp_concat_bwd_bf16": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp],
     "pcb_knn_f32": [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp],
     "pcb_knn_cdist_f32": [_vp, _i, _i, _i, _vp, _vp, _vp],
     "pcb_graph_feature_f32": [_vp, _vp, _i, _i, _i, _i, _vp, _vp],

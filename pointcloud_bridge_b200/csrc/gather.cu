@@ -314,6 +314,66 @@ interp_bwd_kernel(const float *__restrict__ gout, const int64_t *__restrict__ id
 }
 
 // ------------------------------------------------------------------------------------------
+// Input rows of a feature-propagation MLP in one pass (training under bf16 autocast):
+//   out[b,n,:] = [ points1[b,n,:D1] | sum_j w[b,n,j] * points2[b, idx[b,n,j], :D2] | 0 ... ]  as bf16,
+// i.e. interpolate + concat + cast (pointnet_util.py:325-340) without the fp32 intermediate, the
+// torch.cat and the two dtype copies.  One thread per PAIR of output channels (D1, D2, pitch even).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float2 ld_pair(const float *p) { return __ldg(reinterpret_cast<const float2 *>(p)); }
+__device__ __forceinline__ float2 ld_pair(const __nv_bfloat16 *p)
+{
+    return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(p));
+}
+
+template <typename T1, typename T2>
+__global__ void __launch_bounds__(kThreads)
+fp_concat_kernel(const T1 *__restrict__ p1, const T2 *__restrict__ p2, const int64_t *__restrict__ idx,
+                 const float *__restrict__ w, int S, int D1, int D2, int k, FastDiv dHalfPitch, FastDiv dN,
+                 unsigned total, __nv_bfloat16 *__restrict__ out)
+{
+    const unsigned t = blockIdx.x * kThreads + threadIdx.x;
+    if (t >= total) return;
+    const unsigned rowg = dHalfPitch.div(t);           // b*N + n
+    const int c = (int)(t - rowg * dHalfPitch.d) * 2;
+    float2 v = make_float2(0.f, 0.f);
+    if (c < D1) {
+        v = ld_pair(p1 + (size_t)rowg * D1 + c);
+    } else if (c < D1 + D2) {
+        const unsigned b = dN.div(rowg);
+        const int c2 = c - D1;
+        for (int j = 0; j < k; ++j) {
+            long long i = idx[(size_t)rowg * k + j];
+            i = i < 0 ? 0 : (i > S - 1 ? S - 1 : i);
+            const float wj = __ldg(w + (size_t)rowg * k + j);
+            const float2 f = ld_pair(p2 + ((size_t)b * S + i) * D2 + c2);
+            const float px = __fmul_rn(f.x, wj), py = __fmul_rn(f.y, wj);
+            v.x = j == 0 ? px : __fadd_rn(v.x, px);
+            v.y = j == 0 ? py : __fadd_rn(v.y, py);
+        }
+    }
+    *reinterpret_cast<__nv_bfloat162 *>(out + (size_t)t * 2) = __floats2bfloat162_rn(v.x, v.y);
+}
+
+// backward w.r.t. points2: gp2[b, idx, c] += w * gout[b, n, D1 + c]  (gout rows have `pitch` elements)
+__global__ void __launch_bounds__(kThreads)
+fp_concat_bwd_kernel(const __nv_bfloat16 *__restrict__ gout, const int64_t *__restrict__ idx,
+                     const float *__restrict__ w, int S, int D1, int D2, int k, int pitch, FastDiv dD2, FastDiv dN,
+                     unsigned total, float *__restrict__ gp2)
+{
+    const unsigned t = blockIdx.x * kThreads + threadIdx.x;
+    if (t >= total) return;
+    const unsigned rowg = dD2.div(t);
+    const int c = (int)(t - rowg * dD2.d);
+    const unsigned b = dN.div(rowg);
+    const float g = __bfloat162float(gout[(size_t)rowg * pitch + D1 + c]);
+    for (int j = 0; j < k; ++j) {
+        long long i = idx[(size_t)rowg * k + j];
+        i = i < 0 ? 0 : (i > S - 1 ? S - 1 : i);
+        atomicAdd(gp2 + ((size_t)b * S + i) * D2 + c, g * __ldg(w + (size_t)rowg * k + j));
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // square_distance (materialising; kept for API completeness -- the product path never needs it)
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads)
@@ -580,6 +640,58 @@ PCB_API int pcb_interpolate_bwd_f32(const float *grad_out, const int64_t *idx, c
             grad_out + (size_t)b0 * N * D, idx + (size_t)b0 * N * k, weight + (size_t)b0 * N * k, N, S, D, k,
             channels_first, make_fastdiv(channels_first ? N : D), make_fastdiv(channels_first ? D : N), total,
             grad_points2 + (size_t)b0 * S * D);
+    }
+    PCB_RETURN_LAUNCH_STATUS();
+}
+
+template <typename T1, typename T2>
+static int fp_concat_launch(const void *p1, const void *p2, const int64_t *idx, const float *w, int B, int N, int S,
+                            int D1, int D2, int k, int pitch, void *out, cudaStream_t st)
+{
+    const int step = clouds_per_launch(B, (int64_t)N * pitch);
+    PCB_REQUIRE(step > 0, PCB_ERANGE);
+    for (int b0 = 0; b0 < B; b0 += step) {
+        const int nb = B - b0 < step ? B - b0 : step;
+        const unsigned total = (unsigned)((int64_t)nb * N * (pitch / 2));
+        fp_concat_kernel<T1, T2><<<blocks_for(total), kThreads, 0, st>>>(
+            p1 ? (const T1 *)p1 + (size_t)b0 * N * D1 : nullptr, (const T2 *)p2 + (size_t)b0 * S * D2,
+            idx + (size_t)b0 * N * k, w + (size_t)b0 * N * k, S, D1, D2, k, make_fastdiv(pitch / 2), make_fastdiv(N),
+            total, (__nv_bfloat16 *)out + (size_t)b0 * N * pitch);
+    }
+    PCB_RETURN_LAUNCH_STATUS();
+}
+
+PCB_API int pcb_fp_concat_bf16(const void *points1, int p1_bf16, const void *points2, int p2_bf16, const int64_t *idx,
+                               const float *weight, int B, int N, int S, int D1, int D2, int k, int pitch, void *out,
+                               pcb_stream_t stream)
+{
+    PCB_REQUIRE(points2 && idx && weight && out && (points1 || D1 == 0), PCB_EINVAL);
+    PCB_REQUIRE(B > 0 && N > 0 && S > 0 && D1 >= 0 && D2 > 0 && k > 0, PCB_EINVAL);
+    PCB_REQUIRE(D1 % 2 == 0 && D2 % 2 == 0 && pitch % 2 == 0 && pitch >= D1 + D2, PCB_ERANGE);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (p1_bf16 && p2_bf16)
+        return fp_concat_launch<__nv_bfloat16, __nv_bfloat16>(points1, points2, idx, weight, B, N, S, D1, D2, k, pitch, out, st);
+    if (p1_bf16)
+        return fp_concat_launch<__nv_bfloat16, float>(points1, points2, idx, weight, B, N, S, D1, D2, k, pitch, out, st);
+    if (p2_bf16)
+        return fp_concat_launch<float, __nv_bfloat16>(points1, points2, idx, weight, B, N, S, D1, D2, k, pitch, out, st);
+    return fp_concat_launch<float, float>(points1, points2, idx, weight, B, N, S, D1, D2, k, pitch, out, st);
+}
+
+PCB_API int pcb_fp_concat_bwd_bf16(const void *grad_out, const int64_t *idx, const float *weight, int B, int N, int S,
+                                   int D1, int D2, int k, int pitch, float *grad_points2, pcb_stream_t stream)
+{
+    PCB_REQUIRE(grad_out && idx && weight && grad_points2, PCB_EINVAL);
+    PCB_REQUIRE(B > 0 && N > 0 && S > 0 && D1 >= 0 && D2 > 0 && k > 0 && pitch >= D1 + D2, PCB_EINVAL);
+    const int step = clouds_per_launch(B, (int64_t)N * D2);
+    PCB_REQUIRE(step > 0, PCB_ERANGE);
+    for (int b0 = 0; b0 < B; b0 += step) {
+        const int nb = B - b0 < step ? B - b0 : step;
+        const unsigned total = (unsigned)((int64_t)nb * N * D2);
+        fp_concat_bwd_kernel<<<blocks_for(total), kThreads, 0, (cudaStream_t)stream>>>(
+            (const __nv_bfloat16 *)grad_out + (size_t)b0 * N * pitch, idx + (size_t)b0 * N * k,
+            weight + (size_t)b0 * N * k, S, D1, D2, k, pitch, make_fastdiv(D2), make_fastdiv(N), total,
+            grad_points2 + (size_t)b0 * S * D2);
     }
     PCB_RETURN_LAUNCH_STATUS();
 }

@@ -381,6 +381,67 @@ def three_interpolate(points2: torch.Tensor, idx: torch.Tensor, weight: torch.Te
     return _Interpolate.apply(points2, idx, weight, bool(channels_first))
 
 
+class _FpConcat(torch.autograd.Function):
+    """Input rows of a feature-propagation MLP under bf16 autocast, one kernel instead of
+    interpolate (fp32) + torch.cat + cast: out [B,N,pitch] bf16 = [points1 | interp(points2) | 0]."""
+
+    @staticmethod
+    def forward(ctx, points1, points2, idx, weight, pitch):
+        idx = _i64(idx, "idx")
+        weight = _f32(weight, "weight")
+        B, N, k = idx.shape
+        if not points2.is_contiguous():
+            points2 = points2.contiguous()
+        S, D2 = points2.shape[1], points2.shape[2]
+        D1 = 0
+        if points1 is not None:
+            if not points1.is_contiguous():
+                points1 = points1.contiguous()
+            D1 = points1.shape[2]
+        dev = points2.device
+        out = torch.empty(B, N, pitch, dtype=torch.bfloat16, device=dev)
+        _call("pcb_fp_concat_bf16", dev, points1.data_ptr() if D1 else None,
+              int(D1 > 0 and points1.dtype == torch.bfloat16), points2.data_ptr(),
+              int(points2.dtype == torch.bfloat16), idx.data_ptr(), weight.data_ptr(), B, N, S, D1, D2, k, pitch,
+              out.data_ptr(),
+              alg_bytes=B * ((points1.element_size() * N * D1 if D1 else 0) + points2.element_size() * S * D2
+                             + 12 * k * N + 2 * N * pitch))
+        ctx.save_for_backward(idx, weight)
+        ctx.meta = (B, N, S, D1, D2, k, pitch, points1.dtype if D1 else None, points2.dtype)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        idx, weight = ctx.saved_tensors
+        B, N, S, D1, D2, k, pitch, dt1, dt2 = ctx.meta
+        gout = gout.contiguous()
+        if gout.dtype != torch.bfloat16:
+            gout = gout.to(torch.bfloat16)
+        gp1 = gp2 = None
+        if D1 and ctx.needs_input_grad[0]:
+            gp1 = gout[..., :D1].to(dt1)
+        if ctx.needs_input_grad[1]:
+            gp2 = torch.zeros(B, S, D2, dtype=torch.float32, device=gout.device)
+            _call("pcb_fp_concat_bwd_bf16", gout.device, gout.data_ptr(), idx.data_ptr(), weight.data_ptr(), B, N, S,
+                  D1, D2, k, pitch, gp2.data_ptr(), alg_bytes=B * (4 * S * D2 + 12 * k * N + 2 * N * D2))
+            if dt2 != torch.float32:
+                gp2 = gp2.to(dt2)
+        return gp1, gp2, None, None, None
+
+
+def fp_concat_supported(points1, points2) -> bool:
+    ok = lambda t: t.is_cuda and t.dtype in (torch.float32, torch.bfloat16) and t.shape[2] % 2 == 0
+    return (torch.is_autocast_enabled() and torch.get_autocast_dtype("cuda") == torch.bfloat16
+            and ok(points2) and (points1 is None or ok(points1)) and os.environ.get("PCB_NO_FPCONCAT", "0") != "1")
+
+
+def fp_concat(points1, points2, idx, weight, pad_to: int = 8) -> torch.Tensor:
+    """[points1 [B,N,D1] | three_interpolate(points2 [B,S,D2], idx, weight) | zero pad] as bf16 rows
+    [B,N,pitch] (pointnet_util.py:325-340 fused); points1 may be None."""
+    D = points2.shape[2] + (points1.shape[2] if points1 is not None else 0)
+    return _FpConcat.apply(points1, points2, idx, weight, -(-D // pad_to) * pad_to)
+
+
 # ---------------------------------------------------------------------------------------------
 # BatchNorm (batch statistics) + ReLU (+ max over the neighbour axis) on point-major rows
 # ---------------------------------------------------------------------------------------------

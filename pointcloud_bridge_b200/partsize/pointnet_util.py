@@ -251,6 +251,12 @@ class PointNetFeaturePropagation(nn.Module):
             interp = p2.repeat(1, N, 1)
         else:
             _, idx, weight = ops.three_nn(x1, x2, 3)
+            p1 = _rows(points1) if points1 is not None else None
+            if self.mlp_bns[0].training and ops.fp_concat_supported(p1, p2):
+                # bf16 training: interpolate + concat + cast in one pass, rows padded for the GEMM
+                rows = ops.fp_concat(p1, p2, idx, weight, pad_to=8)
+                y = mlp_rows(rows.view(B * N, -1), self.mlp_convs, self.mlp_bns)
+                return _cf_view(y, B, N)
             interp = ops.three_interpolate(p2, idx, weight, channels_first=False)
         if points1 is not None:
             interp = torch.cat([_rows(points1).to(interp.dtype), interp], dim=-1)

@@ -283,3 +283,31 @@ def test_backward_of_gathers_matches_torch_autograd():
         (ga,) = torch.autograd.grad(out, p_in, g)
         (gb,) = torch.autograd.grad(ref, p2, g.transpose(1, 2) if cf else g)
         torch.testing.assert_close(ga.transpose(1, 2) if cf else ga, gb, rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("dt1,dt2", [(torch.float32, torch.float32), (torch.bfloat16, torch.bfloat16),
+                                     (torch.bfloat16, torch.float32), (None, torch.bfloat16)])
+def test_fp_concat_equals_interpolate_cat_cast(dt1, dt2):
+    """The fused feature-propagation input rows (bf16 training) against the unfused chain
+    three_interpolate (fp32) -> cat -> bf16: forward bit-equal, backward within bf16/atomic noise."""
+    torch.manual_seed(1)
+    B, N, S, D1, D2, k = 2, 300, 41, 0 if dt1 is None else 10, 14, 3
+    p1 = torch.randn(B, N, D1, device=DEV).to(dt1).requires_grad_(True) if D1 else None
+    p2 = torch.randn(B, S, D2, device=DEV).to(dt2).requires_grad_(True)
+    idx = torch.randint(0, S, (B, N, k), device=DEV)
+    w = torch.rand(B, N, k, device=DEV)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        assert ops.fp_concat_supported(p1, p2)
+        out = ops.fp_concat(p1, p2, idx, w, pad_to=8)
+    D = D1 + D2
+    assert out.dtype == torch.bfloat16 and out.shape == (B, N, -(-D // 8) * 8)
+    interp = ops.three_interpolate(p2, idx, w, channels_first=False)
+    ref = interp if p1 is None else torch.cat([p1.float(), interp], -1)
+    assert torch.equal(out[..., :D], ref.to(torch.bfloat16)) and not out[..., D:].any()
+    g = torch.randn_like(out)
+    ins = [p2] if p1 is None else [p1, p2]
+    ga = torch.autograd.grad(out, ins, g)
+    gb = torch.autograd.grad(ref, ins, g[..., :D].float())
+    for a, b in zip(ga, gb):
+        assert a.dtype == b.dtype
+        torch.testing.assert_close(a.float(), b.float(), rtol=2e-2, atol=2e-2)

@@ -67,7 +67,14 @@ def main():
                 with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
                     net(x9[:bsz])
             ms = timed(f, a.iters, 3, dev)
-            emit(config="c1 PN++ SSG sem-seg forward", batch=bsz, ms=round(ms, 3), points_per_s=round(bsz * N / ms * 1e3), n_gpus=1)
+            emit(config="c1 PN++ SSG sem-seg forward (eager launches)", batch=bsz, ms=round(ms, 3),
+                 points_per_s=round(bsz * N / ms * 1e3), n_gpus=1)
+            from pointcloud_bridge_b200.engine import BlockInference
+            inf = BlockInference(net, batch_blocks=bsz, amp=True, graph=True)
+            xb = x9[:bsz].contiguous()
+            ms = timed(lambda: inf.run(xb), a.iters, 4, dev)
+            emit(config="c1 PN++ SSG sem-seg forward + argmax (CUDA graph, fused tcgen05 SA blocks)", batch=bsz, ms=round(ms, 3),
+                 points_per_s=round(bsz * N / ms * 1e3), n_gpus=1)
     if "c3" in want:
         torch.manual_seed(0)
         net = dgcnn_mod.DGCNN(5, 20).to(dev).eval()
