@@ -324,14 +324,20 @@ struct FwdApply {
     const T *y;
     T *out;
     const float *mean, *invstd, *gamma, *beta;
+    const float *s_const;                                  // shared copy [sc | sh] of all C channels, or nullptr
     int C, relu;
     float sc[V], sh[V];
     __device__ __forceinline__ void init(int c)
     {
 #pragma unroll
         for (int i = 0; i < V; ++i) {
-            sc[i] = __ldcg(invstd + c + i) * gamma[c + i];
-            sh[i] = beta[c + i] - __ldcg(mean + c + i) * sc[i];
+            if (s_const) {
+                sc[i] = s_const[c + i];
+                sh[i] = s_const[C + c + i];
+            } else {
+                sc[i] = __ldcg(invstd + c + i) * gamma[c + i];
+                sh[i] = beta[c + i] - __ldcg(mean + c + i) * sc[i];
+            }
         }
     }
     __device__ __forceinline__ Pack load(int64_t r, int c) const { return VecIO<T, V>::ldraw(y + r * C + c); }
@@ -443,15 +449,29 @@ bn_fwd_fused_kernel(const BnFwdArgs a)
     BN_STAMP(3);
     grid.sync();
     BN_STAMP(4);
+    // Per-channel constants of the elementwise phase: computed once per CTA into shared memory with
+    // coalesced loads.  (Every thread fetching its own channels' mean / invstd from L2 right after
+    // the barrier -- 2368 warps x 16 requests on the same few cache lines -- serialised on one L2
+    // slice and cost ~10 us per launch whatever the layer size: round-1 phase trace.)
+    float *s_const = nullptr;
+    if (C <= kBnThreads * V) {                             // 2*C floats fit the statistics scratch
+        s_const = &s_part[0][0][0];
+        for (int c = threadIdx.x; c < C; c += kBnThreads) {
+            const float sc = __ldcg(a.invstd + c) * a.gamma[c];
+            s_const[c] = sc;
+            s_const[C + c] = a.beta[c] - __ldcg(a.mean + c) * sc;
+        }
+        __syncthreads();
+    }
     if (a.pool_k > 1) {
         FwdApplyPooled<T, V, 8> f;
         f.y = y, f.out = (T *)a.out, f.mean = a.mean, f.invstd = a.invstd, f.gamma = a.gamma, f.beta = a.beta;
-        f.C = C, f.relu = a.relu, f.argmax = a.argmax, f.pool_k = a.pool_k;
+        f.C = C, f.relu = a.relu, f.argmax = a.argmax, f.pool_k = a.pool_k, f.s_const = s_const;
         row_stream<V, 1>(f, a.M / a.pool_k, C);
     } else {
         FwdApply<T, V> f;
         f.y = y, f.out = (T *)a.out, f.mean = a.mean, f.invstd = a.invstd, f.gamma = a.gamma, f.beta = a.beta;
-        f.C = C, f.relu = a.relu;
+        f.C = C, f.relu = a.relu, f.s_const = s_const;
         row_stream<V, PCB_BN_U>(f, a.M, C);
     }
     BN_STAMP(5);
@@ -467,11 +487,20 @@ struct BwdBase {
     const unsigned char *argmax;
     T *gy;
     const float *mean, *invstd, *gamma, *beta, *sums;
+    const float *s_const;                                  // shared [nm | is | sc | sh | a0 | a1] x C, or nullptr
     int C, relu, pool_k;
     float invM;
     float nm[V], is[V], sc[V], sh[V], a0[V], a1[V];      // nm = -mean * invstd: yhat = fma(y, is, nm)
     __device__ __forceinline__ void consts(int c, bool with_sums)
     {
+        if (s_const) {
+#pragma unroll
+            for (int i = 0; i < V; ++i) {
+                nm[i] = s_const[c + i], is[i] = s_const[C + c + i], sc[i] = s_const[2 * C + c + i];
+                sh[i] = s_const[3 * C + c + i], a0[i] = s_const[4 * C + c + i], a1[i] = s_const[5 * C + c + i];
+            }
+            return;
+        }
 #pragma unroll
         for (int i = 0; i < V; ++i) {
             const float m = mean[c + i];
@@ -610,6 +639,7 @@ __device__ __forceinline__ void bwd_fill(F &f, const BnBwdArgs &a)
     f.y = (const T *)a.y, f.gz = (const T *)a.gz, f.argmax = a.argmax, f.gy = (T *)a.gy;
     f.mean = a.mean, f.invstd = a.invstd, f.gamma = a.gamma, f.beta = a.beta, f.sums = a.work;
     f.C = a.C, f.relu = a.relu, f.pool_k = a.pool_k, f.invM = 1.f / (float)a.M;
+    f.s_const = nullptr;
 }
 
 template <typename T, int V>
@@ -654,13 +684,32 @@ bn_bwd_fused_kernel(const BnBwdArgs a)
     BN_STAMP(3);
     grid.sync();
     BN_STAMP(4);
+    // per-channel constants of the elementwise phase through shared memory (see the forward kernel)
+    float *s_const = nullptr;
+    if (2 * C <= kBnThreads * V) {                         // 6*C floats fit the statistics scratch
+        s_const = &s_part[0][0][0];
+        const float invM = 1.f / (float)a.M;
+        for (int c = threadIdx.x; c < C; c += kBnThreads) {
+            const float m = a.mean[c], is = a.invstd[c];
+            const float sc = is * a.gamma[c];                // same expressions as BwdBase::consts
+            s_const[c] = -m * is;
+            s_const[C + c] = is;
+            s_const[2 * C + c] = sc;
+            s_const[3 * C + c] = a.beta[c] - m * sc;
+            s_const[4 * C + c] = __ldcg(a.work + c) * invM;
+            s_const[5 * C + c] = __ldcg(a.work + C + c) * invM;
+        }
+        __syncthreads();
+    }
     if (pooled) {
         BwdGroups<T, V, true, 4> f;
         bwd_fill<T, V>(f, a);
+        f.s_const = s_const;
         row_stream<V, 1>(f, a.M / a.pool_k, C);
     } else {
         BwdRows<T, V, true> f;
         bwd_fill<T, V>(f, a);
+        f.s_const = s_const;
         row_stream<V, PCB_BN_UB>(f, a.M, C);
     }
     BN_STAMP(5);

@@ -136,6 +136,108 @@ group_points_bwd_kernel(const GT *__restrict__ gout, const int64_t *__restrict__
     atomicAdd(dst, g);
 }
 
+// ---- 8 channels per thread (row pitch a multiple of 8: the padded rows handed to the shared-MLP GEMM) ----
+// One index load and one address decomposition per 8 outputs, one 16-byte store (bf16) or two (fp32);
+// feature chunks of 16-byte aligned point-major rows come in with two 128-bit loads.
+__device__ __forceinline__ uint4 pack8_bf16(const float v[8])
+{
+    __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+    __nv_bfloat162 c = __floats2bfloat162_rn(v[4], v[5]), d = __floats2bfloat162_rn(v[6], v[7]);
+    uint4 u;
+    u.x = *reinterpret_cast<unsigned *>(&a);
+    u.y = *reinterpret_cast<unsigned *>(&b);
+    u.z = *reinterpret_cast<unsigned *>(&c);
+    u.w = *reinterpret_cast<unsigned *>(&d);
+    return u;
+}
+__device__ __forceinline__ void store8(float *p, const float v[8])
+{
+    st_stream_f4(reinterpret_cast<float4 *>(p), make_float4(v[0], v[1], v[2], v[3]));
+    st_stream_f4(reinterpret_cast<float4 *>(p) + 1, make_float4(v[4], v[5], v[6], v[7]));
+}
+__device__ __forceinline__ void store8(__nv_bfloat16 *p, const float v[8])
+{
+    *reinterpret_cast<uint4 *>(p) = pack8_bf16(v);
+}
+
+template <typename OT>
+__global__ void __launch_bounds__(kThreads)
+group_points_chunk_kernel(const float *__restrict__ xyz, const float *__restrict__ points,
+                          const float *__restrict__ new_xyz, const int64_t *__restrict__ idx, int N, int D, FastDiv dQ,
+                          FastDiv dK, FastDiv dS, int xyz_first, int points_cf, int clamp, int vec_ok, unsigned total,
+                          OT *__restrict__ out)
+{
+    // dQ.d = chunks per row = pitch / 8
+    const unsigned t = blockIdx.x * kThreads + threadIdx.x;
+    if (t >= total) return;
+    const unsigned rowg = dQ.div(t);                   // (b*S + s)*K + k
+    const int c0 = (int)(t - rowg * dQ.d) * 8;
+    const unsigned bs = dK.div(rowg);
+    const unsigned b = dS.div(bs);
+    long long i = idx[rowg];
+    const bool ok = resolve_index(i, N, clamp);
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = 0.f;
+    if (ok) {
+        const int f0 = xyz_first ? c0 - 3 : c0;        // feature channel of the chunk's first element
+        if (vec_ok && f0 >= 0 && f0 + 8 <= D && (f0 & 3) == 0) {
+            const float4 *src = reinterpret_cast<const float4 *>(points + ((size_t)b * N + i) * D + f0);
+            const float4 a = __ldg(src), c = __ldg(src + 1);
+            v[0] = a.x, v[1] = a.y, v[2] = a.z, v[3] = a.w, v[4] = c.x, v[5] = c.y, v[6] = c.z, v[7] = c.w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int c = c0 + j;
+                if (c < 3 + D) {
+                    const int cx = xyz_first ? c : c - D;
+                    if (cx >= 0 && cx < 3) {
+                        v[j] = __fsub_rn(__ldg(xyz + ((size_t)b * N + i) * 3 + cx), __ldg(new_xyz + (size_t)bs * 3 + cx));
+                    } else {
+                        const int cf = xyz_first ? c - 3 : c;
+                        v[j] = points_cf ? __ldg(points + ((size_t)b * D + cf) * N + i)
+                                         : __ldg(points + ((size_t)b * N + i) * D + cf);
+                    }
+                }
+            }
+        }
+    }
+    store8(out + (size_t)t * 8, v);
+}
+
+// backward, 4 feature channels per thread: one 128-bit reduction (red.global.add.v4.f32) per thread.
+// D % 4 == 0, point-major gradient rows, 16-byte aligned grad_points.
+__device__ __forceinline__ float4 load_grad4(const float *p) { return ld_stream_f4(reinterpret_cast<const float4 *>(p)); }
+__device__ __forceinline__ float4 load_grad4(const __nv_bfloat16 *p)
+{
+    const uint2 u = *reinterpret_cast<const uint2 *>(p);
+    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&u.x));
+    const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&u.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+}
+
+template <typename GT>
+__global__ void __launch_bounds__(kThreads)
+group_points_bwd_vec_kernel(const GT *__restrict__ gout, const int64_t *__restrict__ idx, int N, int D, int C,
+                            FastDiv dDV, FastDiv dSK, int foff, int clamp, int aligned, unsigned total,
+                            float *__restrict__ gpoints)
+{
+    const unsigned t = blockIdx.x * kThreads + threadIdx.x;
+    if (t >= total) return;
+    const unsigned rowg = dDV.div(t);
+    const int cf = (int)(t - rowg * dDV.d) * 4;
+    const unsigned b = dSK.div(rowg);
+    long long i = idx[rowg];
+    if (!resolve_index(i, N, clamp)) return;
+    const GT *g = gout + (size_t)rowg * C + foff + cf;
+    float4 gv;
+    if (aligned)
+        gv = load_grad4(g);
+    else
+        gv = make_float4(load_grad(g), load_grad(g + 1), load_grad(g + 2), load_grad(g + 3));
+    atomicAdd(reinterpret_cast<float4 *>(gpoints + ((size_t)b * N + i) * D + cf), gv);
+}
+
 // ------------------------------------------------------------------------------------------
 // get_graph_feature.  x [B,D,N], idx [B,N,k] -> out [B,2D,N,k].
 // A thread owns EPT consecutive (n, j) edges and walks CPT channels: indices are read once per
@@ -373,6 +475,78 @@ fp_concat_bwd_kernel(const __nv_bfloat16 *__restrict__ gout, const int64_t *__re
     }
 }
 
+// ---- 8 channels per thread (D1, D2, pitch multiples of 8): 16-byte loads and stores ----
+__device__ __forceinline__ void ld8(const float *p, float v[8])
+{
+    const float4 a = __ldg(reinterpret_cast<const float4 *>(p)), b = __ldg(reinterpret_cast<const float4 *>(p) + 1);
+    v[0] = a.x, v[1] = a.y, v[2] = a.z, v[3] = a.w, v[4] = b.x, v[5] = b.y, v[6] = b.z, v[7] = b.w;
+}
+__device__ __forceinline__ void ld8(const __nv_bfloat16 *p, float v[8])
+{
+    const uint4 u = *reinterpret_cast<const uint4 *>(p);
+    const unsigned w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&w[j]));
+        v[2 * j] = f.x, v[2 * j + 1] = f.y;
+    }
+}
+
+template <typename T1, typename T2>
+__global__ void __launch_bounds__(kThreads)
+fp_concat_chunk_kernel(const T1 *__restrict__ p1, const T2 *__restrict__ p2, const int64_t *__restrict__ idx,
+                       const float *__restrict__ w, int S, int D1, int D2, int k, FastDiv dQ, FastDiv dN,
+                       unsigned total, __nv_bfloat16 *__restrict__ out)
+{
+    const unsigned t = blockIdx.x * kThreads + threadIdx.x;
+    if (t >= total) return;
+    const unsigned rowg = dQ.div(t);                   // b*N + n
+    const int c = (int)(t - rowg * dQ.d) * 8;
+    float v[8];
+#pragma unroll
+    for (int m = 0; m < 8; ++m) v[m] = 0.f;
+    if (c < D1) {
+        ld8(p1 + (size_t)rowg * D1 + c, v);
+    } else if (c < D1 + D2) {
+        const unsigned b = dN.div(rowg);
+        const int c2 = c - D1;
+        for (int j = 0; j < k; ++j) {
+            long long i = idx[(size_t)rowg * k + j];
+            i = i < 0 ? 0 : (i > S - 1 ? S - 1 : i);
+            const float wj = __ldg(w + (size_t)rowg * k + j);
+            float f[8];
+            ld8(p2 + ((size_t)b * S + i) * D2 + c2, f);
+#pragma unroll
+            for (int m = 0; m < 8; ++m) {
+                const float pr = __fmul_rn(f[m], wj);
+                v[m] = j == 0 ? pr : __fadd_rn(v[m], pr);
+            }
+        }
+    }
+    *reinterpret_cast<uint4 *>(out + (size_t)t * 8) = pack8_bf16(v);
+}
+
+// backward, 4 channels per thread (D1, D2, pitch multiples of 4): k 128-bit reductions per thread
+__global__ void __launch_bounds__(kThreads)
+fp_concat_bwd_vec_kernel(const __nv_bfloat16 *__restrict__ gout, const int64_t *__restrict__ idx,
+                         const float *__restrict__ w, int S, int D1, int D2, int k, int pitch, FastDiv dDV, FastDiv dN,
+                         unsigned total, float *__restrict__ gp2)
+{
+    const unsigned t = blockIdx.x * kThreads + threadIdx.x;
+    if (t >= total) return;
+    const unsigned rowg = dDV.div(t);
+    const int c = (int)(t - rowg * dDV.d) * 4;
+    const unsigned b = dN.div(rowg);
+    const float4 g = load_grad4(gout + (size_t)rowg * pitch + D1 + c);
+    for (int j = 0; j < k; ++j) {
+        long long i = idx[(size_t)rowg * k + j];
+        i = i < 0 ? 0 : (i > S - 1 ? S - 1 : i);
+        const float wj = __ldg(w + (size_t)rowg * k + j);
+        atomicAdd(reinterpret_cast<float4 *>(gp2 + ((size_t)b * S + i) * D2 + c),
+                  make_float4(g.x * wj, g.y * wj, g.z * wj, g.w * wj));
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // square_distance (materialising; kept for API completeness -- the product path never needs it)
 // ------------------------------------------------------------------------------------------
@@ -502,10 +676,19 @@ static int group_points_launch(const float *xyz, const float *points, const floa
     for (int b0 = 0; b0 < B; b0 += step) {
         const int nb = B - b0 < step ? B - b0 : step;
         const unsigned total = (unsigned)((int64_t)nb * S * K * C);
+        const float *pts = points ? points + (size_t)b0 * N * D : nullptr;
+        OT *o = out + (size_t)b0 * S * K * C;
+        if (C % 8 == 0 && aligned16(o)) {               // padded rows: 8 channels per thread
+            const int vec_ok = pts && !points_cf && D % 4 == 0 && aligned16(pts);
+            group_points_chunk_kernel<OT><<<blocks_for(total / 8), kThreads, 0, st>>>(
+                xyz + (size_t)b0 * N * 3, pts, new_xyz + (size_t)b0 * S * 3, idx + (size_t)b0 * S * K, N, D,
+                make_fastdiv(C / 8), make_fastdiv(K), make_fastdiv(S), xyz_first, points_cf, clamp, vec_ok, total / 8, o);
+            continue;
+        }
         group_points_kernel<OT><<<blocks_for(total), kThreads, 0, st>>>(
-            xyz + (size_t)b0 * N * 3, points ? points + (size_t)b0 * N * D : nullptr, new_xyz + (size_t)b0 * S * 3,
+            xyz + (size_t)b0 * N * 3, pts, new_xyz + (size_t)b0 * S * 3,
             idx + (size_t)b0 * S * K, N, D, make_fastdiv(C), make_fastdiv(K), make_fastdiv(S), xyz_first, points_cf,
-            clamp, total, out + (size_t)b0 * S * K * C);
+            clamp, total, o);
     }
     PCB_RETURN_LAUNCH_STATUS();
 }
@@ -524,6 +707,17 @@ static int group_points_bwd_launch(const GT *grad_out, const int64_t *idx, int B
     for (int b0 = 0; b0 < B; b0 += step) {
         const int nb = B - b0 < step ? B - b0 : step;
         const unsigned total = (unsigned)((int64_t)nb * S * K * D);
+        const GT *go = grad_out + (size_t)b0 * S * K * C;
+        float *gp = grad_points + (size_t)b0 * N * D;
+        if (D % 4 == 0 && !points_cf && aligned16(gp)) {
+            const int foff = xyz_first ? 3 : 0;
+            const int al = (sizeof(GT) == 4 ? (C % 4 == 0 && foff % 4 == 0 && aligned16(go))
+                                            : (C % 4 == 0 && foff % 4 == 0 && (reinterpret_cast<uintptr_t>(go) & 7) == 0));
+            group_points_bwd_vec_kernel<GT><<<blocks_for(total / 4), kThreads, 0, st>>>(
+                go, idx + (size_t)b0 * S * K, N, D, C, make_fastdiv(D / 4), make_fastdiv((unsigned)(S * K)), foff, clamp,
+                al, total / 4, gp);
+            continue;
+        }
         group_points_bwd_kernel<GT><<<blocks_for(total), kThreads, 0, st>>>(
             grad_out + (size_t)b0 * S * K * C, idx + (size_t)b0 * S * K, N, D, C, make_fastdiv(D),
             make_fastdiv((unsigned)(S * K)), xyz_first, points_cf, clamp, total, grad_points + (size_t)b0 * N * D);
@@ -653,6 +847,13 @@ static int fp_concat_launch(const void *p1, const void *p2, const int64_t *idx, 
     for (int b0 = 0; b0 < B; b0 += step) {
         const int nb = B - b0 < step ? B - b0 : step;
         const unsigned total = (unsigned)((int64_t)nb * N * (pitch / 2));
+        if (D1 % 8 == 0 && D2 % 8 == 0 && pitch % 8 == 0 && aligned16(out) && aligned16(p2) && (!p1 || aligned16(p1))) {
+            fp_concat_chunk_kernel<T1, T2><<<blocks_for(total / 4), kThreads, 0, st>>>(
+                p1 ? (const T1 *)p1 + (size_t)b0 * N * D1 : nullptr, (const T2 *)p2 + (size_t)b0 * S * D2,
+                idx + (size_t)b0 * N * k, w + (size_t)b0 * N * k, S, D1, D2, k, make_fastdiv(pitch / 8), make_fastdiv(N),
+                total / 4, (__nv_bfloat16 *)out + (size_t)b0 * N * pitch);
+            continue;
+        }
         fp_concat_kernel<T1, T2><<<blocks_for(total), kThreads, 0, st>>>(
             p1 ? (const T1 *)p1 + (size_t)b0 * N * D1 : nullptr, (const T2 *)p2 + (size_t)b0 * S * D2,
             idx + (size_t)b0 * N * k, w + (size_t)b0 * N * k, S, D1, D2, k, make_fastdiv(pitch / 2), make_fastdiv(N),
@@ -688,6 +889,14 @@ PCB_API int pcb_fp_concat_bwd_bf16(const void *grad_out, const int64_t *idx, con
     for (int b0 = 0; b0 < B; b0 += step) {
         const int nb = B - b0 < step ? B - b0 : step;
         const unsigned total = (unsigned)((int64_t)nb * N * D2);
+        if (D1 % 4 == 0 && D2 % 4 == 0 && pitch % 4 == 0 && (reinterpret_cast<uintptr_t>(grad_out) & 7) == 0 &&
+            aligned16(grad_points2)) {
+            fp_concat_bwd_vec_kernel<<<blocks_for(total / 4), kThreads, 0, (cudaStream_t)stream>>>(
+                (const __nv_bfloat16 *)grad_out + (size_t)b0 * N * pitch, idx + (size_t)b0 * N * k,
+                weight + (size_t)b0 * N * k, S, D1, D2, k, pitch, make_fastdiv(D2 / 4), make_fastdiv(N), total / 4,
+                grad_points2 + (size_t)b0 * S * D2);
+            continue;
+        }
         fp_concat_bwd_kernel<<<blocks_for(total), kThreads, 0, (cudaStream_t)stream>>>(
             (const __nv_bfloat16 *)grad_out + (size_t)b0 * N * pitch, idx + (size_t)b0 * N * k,
             weight + (size_t)b0 * N * k, S, D1, D2, k, pitch, make_fastdiv(D2), make_fastdiv(N), total,

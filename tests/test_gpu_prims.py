@@ -287,11 +287,13 @@ def test_backward_of_gathers_matches_torch_autograd():
 
 @pytest.mark.parametrize("dt1,dt2", [(torch.float32, torch.float32), (torch.bfloat16, torch.bfloat16),
                                      (torch.bfloat16, torch.float32), (None, torch.bfloat16)])
-def test_fp_concat_equals_interpolate_cat_cast(dt1, dt2):
+@pytest.mark.parametrize("dims", [(10, 14), (16, 24), (8, 12)])      # pair kernel / 8-channel chunks / mixed
+def test_fp_concat_equals_interpolate_cat_cast(dt1, dt2, dims):
     """The fused feature-propagation input rows (bf16 training) against the unfused chain
     three_interpolate (fp32) -> cat -> bf16: forward bit-equal, backward within bf16/atomic noise."""
     torch.manual_seed(1)
-    B, N, S, D1, D2, k = 2, 300, 41, 0 if dt1 is None else 10, 14, 3
+    B, N, S, k = 2, 300, 41, 3
+    D1, D2 = (0 if dt1 is None else dims[0]), dims[1]
     p1 = torch.randn(B, N, D1, device=DEV).to(dt1).requires_grad_(True) if D1 else None
     p2 = torch.randn(B, S, D2, device=DEV).to(dt2).requires_grad_(True)
     idx = torch.randint(0, S, (B, N, k), device=DEV)
@@ -311,3 +313,28 @@ def test_fp_concat_equals_interpolate_cat_cast(dt1, dt2):
     for a, b in zip(ga, gb):
         assert a.dtype == b.dtype
         torch.testing.assert_close(a.float(), b.float(), rtol=2e-2, atol=2e-2)
+
+
+@pytest.mark.parametrize("D,xyz_first", [(16, False), (16, True), (9, False), (24, False)])
+def test_group_points_padded_bf16_rows_fwd_bwd(D, xyz_first):
+    """Padded bf16 rows of the training path (8-channel chunk kernel, 128-bit reductions backward)
+    against plain indexing."""
+    torch.manual_seed(2)
+    B, N, S, K = 2, 301, 37, 16
+    pts = torch.randn(B, N, D, device=DEV, requires_grad=True)
+    xyz = torch.randn(B, N, 3, device=DEV)
+    idx = torch.randint(0, N, (B, S, K), device=DEV)
+    new_xyz = torch.randn(B, S, 3, device=DEV)
+    bi = torch.arange(B, device=DEV).view(B, 1, 1).expand(B, S, K)
+    C = 3 + D
+    for bf16 in (True, False):
+        parts = [xyz[bi, idx] - new_xyz.view(B, S, 1, 3), pts[bi, idx]]
+        ref = torch.cat(parts if xyz_first else parts[::-1], -1)
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=bf16):
+            out = ops.group_points(xyz, pts, new_xyz, idx, xyz_first=xyz_first, pad_to=8)
+        assert out.dtype == (torch.bfloat16 if bf16 else torch.float32) and out.shape[-1] % 8 == 0
+        assert torch.equal(out[..., :C], ref.to(out.dtype)) and not out[..., C:].any()
+        g = torch.randn_like(out)
+        (ga,) = torch.autograd.grad(out, pts, g)
+        (gb,) = torch.autograd.grad(ref, pts, g[..., :C].float())
+        torch.testing.assert_close(ga, gb, rtol=1e-5, atol=1e-5)
