@@ -87,8 +87,9 @@ int pcb_group_points_bwd_f32(const float *grad_out, const int64_t *idx, int B, i
                              int D, int xyz_first, int points_cf, int clamp, int pitch, float *grad_points,
                              pcb_stream_t stream);
 /* bf16 variants: the grouped tensor (and its gradient) in bf16, as the autocast GEMM consumes it;
- * inputs and grad_points stay fp32 */
-int pcb_group_points_bf16(const float *xyz, const float *points, const float *new_xyz,
+ * xyz and grad_points stay fp32; `points` is fp32, or bf16 (points_bf16 != 0: the previous layer's
+ * autocast output, taken as is -- needs pitch % 8 == 0) */
+int pcb_group_points_bf16(const float *xyz, const void *points, int points_bf16, const float *new_xyz,
                           const int64_t *idx, int B, int N, int S, int K, int D, int xyz_first,
                           int points_cf, int clamp, int pitch, void *out, pcb_stream_t stream);
 int pcb_group_points_bwd_bf16(const void *grad_out, const int64_t *idx, int B, int N, int S, int K,
@@ -167,6 +168,15 @@ int pcb_bn_fwd_rows(const void *y, int dtype, int64_t M, int C, int pool_k, cons
 int pcb_bn_bwd_rows(const void *gz, const void *y, const unsigned char *argmax, int dtype, int64_t M, int C,
                     int pool_k, const float *mean, const float *invstd, const float *gamma, const float *beta,
                     int relu, float *work, void *gy, pcb_stream_t stream);
+
+/* ---- a11 (training, backward of the 1x1 convolutions on rows)
+ *          pointnet_util.py:213-215, 273-277, 343-345 (Conv2d / Conv1d 1x1 weight gradient)
+ * gw[n, k] += sum_r gy[r, n] * x[r, k]:  gy [M, N] bf16 (N % 8 == 0), x [M, ldx] bf16 row-major with
+ * ldx % 8 == 0 and zero pad columns beyond K, gw [N, ldw] fp32 -- ACCUMULATED into (zero it for a plain
+ * gradient, or point it at a gradient bucket).  One pass over gy and x per 64x64 output tile, fp32
+ * accumulation, atomics only for the per-CTA partial results. */
+int pcb_wgrad_rows_bf16(const void *gy, const void *x, int64_t M, int N, int K, int ldx, float *gw, int ldw,
+                        pcb_stream_t stream);
 
 /* ---- a11 / section 8f rank 1: fused set-abstraction / EdgeConv block for inference
  *          pointnet_util.py:137-147, 203-217, 258-279; pointnet2_utils.py:140-154, 341-356;

@@ -28,13 +28,14 @@ _SIGNATURES = {
     "pcb_gather_bwd_f32": [_vp, _vp, _i, _i, _i, _i64, _i, _vp, _vp],
     "pcb_group_points_f32": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp],
     "pcb_group_points_bwd_f32": [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp],
-    "pcb_group_points_bf16": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp],
+    "pcb_group_points_bf16": [_vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp],
     "pcb_group_points_bwd_bf16": [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp],
     "pcb_three_nn_f32": [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp],
     "pcb_interpolate_f32": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp],
     "pcb_interpolate_bwd_f32": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp],
     "pcb_fp_concat_bf16": [_vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp],
     "pcb_fp_concat_bwd_bf16": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp],
+    "pcb_wgrad_rows_bf16": [_vp, _vp, _i64, _i, _i, _i, _vp, _i, _vp],
     "pcb_knn_f32": [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp],
     "pcb_knn_cdist_f32": [_vp, _i, _i, _i, _vp, _vp, _vp],
     "pcb_graph_feature_f32": [_vp, _vp, _i, _i, _i, _i, _vp, _vp],

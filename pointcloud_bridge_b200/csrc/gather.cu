@@ -160,9 +160,28 @@ __device__ __forceinline__ void store8(__nv_bfloat16 *p, const float v[8])
     *reinterpret_cast<uint4 *>(p) = pack8_bf16(v);
 }
 
-template <typename OT>
+__device__ __forceinline__ float ldp(const float *p) { return __ldg(p); }
+__device__ __forceinline__ float ldp(const __nv_bfloat16 *p) { return __bfloat162float(*p); }
+__device__ __forceinline__ void ldp8(const float *p, float v[8])
+{
+    const float4 a = __ldg(reinterpret_cast<const float4 *>(p)), c = __ldg(reinterpret_cast<const float4 *>(p) + 1);
+    v[0] = a.x, v[1] = a.y, v[2] = a.z, v[3] = a.w, v[4] = c.x, v[5] = c.y, v[6] = c.z, v[7] = c.w;
+}
+__device__ __forceinline__ void ldp8(const __nv_bfloat16 *p, float v[8])
+{
+    const uint4 u = __ldg(reinterpret_cast<const uint4 *>(p));
+    const unsigned w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        v[2 * j] = __uint_as_float(w[j] << 16);
+        v[2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u);
+    }
+}
+
+// PT: type of the feature rows (fp32, or bf16 when the previous layer ran under autocast)
+template <typename OT, typename PT>
 __global__ void __launch_bounds__(kThreads)
-group_points_chunk_kernel(const float *__restrict__ xyz, const float *__restrict__ points,
+group_points_chunk_kernel(const float *__restrict__ xyz, const PT *__restrict__ points,
                           const float *__restrict__ new_xyz, const int64_t *__restrict__ idx, int N, int D, FastDiv dQ,
                           FastDiv dK, FastDiv dS, int xyz_first, int points_cf, int clamp, int vec_ok, unsigned total,
                           OT *__restrict__ out)
@@ -181,10 +200,8 @@ group_points_chunk_kernel(const float *__restrict__ xyz, const float *__restrict
     for (int j = 0; j < 8; ++j) v[j] = 0.f;
     if (ok) {
         const int f0 = xyz_first ? c0 - 3 : c0;        // feature channel of the chunk's first element
-        if (vec_ok && f0 >= 0 && f0 + 8 <= D && (f0 & 3) == 0) {
-            const float4 *src = reinterpret_cast<const float4 *>(points + ((size_t)b * N + i) * D + f0);
-            const float4 a = __ldg(src), c = __ldg(src + 1);
-            v[0] = a.x, v[1] = a.y, v[2] = a.z, v[3] = a.w, v[4] = c.x, v[5] = c.y, v[6] = c.z, v[7] = c.w;
+        if (vec_ok && f0 >= 0 && f0 + 8 <= D && (f0 & 7) == 0) {
+            ldp8(points + ((size_t)b * N + i) * D + f0, v);
         } else {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -195,8 +212,8 @@ group_points_chunk_kernel(const float *__restrict__ xyz, const float *__restrict
                         v[j] = __fsub_rn(__ldg(xyz + ((size_t)b * N + i) * 3 + cx), __ldg(new_xyz + (size_t)bs * 3 + cx));
                     } else {
                         const int cf = xyz_first ? c - 3 : c;
-                        v[j] = points_cf ? __ldg(points + ((size_t)b * D + cf) * N + i)
-                                         : __ldg(points + ((size_t)b * N + i) * D + cf);
+                        v[j] = points_cf ? ldp(points + ((size_t)b * D + cf) * N + i)
+                                         : ldp(points + ((size_t)b * N + i) * D + cf);
                     }
                 }
             }
@@ -661,8 +678,8 @@ PCB_API int pcb_gather_bwd_f32(const float *grad_out, const int64_t *idx, int B,
     PCB_RETURN_LAUNCH_STATUS();
 }
 
-template <typename OT>
-static int group_points_launch(const float *xyz, const float *points, const float *new_xyz, const int64_t *idx, int B,
+template <typename OT, typename PT>
+static int group_points_launch(const float *xyz, const PT *points, const float *new_xyz, const int64_t *idx, int B,
                                int N, int S, int K, int D, int xyz_first, int points_cf, int clamp, int pitch, OT *out,
                                cudaStream_t st)
 {
@@ -676,17 +693,18 @@ static int group_points_launch(const float *xyz, const float *points, const floa
     for (int b0 = 0; b0 < B; b0 += step) {
         const int nb = B - b0 < step ? B - b0 : step;
         const unsigned total = (unsigned)((int64_t)nb * S * K * C);
-        const float *pts = points ? points + (size_t)b0 * N * D : nullptr;
+        const PT *pts = points ? points + (size_t)b0 * N * D : nullptr;
         OT *o = out + (size_t)b0 * S * K * C;
         if (C % 8 == 0 && aligned16(o)) {               // padded rows: 8 channels per thread
-            const int vec_ok = pts && !points_cf && D % 4 == 0 && aligned16(pts);
-            group_points_chunk_kernel<OT><<<blocks_for(total / 8), kThreads, 0, st>>>(
+            const int vec_ok = pts && !points_cf && D % 8 == 0 && aligned16(pts);
+            group_points_chunk_kernel<OT, PT><<<blocks_for(total / 8), kThreads, 0, st>>>(
                 xyz + (size_t)b0 * N * 3, pts, new_xyz + (size_t)b0 * S * 3, idx + (size_t)b0 * S * K, N, D,
                 make_fastdiv(C / 8), make_fastdiv(K), make_fastdiv(S), xyz_first, points_cf, clamp, vec_ok, total / 8, o);
             continue;
         }
+        if (sizeof(PT) != 4) return PCB_ERANGE;         // bf16 feature rows need the padded (pitch % 8 == 0) layout
         group_points_kernel<OT><<<blocks_for(total), kThreads, 0, st>>>(
-            xyz + (size_t)b0 * N * 3, pts, new_xyz + (size_t)b0 * S * 3,
+            xyz + (size_t)b0 * N * 3, reinterpret_cast<const float *>(pts), new_xyz + (size_t)b0 * S * 3,
             idx + (size_t)b0 * S * K, N, D, make_fastdiv(C), make_fastdiv(K), make_fastdiv(S), xyz_first, points_cf,
             clamp, total, o);
     }
@@ -729,16 +747,20 @@ PCB_API int pcb_group_points_f32(const float *xyz, const float *points, const fl
                                  const int64_t *idx, int B, int N, int S, int K, int D, int xyz_first,
                                  int points_cf, int clamp, int pitch, float *out, pcb_stream_t stream)
 {
-    return group_points_launch<float>(xyz, points, new_xyz, idx, B, N, S, K, D, xyz_first, points_cf, clamp, pitch, out,
-                                      (cudaStream_t)stream);
+    return group_points_launch<float, float>(xyz, points, new_xyz, idx, B, N, S, K, D, xyz_first, points_cf, clamp, pitch,
+                                             out, (cudaStream_t)stream);
 }
 
-PCB_API int pcb_group_points_bf16(const float *xyz, const float *points, const float *new_xyz,
+PCB_API int pcb_group_points_bf16(const float *xyz, const void *points, int points_bf16, const float *new_xyz,
                                   const int64_t *idx, int B, int N, int S, int K, int D, int xyz_first,
                                   int points_cf, int clamp, int pitch, void *out, pcb_stream_t stream)
 {
-    return group_points_launch<__nv_bfloat16>(xyz, points, new_xyz, idx, B, N, S, K, D, xyz_first, points_cf, clamp,
-                                              pitch, (__nv_bfloat16 *)out, (cudaStream_t)stream);
+    if (points_bf16)
+        return group_points_launch<__nv_bfloat16, __nv_bfloat16>(xyz, (const __nv_bfloat16 *)points, new_xyz, idx, B, N, S,
+                                                                 K, D, xyz_first, points_cf, clamp, pitch,
+                                                                 (__nv_bfloat16 *)out, (cudaStream_t)stream);
+    return group_points_launch<__nv_bfloat16, float>(xyz, (const float *)points, new_xyz, idx, B, N, S, K, D, xyz_first,
+                                                     points_cf, clamp, pitch, (__nv_bfloat16 *)out, (cudaStream_t)stream);
 }
 
 PCB_API int pcb_group_points_bwd_f32(const float *grad_out, const int64_t *idx, int B, int N, int S, int K,

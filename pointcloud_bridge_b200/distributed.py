@@ -64,8 +64,9 @@ class FlatGradBucket:
     """One flat fp32 buffer for all parameter gradients of `module` = one collective per step.
 
     Gradients are produced by autograd as ordinary per-parameter tensors (`p.grad = None` before
-    backward, so no accumulate kernels run); `pack()` gathers them into the flat buffer with one
-    batched multi-tensor copy, `allreduce_mean()` is a single NCCL all-reduce over the buffer,
+    backward, so no accumulate kernels run) or written straight into their flat view by the producing
+    kernel (`zero()` clears the buffer at the start of a step); `pack()` gathers the former into the
+    flat buffer with one batched multi-tensor copy, `allreduce_mean()` is a single NCCL all-reduce over the buffer,
     and `unpack()` scatters the averaged values back with another batched copy.  With one rank
     nothing is packed at all.
     """
@@ -87,16 +88,17 @@ class FlatGradBucket:
         return self.flat.numel() * self.flat.element_size()
 
     def zero(self) -> None:
+        """Start of a step: no per-parameter gradients, flat buffer zero (kernels that write their
+        gradient straight into a flat view -- ops.wgrad_rows -- accumulate into it)."""
         for p in self.params:
             p.grad = None
+        self.flat.zero_()
 
     def _live(self):
         return [(v, p.grad) for v, p in zip(self.views, self.params) if p.grad is not None]
 
     def pack(self) -> None:
-        live = self._live()
-        if len(live) != len(self.params):
-            self.flat.zero_()                      # parameters without a gradient contribute zeros
+        live = self._live()                        # parameters without a .grad were written in place or are unused
         if live:
             torch._foreach_copy_([v for v, _ in live], [g for _, g in live])
 

@@ -91,7 +91,8 @@ class Trainer:
         self.flat_param.grad = self.bucket.flat
         self.opt = torch.optim.Adam([self.flat_param], lr=lr, weight_decay=weight_decay, fused=True,
                                     capturable=graph if capturable is None else capturable)
-        self._ctx = ops.StepContext(net, bf16=amp)
+        self._ctx = ops.StepContext(net, bf16=amp,
+                                    grad_views={id(p): v for p, v in zip(self.bucket.params, self.bucket.views)})
         self._g = None                 # captured (zero, forward, loss, backward[, Adam]) graph
         self._static = None
         self._starts = FpsStartBuffers()

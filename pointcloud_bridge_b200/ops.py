@@ -271,18 +271,24 @@ class _GroupPoints(torch.autograd.Function):
         idx = _i64(idx, "idx")
         B, N, _ = xyz.shape
         _, S, K = idx.shape
-        if points is not None:
-            points = _f32(points, "points")
-            D = points.shape[1] if points_cf else points.shape[2]
-        else:
-            D = 0
         # under bf16 autocast the consumer is a bf16 GEMM: emit the grouped tensor in bf16 directly
         bf16 = torch.is_autocast_enabled() and torch.get_autocast_dtype("cuda") == torch.bfloat16
+        D = 0 if points is None else (points.shape[1] if points_cf else points.shape[2])
         pitch = -(-(3 + D) // pad_to) * pad_to
+        # bf16 feature rows of the previous layer are gathered as they are (no fp32 round trip)
+        pts_bf16 = bf16 and D > 0 and points.dtype == torch.bfloat16 and pitch % 8 == 0 and points.is_cuda
+        if D:
+            points = (points if points.is_contiguous() else points.contiguous()) if pts_bf16 else _f32(points, "points")
         out = torch.empty(B, S, K, pitch, dtype=torch.bfloat16 if bf16 else torch.float32, device=xyz.device)
-        _call("pcb_group_points_bf16" if bf16 else "pcb_group_points_f32", xyz.device, xyz.data_ptr(), points.data_ptr() if D else None,
-              new_xyz.data_ptr(), idx.data_ptr(), B, N, S, K, D, int(xyz_first), int(points_cf), int(clamp), pitch,
-              out.data_ptr(), alg_bytes=B * (4 * N * (3 + D) + 12 * S + 8 * S * K + out.element_size() * S * K * pitch))
+        ab = B * (4 * N * 3 + (points.element_size() * N * D if D else 0) + 12 * S + 8 * S * K + out.element_size() * S * K * pitch)
+        if bf16:
+            _call("pcb_group_points_bf16", xyz.device, xyz.data_ptr(), points.data_ptr() if D else None, int(pts_bf16),
+                  new_xyz.data_ptr(), idx.data_ptr(), B, N, S, K, D, int(xyz_first), int(points_cf), int(clamp), pitch,
+                  out.data_ptr(), alg_bytes=ab)
+        else:
+            _call("pcb_group_points_f32", xyz.device, xyz.data_ptr(), points.data_ptr() if D else None,
+                  new_xyz.data_ptr(), idx.data_ptr(), B, N, S, K, D, int(xyz_first), int(points_cf), int(clamp), pitch,
+                  out.data_ptr(), alg_bytes=ab)
         ctx.save_for_backward(idx)
         ctx.meta = (B, N, S, K, D, int(xyz_first), int(points_cf), int(clamp), pitch)
         return out
@@ -627,8 +633,11 @@ class StepContext:
     weights are ONE multi-tensor copy on entry into persistent shadows that `linear_rows` picks up
     (autocast would cast each weight on use, forward and again backward)."""
 
-    def __init__(self, module: torch.nn.Module, bf16: bool):
+    def __init__(self, module: torch.nn.Module, bf16: bool, grad_views: dict | None = None):
         self.counters = []
+        # id(parameter) -> fp32 view of the runner's flat gradient buffer (zeroed at the start of every
+        # step): the weight-gradient kernel accumulates straight into it, the parameter's .grad stays None
+        self.grad_views = grad_views or {}
         params = [p for p in module.parameters() if p.dim() >= 2] if bf16 else []
         # shadows are [N, K rounded up to 8] with zero pad columns (written once, here): the padded
         # ones match the zero-padded rows of group_points(pad_to=8)
@@ -666,9 +675,35 @@ class StepContext:
         base = w._base if w._base is not None else w
         return self.by_id.get(id(base))
 
+    def grad_view(self, w):
+        base = w._base if w._base is not None else w
+        return self.grad_views.get(id(base))
+
 
 _step_ctx = None
 _WGRAD_CHUNK = int(os.environ.get("PCB_WGRAD_CHUNK", "2048"))
+
+
+_WGRAD_KERNEL = os.environ.get("PCB_NO_WGRAD_KERNEL", "0") != "1"
+
+
+def wgrad_rows_supported(gy, x) -> bool:
+    return (gy.is_cuda and gy.dtype == torch.bfloat16 and x.dtype == torch.bfloat16 and gy.dim() == 2 and x.dim() == 2
+            and gy.is_contiguous() and x.is_contiguous() and gy.shape[1] % 8 == 0 and x.shape[1] % 8 == 0
+            and gy.data_ptr() % 16 == 0 and x.data_ptr() % 16 == 0)
+
+
+@torch.no_grad()
+def wgrad_rows(gy, x, k: int | None = None, out: torch.Tensor | None = None) -> torch.Tensor:
+    """gy [M,N]^T @ x [M,Kp][:, :k] in fp32 (bf16 operands, rows = the long contraction dimension).
+    `out` [N,k] fp32 is accumulated into when given."""
+    M, N = gy.shape
+    k = x.shape[1] if k is None else k
+    if out is None:
+        out = torch.zeros(N, k, dtype=torch.float32, device=gy.device)
+    _call("pcb_wgrad_rows_bf16", gy.device, gy.data_ptr(), x.data_ptr(), M, N, k, x.shape[1], out.data_ptr(),
+          out.stride(0), alg_bytes=2 * M * (N + x.shape[1]) + 4 * N * k)
+    return out
 
 
 class _LinearRows(torch.autograd.Function):
@@ -678,8 +713,10 @@ class _LinearRows(torch.autograd.Function):
     K (`group_points(pad_to=8)`): the weight is padded to match and its gradient sliced back."""
 
     @staticmethod
-    def forward(ctx, x, w, w_lp):
+    def forward(ctx, x, w, w_lp, gview=None):
         # w_lp: the weight already in x's dtype (StepContext shadow) or None
+        # gview: fp32 view of the step runner's flat gradient buffer for w, or None
+        ctx.gview = gview
         wl = w_lp if w_lp is not None else w.to(x.dtype)
         if wl.shape[1] > x.shape[1]:                      # padded shadow, dense rows
             wl = wl[:, :x.shape[1]]
@@ -701,7 +738,12 @@ class _LinearRows(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             M = x.shape[0]
             c = _WGRAD_CHUNK
-            if c and M % c == 0 and M // c >= 8:
+            if _WGRAD_KERNEL and wgrad_rows_supported(gy, x):
+                if ctx.gview is not None:                 # accumulate in place; .grad of the parameter stays None
+                    wgrad_rows(gy, x, ctx.kw, out=ctx.gview.view(gy.shape[1], ctx.kw))
+                    return gx, None, None, None
+                gw = wgrad_rows(gy, x, ctx.kw)
+            elif c and M % c == 0 and M // c >= 8:
                 p = M // c
                 part = torch.bmm(gy.view(p, c, -1).transpose(1, 2), x.view(p, c, -1))   # [p,N,K]
                 gw = part.sum(dim=0, dtype=torch.float32)
@@ -709,7 +751,7 @@ class _LinearRows(torch.autograd.Function):
                 gw = torch.mm(gy.t(), x).float()
             if gw.shape[1] != ctx.kw:
                 gw = gw[:, :ctx.kw]
-        return gx, gw, None
+        return gx, gw, None, None
 
 
 def linear_rows(x, w):
@@ -719,4 +761,5 @@ def linear_rows(x, w):
         dt = torch.get_autocast_dtype("cuda")
         x = x if x.dtype == dt else x.to(dt)
     w_lp = _step_ctx.shadow(w) if (_step_ctx is not None and x.dtype == torch.bfloat16) else None
-    return _LinearRows.apply(x, w, w_lp)
+    gview = _step_ctx.grad_view(w) if (_step_ctx is not None and x.dtype == torch.bfloat16) else None
+    return _LinearRows.apply(x, w, w_lp, gview)

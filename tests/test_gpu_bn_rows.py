@@ -51,3 +51,24 @@ def test_bn_relu_rows_matches_torch(M, C, pool_k, dtype):
         assert (pa.grad - pb.grad).abs().max().item() <= gtol * (pb.grad.abs().max().item() + 1e-6)
     # the conv bias feeds a training-mode BN: its gradient is zero up to rounding on both paths
     assert ba.grad.abs().max().item() <= 1e-2 * (bn_b.weight.grad.abs().max().item() + 1.0)
+
+
+@pytest.mark.parametrize("M,N,K,Kp", [(4096, 16, 12, 16), (100000, 32, 32, 32), (5000, 96, 99, 104), (777, 256, 520, 520),
+                                      (65, 8, 8, 8), (20000, 128, 67, 72)])
+def test_wgrad_rows_kernel(M, N, K, Kp):
+    """gw = gy^T x over the long row dimension (bf16 operands, fp32 accumulation) against an fp64 matmul."""
+    from pointcloud_bridge_b200 import ops
+    torch.manual_seed(M + N)
+    gy = torch.randn(M, N, device="cuda").to(torch.bfloat16)
+    x = torch.zeros(M, Kp, device="cuda", dtype=torch.bfloat16)
+    x[:, :K] = torch.randn(M, K, device="cuda").to(torch.bfloat16)
+    assert ops.wgrad_rows_supported(gy, x)
+    gw = ops.wgrad_rows(gy, x, K)
+    ref = (gy.double().t() @ x.double())[:, :K]
+    assert gw.shape == (N, K) and gw.dtype == torch.float32
+    scale = ref.abs().max().item()
+    assert (gw.double() - ref).abs().max().item() <= 2e-5 * scale + 1e-4 * (M ** 0.5) * 1e-2
+    # accumulation into an existing buffer
+    out = torch.ones(N, K, device="cuda")
+    ops.wgrad_rows(gy, x, K, out=out)
+    assert (out.double() - 1.0 - ref).abs().max().item() <= 2e-5 * scale + 1e-4 * (M ** 0.5) * 1e-2

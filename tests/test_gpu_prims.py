@@ -338,3 +338,26 @@ def test_group_points_padded_bf16_rows_fwd_bwd(D, xyz_first):
         (ga,) = torch.autograd.grad(out, pts, g)
         (gb,) = torch.autograd.grad(ref, pts, g[..., :C].float())
         torch.testing.assert_close(ga, gb, rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("D", [16, 12])
+def test_group_points_takes_bf16_feature_rows(D):
+    """bf16 features of the previous autocast layer are gathered without an fp32 round trip: the grouped
+    bf16 rows equal those obtained from the same features given as fp32; gradient as plain indexing."""
+    torch.manual_seed(3)
+    B, N, S, K = 2, 200, 23, 16
+    pts = torch.randn(B, N, D, device=DEV).to(torch.bfloat16).requires_grad_(True)
+    xyz = torch.randn(B, N, 3, device=DEV)
+    idx = torch.randint(0, N, (B, S, K), device=DEV)
+    new_xyz = torch.randn(B, S, 3, device=DEV)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        out = ops.group_points(xyz, pts, new_xyz, idx, xyz_first=False, pad_to=8)
+        ref = ops.group_points(xyz, pts.detach().float(), new_xyz, idx, xyz_first=False, pad_to=8)
+    assert out.dtype == torch.bfloat16 and torch.equal(out, ref)
+    g = torch.randn_like(out)
+    (ga,) = torch.autograd.grad(out, pts, g)
+    bi = torch.arange(B, device=DEV).view(B, 1, 1).expand(B, S, K)
+    p32 = pts.detach().float().requires_grad_(True)
+    (gb,) = torch.autograd.grad(p32[bi, idx], p32, g[..., :D].float())
+    assert ga.dtype == torch.bfloat16
+    torch.testing.assert_close(ga.float(), gb, rtol=1e-2, atol=1e-2)
