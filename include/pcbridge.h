@@ -160,23 +160,26 @@ int pcb_graph_feature_bwd_f32(const float *grad_out, const int64_t *idx, int B, 
  *   pcb_bn_bwd_rows : gy = gamma*invstd*(dy - sum_dy/M - yhat*sum_dy_yhat/M) with dy = gz masked by the
  *                     ReLU / argmax of the forward pass, gz is [M/pool_k, C];
  *                     work[0:C] = sum dy (grad beta), work[C:2C] = sum dy*yhat (grad gamma),
- *                     work[2C:3C] = gradient of the folded conv bias */
+ *                     work[2C:3C] = gradient of the folded conv bias
+ * C is the row pitch, Cv <= C the number of real channels: columns Cv..C-1 of y are zero padding that keeps
+ * rows 16-byte aligned (196 -> 200 channels in the MSG network); parameter arrays have Cv entries, mean /
+ * invstd / work are sized for C, and the padded columns of out / gy are written as zeros. */
 int64_t pcb_bn_work_floats(int C);
-int pcb_bn_fwd_rows(const void *y, int dtype, int64_t M, int C, int pool_k, const float *bias, const float *gamma,
+int pcb_bn_fwd_rows(const void *y, int dtype, int64_t M, int C, int Cv, int pool_k, const float *bias, const float *gamma,
                     const float *beta, float eps, float momentum, float *running_mean, float *running_var, int relu,
                     float *mean, float *invstd, void *out, unsigned char *argmax, float *work, pcb_stream_t stream);
 int pcb_bn_bwd_rows(const void *gz, const void *y, const unsigned char *argmax, int dtype, int64_t M, int C,
-                    int pool_k, const float *mean, const float *invstd, const float *gamma, const float *beta,
+                    int Cv, int pool_k, const float *mean, const float *invstd, const float *gamma, const float *beta,
                     int relu, float *work, void *gy, pcb_stream_t stream);
 
 /* ---- a11 (training, backward of the 1x1 convolutions on rows)
  *          pointnet_util.py:213-215, 273-277, 343-345 (Conv2d / Conv1d 1x1 weight gradient)
- * gw[n, k] += sum_r gy[r, n] * x[r, k]:  gy [M, N] bf16 (N % 8 == 0), x [M, ldx] bf16 row-major with
- * ldx % 8 == 0 and zero pad columns beyond K, gw [N, ldw] fp32 -- ACCUMULATED into (zero it for a plain
+ * gw[n, k] += sum_r gy[r, n] * x[r, k]:  gy [M, ldgy] and x [M, ldx] bf16 row-major, ldgy % 8 == ldx % 8 == 0,
+ * zero pad columns beyond N resp. K, gw [N, ldw] fp32 -- ACCUMULATED into (zero it for a plain
  * gradient, or point it at a gradient bucket).  One pass over gy and x per 64x64 output tile, fp32
  * accumulation, atomics only for the per-CTA partial results. */
-int pcb_wgrad_rows_bf16(const void *gy, const void *x, int64_t M, int N, int K, int ldx, float *gw, int ldw,
-                        pcb_stream_t stream);
+int pcb_wgrad_rows_bf16(const void *gy, const void *x, int64_t M, int N, int K, int ldgy, int ldx, float *gw,
+                        int ldw, pcb_stream_t stream);
 
 /* ---- a11 / section 8f rank 1: fused set-abstraction / EdgeConv block for inference
  *          pointnet_util.py:137-147, 203-217, 258-279; pointnet2_utils.py:140-154, 341-356;

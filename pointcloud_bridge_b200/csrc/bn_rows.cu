@@ -398,7 +398,7 @@ struct BnFwdArgs {
     const float *bias, *gamma, *beta;
     float *running_mean, *running_var, *mean, *invstd, *work;
     int64_t M, upc;
-    int C, pool_k, relu, nparts;
+    int C, Cv, pool_k, relu, nparts;                   // C = row pitch (multiple of 4), Cv <= C real channels
     float eps, momentum;
 };
 
@@ -424,7 +424,7 @@ bn_fwd_fused_kernel(const BnFwdArgs a)
     // variance, conv bias added to the running mean) as torch.nn.functional.batch_norm does
     {
         const int lane = threadIdx.x & 31;
-        PCB_FOLD_LOOP(c, C) {
+        PCB_FOLD_LOOP(c, a.Cv) {
             // operands of the finalize step first, so that their latency overlaps the fold's
             const float shift = (float)y[c];
             const float b = a.bias ? a.bias[c] : 0.f;
@@ -457,9 +457,10 @@ bn_fwd_fused_kernel(const BnFwdArgs a)
     if (C <= kBnThreads * V) {                             // 2*C floats fit the statistics scratch
         s_const = &s_part[0][0][0];
         for (int c = threadIdx.x; c < C; c += kBnThreads) {
-            const float sc = __ldcg(a.invstd + c) * a.gamma[c];
+            const bool real = c < a.Cv;                     // pad channels (zero columns of y) produce zeros
+            const float sc = real ? __ldcg(a.invstd + c) * a.gamma[c] : 0.f;
             s_const[c] = sc;
-            s_const[C + c] = a.beta[c] - __ldcg(a.mean + c) * sc;
+            s_const[C + c] = real ? a.beta[c] - __ldcg(a.mean + c) * sc : 0.f;
         }
         __syncthreads();
     }
@@ -488,7 +489,7 @@ struct BwdBase {
     T *gy;
     const float *mean, *invstd, *gamma, *beta, *sums;
     const float *s_const;                                  // shared [nm | is | sc | sh | a0 | a1] x C, or nullptr
-    int C, relu, pool_k;
+    int C, Cv, relu, pool_k;
     float invM;
     float nm[V], is[V], sc[V], sh[V], a0[V], a1[V];      // nm = -mean * invstd: yhat = fma(y, is, nm)
     __device__ __forceinline__ void consts(int c, bool with_sums)
@@ -503,6 +504,10 @@ struct BwdBase {
         }
 #pragma unroll
         for (int i = 0; i < V; ++i) {
+            if (c + i >= Cv) {                                // pad channel: yhat = 0, z = 0 (masked), gy = 0
+                nm[i] = is[i] = sc[i] = sh[i] = a0[i] = a1[i] = 0.f;
+                continue;
+            }
             const float m = mean[c + i];
             is[i] = invstd[c + i];
             nm[i] = -m * is[i];
@@ -630,7 +635,7 @@ struct BnBwdArgs {
     const float *mean, *invstd, *gamma, *beta;
     float *work;
     int64_t M, upc;
-    int C, pool_k, relu, nparts;
+    int C, Cv, pool_k, relu, nparts;
 };
 
 template <typename T, int V, typename F>
@@ -638,7 +643,7 @@ __device__ __forceinline__ void bwd_fill(F &f, const BnBwdArgs &a)
 {
     f.y = (const T *)a.y, f.gz = (const T *)a.gz, f.argmax = a.argmax, f.gy = (T *)a.gy;
     f.mean = a.mean, f.invstd = a.invstd, f.gamma = a.gamma, f.beta = a.beta, f.sums = a.work;
-    f.C = a.C, f.relu = a.relu, f.pool_k = a.pool_k, f.invM = 1.f / (float)a.M;
+    f.C = a.C, f.Cv = a.Cv, f.relu = a.relu, f.pool_k = a.pool_k, f.invM = 1.f / (float)a.M;
     f.s_const = nullptr;
 }
 
@@ -670,7 +675,7 @@ bn_bwd_fused_kernel(const BnBwdArgs a)
     // the folded conv bias = sum_rows gy = -gamma*invstd * (sum yhat) * (sum dy*yhat) / M
     {
         const int lane = threadIdx.x & 31;
-        PCB_FOLD_LOOP(c, C) {
+        PCB_FOLD_LOOP(c, a.Cv) {
             const float gi = a.gamma[c] * a.invstd[c];
             float s[3];
             fold_channel<3>(parts, a.nparts, C, c, s);
@@ -690,6 +695,11 @@ bn_bwd_fused_kernel(const BnBwdArgs a)
         s_const = &s_part[0][0][0];
         const float invM = 1.f / (float)a.M;
         for (int c = threadIdx.x; c < C; c += kBnThreads) {
+            if (c >= a.Cv) {                                 // pad channel: every constant zero -> gy = 0
+#pragma unroll
+                for (int j = 0; j < 6; ++j) s_const[j * C + c] = 0.f;
+                continue;
+            }
             const float m = a.mean[c], is = a.invstd[c];
             const float sc = is * a.gamma[c];                // same expressions as BwdBase::consts
             s_const[c] = -m * is;
@@ -807,18 +817,19 @@ PCB_API int pcb_bn_debug_trace(unsigned long long *host_out)
 
 PCB_API int64_t pcb_bn_work_floats(int C) { return 3 * (int64_t)C * (1 + kBnMaxParts); }
 
-PCB_API int pcb_bn_fwd_rows(const void *y, int dtype, int64_t M, int C, int pool_k, const float *bias,
+PCB_API int pcb_bn_fwd_rows(const void *y, int dtype, int64_t M, int C, int Cv, int pool_k, const float *bias,
                             const float *gamma, const float *beta, float eps, float momentum, float *running_mean,
                             float *running_var, int relu, float *mean, float *invstd, void *out,
                             unsigned char *argmax, float *work, pcb_stream_t stream)
 {
     PCB_REQUIRE(y && gamma && beta && mean && invstd && out && work, PCB_EINVAL);
     PCB_BN_CHECK(M, C, pool_k);
+    PCB_REQUIRE(Cv > 0 && Cv <= C && (Cv == C || C <= 1024), PCB_ERANGE);   // padded rows use the shared-memory constants
     PCB_REQUIRE(!running_mean || running_var, PCB_EINVAL);
     BnFwdArgs a;
     a.y = y, a.out = out, a.argmax = argmax, a.bias = bias, a.gamma = gamma, a.beta = beta;
     a.running_mean = running_mean, a.running_var = running_var;
-    a.mean = mean, a.invstd = invstd, a.work = work, a.M = M, a.C = C, a.pool_k = pool_k, a.relu = relu;
+    a.mean = mean, a.invstd = invstd, a.work = work, a.M = M, a.C = C, a.Cv = Cv, a.pool_k = pool_k, a.relu = relu;
     a.eps = eps, a.momentum = momentum, a.upc = 0, a.nparts = 0;
     cudaStream_t st = (cudaStream_t)stream;
     if (!dtype) return bn_fwd_launch<float, 4>(a, st);
@@ -827,15 +838,16 @@ PCB_API int pcb_bn_fwd_rows(const void *y, int dtype, int64_t M, int C, int pool
 }
 
 PCB_API int pcb_bn_bwd_rows(const void *gz, const void *y, const unsigned char *argmax, int dtype, int64_t M, int C,
-                            int pool_k, const float *mean, const float *invstd, const float *gamma, const float *beta,
+                            int Cv, int pool_k, const float *mean, const float *invstd, const float *gamma, const float *beta,
                             int relu, float *work, void *gy, pcb_stream_t stream)
 {
     PCB_REQUIRE(gz && y && mean && invstd && gamma && beta && work && gy, PCB_EINVAL);
     PCB_BN_CHECK(M, C, pool_k);
+    PCB_REQUIRE(Cv > 0 && Cv <= C, PCB_ERANGE);
     PCB_REQUIRE(pool_k == 1 || argmax, PCB_EINVAL);
     BnBwdArgs a;
     a.gz = gz, a.y = y, a.argmax = argmax, a.gy = gy, a.mean = mean, a.invstd = invstd, a.gamma = gamma, a.beta = beta;
-    a.work = work, a.M = M, a.C = C, a.pool_k = pool_k, a.relu = relu, a.upc = 0, a.nparts = 0;
+    a.work = work, a.M = M, a.C = C, a.Cv = Cv, a.pool_k = pool_k, a.relu = relu, a.upc = 0, a.nparts = 0;
     cudaStream_t st = (cudaStream_t)stream;
     if (!dtype) return bn_bwd_launch<float, 4>(a, st);
     if (C % 8 == 0 && al16(y) && al16(gz) && al16(gy)) return bn_bwd_launch<__nv_bfloat16, 8>(a, st);

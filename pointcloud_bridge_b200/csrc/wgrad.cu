@@ -59,7 +59,7 @@ __device__ __forceinline__ void load_tile(unsigned char *dst, const __nv_bfloat1
 
 __global__ void __launch_bounds__(kWgThreads, 3)
 wgrad_rows_kernel(const __nv_bfloat16 *__restrict__ gy, const __nv_bfloat16 *__restrict__ x, int64_t M, int N, int K,
-                  int ldx, int tiles_k, int64_t rows_per_split, float *__restrict__ gw, int ldw)
+                  int ldgy, int ldx, int tiles_k, int64_t rows_per_split, float *__restrict__ gw, int ldw)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     const int tile = blockIdx.x;
@@ -88,7 +88,7 @@ wgrad_rows_kernel(const __nv_bfloat16 *__restrict__ gy, const __nv_bfloat16 *__r
             const int s = chunk % kWgStages;
             const int64_t r0 = rbeg + (int64_t)chunk * kWgTile;
             // rows beyond this split's end belong to the next split: mask them through M = rend
-            load_tile(stage_a(s), gy, rend, N, N, r0, n0);
+            load_tile(stage_a(s), gy, rend, (N + 7) & ~7, ldgy, r0, n0);   // columns N..ldgy-1 of gy are zero
             load_tile(stage_b(s), x, rend, K8, ldx, r0, k0);
         }
         cp_async_commit();
@@ -179,12 +179,12 @@ wgrad_rows_kernel(const __nv_bfloat16 *__restrict__ gy, const __nv_bfloat16 *__r
 
 using namespace pcb;
 
-PCB_API int pcb_wgrad_rows_bf16(const void *gy, const void *x, int64_t M, int N, int K, int ldx, float *gw, int ldw,
-                                pcb_stream_t stream)
+PCB_API int pcb_wgrad_rows_bf16(const void *gy, const void *x, int64_t M, int N, int K, int ldgy, int ldx, float *gw,
+                                int ldw, pcb_stream_t stream)
 {
     PCB_REQUIRE(gy && x && gw, PCB_EINVAL);
     PCB_REQUIRE(M > 0 && N > 0 && K > 0 && ldw >= K, PCB_EINVAL);
-    PCB_REQUIRE(N % 8 == 0 && ldx % 8 == 0 && ldx >= ((K + 7) & ~7), PCB_ERANGE);
+    PCB_REQUIRE(ldgy % 8 == 0 && ldgy >= ((N + 7) & ~7) && ldx % 8 == 0 && ldx >= ((K + 7) & ~7), PCB_ERANGE);
     PCB_REQUIRE((reinterpret_cast<uintptr_t>(gy) & 15) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0, PCB_EALIGN);
     const int tiles_n = (N + kWgTile - 1) / kWgTile, tiles_k = (K + kWgTile - 1) / kWgTile;
     const int64_t tiles = (int64_t)tiles_n * tiles_k;
@@ -210,6 +210,6 @@ PCB_API int pcb_wgrad_rows_bf16(const void *gy, const void *x, int64_t M, int N,
     }
     dim3 grid((unsigned)tiles, (unsigned)splits);
     wgrad_rows_kernel<<<grid, kWgThreads, smem, (cudaStream_t)stream>>>(
-        (const __nv_bfloat16 *)gy, (const __nv_bfloat16 *)x, M, N, K, ldx, tiles_k, rows_per_split, gw, ldw);
+        (const __nv_bfloat16 *)gy, (const __nv_bfloat16 *)x, M, N, K, ldgy, ldx, tiles_k, rows_per_split, gw, ldw);
     PCB_RETURN_LAUNCH_STATUS();
 }

@@ -472,7 +472,8 @@ class _BnReluRows(torch.autograd.Function):
     def forward(ctx, y, bias, gamma, beta, running_mean, running_var, momentum, eps, relu, pool_k):
         if not y.is_contiguous():
             y = y.contiguous()
-        M, C = y.shape
+        M, C = y.shape                    # C: row pitch; Cv real channels (y may carry zero pad columns)
+        Cv = gamma.shape[0]
         dt = _act_dtype(y)
         dev = y.device
         stats = torch.empty(2, C, dtype=torch.float32, device=dev)          # mean, invstd of bias-free y
@@ -482,33 +483,33 @@ class _BnReluRows(torch.autograd.Function):
         g32, b32 = gamma.float(), beta.float()
         work = _bn_work(C, dev)
         esz = y.element_size()
-        _call("pcb_bn_fwd_rows", dev, y.data_ptr(), dt, M, C, int(pool_k),
+        _call("pcb_bn_fwd_rows", dev, y.data_ptr(), dt, M, C, Cv, int(pool_k),
               bias.data_ptr() if bias is not None else None, g32.data_ptr(), b32.data_ptr(), float(eps),
               float(momentum), running_mean.data_ptr() if running_mean is not None else None,
               running_var.data_ptr() if running_var is not None else None, int(relu), stats[0].data_ptr(),
               stats[1].data_ptr(), out.data_ptr(), argmax.data_ptr() if argmax is not None else None,
               work.data_ptr(), alg_bytes=(y.numel() + out.numel()) * esz + (Mout * C if pool_k > 1 else 0))
         ctx.save_for_backward(y, stats, g32, b32, argmax)
-        ctx.meta = (M, C, dt, int(relu), int(pool_k), bias is not None)
+        ctx.meta = (M, C, Cv, dt, int(relu), int(pool_k), bias is not None)
         return out
 
     @staticmethod
     def backward(ctx, gz):
         y, stats, g32, b32, argmax = ctx.saved_tensors
-        M, C, dt, relu, pool_k, has_bias = ctx.meta
+        M, C, Cv, dt, relu, pool_k, has_bias = ctx.meta
         gz = gz.contiguous()
         if gz.dtype != y.dtype:
             gz = gz.to(y.dtype)
         gy = torch.empty_like(y)
         work = _bn_work(C, y.device)
         _call("pcb_bn_bwd_rows", y.device, gz.data_ptr(), y.data_ptr(), argmax.data_ptr() if argmax is not None else None,
-              dt, M, C, pool_k, stats[0].data_ptr(), stats[1].data_ptr(), g32.data_ptr(), b32.data_ptr(), relu,
+              dt, M, C, Cv, pool_k, stats[0].data_ptr(), stats[1].data_ptr(), g32.data_ptr(), b32.data_ptr(), relu,
               work.data_ptr(), gy.data_ptr(),
               alg_bytes=(2 * y.numel() + gz.numel()) * y.element_size() + (gz.numel() if pool_k > 1 else 0))
         s = work[:3 * C].view(3, C)
         # s[2] = d/d(conv bias) = sum_rows gy: zero up to rounding, as in the reference, where the bias of a
         # conv that feeds a training-mode BN gets a noise gradient
-        return gy, (s[2] if has_bias else None), s[1], s[0], None, None, None, None, None, None
+        return gy, (s[2, :Cv] if has_bias else None), s[1, :Cv], s[0, :Cv], None, None, None, None, None, None
 
 
 def bn_relu_rows(y, bias, bn, relu=True, pool_k=1):
@@ -645,13 +646,15 @@ class StepContext:
         self.by_id = {}
         for p in params:
             n, k = p.shape[0], p[0].numel()
-            sh = torch.zeros(n, -(-k // 8) * 8, dtype=torch.bfloat16, device=p.device)
+            # [n rounded up to 8, k rounded up to 8], zero padded: pad columns match zero-padded input rows,
+            # pad rows make the OUTPUT rows 16-byte aligned (196 -> 200 channels) when linear_rows(pad_n=True)
+            sh = torch.zeros(-(-n // 8) * 8, -(-k // 8) * 8, dtype=torch.bfloat16, device=p.device)
             self.by_id[id(p)] = sh
             if sh.shape[1] == k:
                 self.dense.append(p)
-                self.dense_shadows.append(sh)
+                self.dense_shadows.append(sh[:n])
             else:
-                self.ragged.append((p, sh[:, :k]))
+                self.ragged.append((p, sh[:n, :k]))
 
     def __enter__(self):
         global _step_ctx
@@ -685,6 +688,7 @@ _WGRAD_CHUNK = int(os.environ.get("PCB_WGRAD_CHUNK", "2048"))
 
 
 _WGRAD_KERNEL = os.environ.get("PCB_NO_WGRAD_KERNEL", "0") != "1"
+_PAD_N = os.environ.get("PCB_NO_PAD_N", "0") != "1"          # debugging aid: keep unaligned output rows
 
 
 def wgrad_rows_supported(gy, x) -> bool:
@@ -694,15 +698,16 @@ def wgrad_rows_supported(gy, x) -> bool:
 
 
 @torch.no_grad()
-def wgrad_rows(gy, x, k: int | None = None, out: torch.Tensor | None = None) -> torch.Tensor:
-    """gy [M,N]^T @ x [M,Kp][:, :k] in fp32 (bf16 operands, rows = the long contraction dimension).
-    `out` [N,k] fp32 is accumulated into when given."""
-    M, N = gy.shape
+def wgrad_rows(gy, x, k: int | None = None, out: torch.Tensor | None = None, n: int | None = None) -> torch.Tensor:
+    """gy [M,Np][:, :n]^T @ x [M,Kp][:, :k] in fp32 (bf16 operands, rows = the long contraction dimension;
+    pad columns of gy and x are zero).  `out` [n,k] fp32 is accumulated into when given."""
+    M = gy.shape[0]
+    n = gy.shape[1] if n is None else n
     k = x.shape[1] if k is None else k
     if out is None:
-        out = torch.zeros(N, k, dtype=torch.float32, device=gy.device)
-    _call("pcb_wgrad_rows_bf16", gy.device, gy.data_ptr(), x.data_ptr(), M, N, k, x.shape[1], out.data_ptr(),
-          out.stride(0), alg_bytes=2 * M * (N + x.shape[1]) + 4 * N * k)
+        out = torch.zeros(n, k, dtype=torch.float32, device=gy.device)
+    _call("pcb_wgrad_rows_bf16", gy.device, gy.data_ptr(), x.data_ptr(), M, n, k, gy.shape[1], x.shape[1],
+          out.data_ptr(), out.stride(0), alg_bytes=2 * M * (gy.shape[1] + x.shape[1]) + 4 * n * k)
     return out
 
 
@@ -713,17 +718,23 @@ class _LinearRows(torch.autograd.Function):
     K (`group_points(pad_to=8)`): the weight is padded to match and its gradient sliced back."""
 
     @staticmethod
-    def forward(ctx, x, w, w_lp, gview=None):
-        # w_lp: the weight already in x's dtype (StepContext shadow) or None
+    def forward(ctx, x, w, w_lp, gview=None, pad_n=False):
+        # w_lp: the weight already in x's dtype (StepContext shadow [n8, k8], zero padded) or None
         # gview: fp32 view of the step runner's flat gradient buffer for w, or None
+        # pad_n: emit n8 output columns (zero pad columns) instead of n
         ctx.gview = gview
-        wl = w_lp if w_lp is not None else w.to(x.dtype)
+        n = w.shape[0]
+        if w_lp is not None:
+            wl = w_lp if pad_n else w_lp[:n]
+        else:
+            wl = w.to(x.dtype)
         if wl.shape[1] > x.shape[1]:                      # padded shadow, dense rows
             wl = wl[:, :x.shape[1]]
         elif wl.shape[1] < x.shape[1]:
             wl = torch.nn.functional.pad(wl, (0, x.shape[1] - wl.shape[1]))
         ctx.save_for_backward(x, wl)
         ctx.kw = w.shape[1]
+        ctx.n = n
         return torch.mm(x, wl.t())
 
     @staticmethod
@@ -740,26 +751,28 @@ class _LinearRows(torch.autograd.Function):
             c = _WGRAD_CHUNK
             if _WGRAD_KERNEL and wgrad_rows_supported(gy, x):
                 if ctx.gview is not None:                 # accumulate in place; .grad of the parameter stays None
-                    wgrad_rows(gy, x, ctx.kw, out=ctx.gview.view(gy.shape[1], ctx.kw))
-                    return gx, None, None, None
-                gw = wgrad_rows(gy, x, ctx.kw)
+                    wgrad_rows(gy, x, ctx.kw, out=ctx.gview.view(ctx.n, ctx.kw), n=ctx.n)
+                    return gx, None, None, None, None
+                gw = wgrad_rows(gy, x, ctx.kw, n=ctx.n)
             elif c and M % c == 0 and M // c >= 8:
                 p = M // c
                 part = torch.bmm(gy.view(p, c, -1).transpose(1, 2), x.view(p, c, -1))   # [p,N,K]
                 gw = part.sum(dim=0, dtype=torch.float32)
             else:
                 gw = torch.mm(gy.t(), x).float()
-            if gw.shape[1] != ctx.kw:
-                gw = gw[:, :ctx.kw]
-        return gx, gw, None, None
+            if gw.shape[1] != ctx.kw or gw.shape[0] != ctx.n:
+                gw = gw[:ctx.n, :ctx.kw]
+        return gx, gw, None, None, None
 
 
-def linear_rows(x, w):
+def linear_rows(x, w, pad_n: bool = False):
     """x [M,K] @ w[N,K]^T under the ambient autocast dtype.  x may carry zero pad columns beyond
-    K (group_points(pad_to=8)); the weight is padded to match and its gradient sliced back."""
+    K (group_points(pad_to=8)); the weight is padded to match and its gradient sliced back.
+    pad_n: when N is not a multiple of 8 and a bf16 weight shadow exists (StepContext), the result
+    has N rounded up to 8 columns, the extra ones zero -- 16-byte aligned rows for the next GEMM."""
     if torch.is_autocast_enabled():
         dt = torch.get_autocast_dtype("cuda")
         x = x if x.dtype == dt else x.to(dt)
     w_lp = _step_ctx.shadow(w) if (_step_ctx is not None and x.dtype == torch.bfloat16) else None
     gview = _step_ctx.grad_view(w) if (_step_ctx is not None and x.dtype == torch.bfloat16) else None
-    return _LinearRows.apply(x, w, w_lp, gview)
+    return _LinearRows.apply(x, w, w_lp, gview, bool(pad_n and w_lp is not None and _PAD_N))

@@ -121,12 +121,15 @@ def conv_bn_relu_rows(x, conv, bn, pool_k=1):
     the normalisation and ReLU / max-pool happen in the same pass."""
     w = conv.weight.flatten(1)
     padded = x.shape[1] != w.shape[1]                     # zero pad columns from group_points(pad_to=8)
-    if bn.training and x.is_cuda and w.shape[0] % 4 == 0 and bn.momentum is not None and bn.affine \
+    if bn.training and x.is_cuda and bn.momentum is not None and bn.affine \
             and x.shape[0] % pool_k == 0 and 1 < pool_k + 1 <= 256 and x.shape[0] > 1:
-        # bias-free: BN(xW + b) == BN(xW) + running-mean shift
-        y = ops.linear_rows(x, w)
+        # bias-free: BN(xW + b) == BN(xW) + running-mean shift.  Output channels that are not a multiple
+        # of 8 (196 in the MSG network) are carried as zero pad columns through BN into the next layer:
+        # 392-byte rows would send the neighbouring GEMMs to cuBLAS's unaligned legacy kernels
+        y = ops.linear_rows(x, w, pad_n=True)
         if ops.bn_rows_supported(y, bn, pool_k):
             return ops.bn_relu_rows(y, conv.bias, bn, relu=True, pool_k=pool_k)
+        y = y[:, :w.shape[0]]
         x = y if conv.bias is None else y + conv.bias
     else:
         x = F.linear(x, F.pad(w, (0, x.shape[1] - w.shape[1])) if padded else w, conv.bias)
@@ -142,6 +145,8 @@ def mlp_rows(x, convs, bns, pool_k=1):
     n = len(convs)
     for i, (conv, bn) in enumerate(zip(convs, bns)):
         x = conv_bn_relu_rows(x, conv, bn, pool_k if i == n - 1 else 1)
+    if x.shape[1] != convs[-1].weight.shape[0]:          # zero pad columns of the last layer are dropped
+        x = x[:, :convs[-1].weight.shape[0]].contiguous()
     return x
 
 

@@ -72,3 +72,68 @@ def test_wgrad_rows_kernel(M, N, K, Kp):
     out = torch.ones(N, K, device="cuda")
     ops.wgrad_rows(gy, x, K, out=out)
     assert (out.double() - 1.0 - ref).abs().max().item() <= 2e-5 * scale + 1e-4 * (M ** 0.5) * 1e-2
+
+
+@pytest.mark.parametrize("M,Cv,pool_k", [(1024 * 16, 196, 1), (512 * 16, 196, 16), (300, 12, 1)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_bn_relu_rows_with_zero_pad_columns(M, Cv, pool_k, dtype):
+    """Rows padded with zero columns up to a multiple of 8 (196 -> 200 channels): the real channels match the
+    unpadded computation, the pad columns of the output and of the input gradient are exactly zero."""
+    torch.manual_seed(M + Cv)
+    C = -(-Cv // 8) * 8
+    y0 = (torch.randn(M, Cv, device=DEV) * 2 + 3 * torch.randn(Cv, device=DEV)).to(dtype)
+    yp0 = torch.zeros(M, C, device=DEV, dtype=dtype)
+    yp0[:, :Cv] = y0
+    bias0 = torch.randn(Cv, device=DEV)
+    bn_a, bn_b = torch.nn.BatchNorm1d(Cv).to(DEV).train(), torch.nn.BatchNorm1d(Cv).to(DEV).train()
+    with torch.no_grad():
+        bn_a.weight.uniform_(0.5, 1.5)
+        bn_a.bias.normal_()
+        bn_b.load_state_dict(bn_a.state_dict())
+    ya, ba = yp0.clone().requires_grad_(True), bias0.clone().requires_grad_(True)
+    yb, bb = y0.clone().requires_grad_(True), bias0.clone().requires_grad_(True)
+    za = ops.bn_relu_rows(ya, ba, bn_a, relu=True, pool_k=pool_k)
+    zb = ops.bn_relu_rows(yb, bb, bn_b, relu=True, pool_k=pool_k)
+    assert za.shape == (M // pool_k, C) and not za[:, Cv:].any()
+    ftol = 1e-5 if dtype == torch.float32 else 1e-2        # the partial-sum grouping differs with the row pitch
+    assert (za[:, :Cv].float() - zb.float()).abs().max().item() <= ftol * (zb.float().abs().max().item() + 1e-6)
+    assert torch.allclose(bn_a.running_mean, bn_b.running_mean, rtol=1e-5, atol=1e-6)
+    assert torch.allclose(bn_a.running_var, bn_b.running_var, rtol=1e-5, atol=1e-6)
+    g = torch.randn_like(zb)
+    gp = torch.zeros_like(za)
+    gp[:, :Cv] = g
+    za.backward(gp)
+    zb.backward(g)
+    assert not ya.grad[:, Cv:].any()
+    tol = 1e-5 if dtype == torch.float32 else 2e-2
+    assert (ya.grad[:, :Cv].float() - yb.grad.float()).abs().max().item() <= tol * (yb.grad.abs().max().item() + 1e-9)
+    for pa, pb in ((bn_a.weight, bn_b.weight), (bn_a.bias, bn_b.bias)):
+        assert pa.grad.shape == pb.grad.shape
+        assert (pa.grad - pb.grad).abs().max().item() <= 1e-4 * (pb.grad.abs().max().item() + 1e-6)
+
+
+def test_linear_rows_padded_output_channels():
+    """linear_rows(pad_n=True) with a StepContext shadow: 196 output channels come out as 200 columns, the
+    extra ones zero; values, input gradient and weight gradient equal the unpadded layer's."""
+    torch.manual_seed(0)
+    M, K, N = 4096, 24, 196
+    conv = torch.nn.Conv2d(K, N, 1).to(DEV)
+    nxt = torch.nn.Conv2d(N, 64, 1).to(DEV)
+    mod = torch.nn.ModuleList([conv, nxt])
+    x = torch.randn(M, K, device=DEV).to(torch.bfloat16).requires_grad_(True)
+    ctx = ops.StepContext(mod, bf16=True)
+    with ctx, torch.autocast("cuda", dtype=torch.bfloat16):
+        yp = ops.linear_rows(x, conv.weight.flatten(1), pad_n=True)
+        yr = ops.linear_rows(x, conv.weight.flatten(1), pad_n=False)
+        assert yp.shape == (M, 200) and yr.shape == (M, N) and not yp[:, N:].any()
+        assert (yp[:, :N].float() - yr.float()).abs().max().item() <= 1e-2 * yr.float().abs().max().item()
+        # the next layer consumes the padded rows as they are
+        zp = ops.linear_rows(yp, nxt.weight.flatten(1))
+        zr = ops.linear_rows(yr, nxt.weight.flatten(1))
+        assert (zp.float() - zr.float()).abs().max().item() <= 2e-2 * zr.float().abs().max().item()
+        g = torch.randn_like(zr)
+        gp = torch.autograd.grad(zp, [x, conv.weight, nxt.weight], g)
+        gr = torch.autograd.grad(zr, [x, conv.weight, nxt.weight], g)
+    for a, b in zip(gp, gr):
+        assert a.shape == b.shape
+        assert ((a.float() - b.float()).norm() / b.float().norm()).item() <= 2e-2

@@ -60,12 +60,12 @@ def main():
         nb = y.numel() * 2
 
         def fwd():
-            return lib.pcb_bn_fwd_rows(y.data_ptr(), 1, M, C, K, None, g.data_ptr(), b.data_ptr(), 1e-5, 0.1, None, None, 1,
+            return lib.pcb_bn_fwd_rows(y.data_ptr(), 1, M, C, C, K, None, g.data_ptr(), b.data_ptr(), 1e-5, 0.1, None, None, 1,
                                        stats[0].data_ptr(), stats[1].data_ptr(), out.data_ptr(),
                                        am.data_ptr() if K > 1 else None, work.data_ptr(), torch.cuda.current_stream().cuda_stream)
 
         def bwd():
-            return lib.pcb_bn_bwd_rows(gz.data_ptr(), y.data_ptr(), am.data_ptr() if K > 1 else None, 1, M, C, K,
+            return lib.pcb_bn_bwd_rows(gz.data_ptr(), y.data_ptr(), am.data_ptr() if K > 1 else None, 1, M, C, C, K,
                                        stats[0].data_ptr(), stats[1].data_ptr(), g.data_ptr(), b.data_ptr(), 1,
                                        work.data_ptr(), gy.data_ptr(), torch.cuda.current_stream().cuda_stream)
         assert fwd() == 0 and bwd() == 0
