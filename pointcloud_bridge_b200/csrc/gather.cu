@@ -57,6 +57,43 @@ gather_kernel(const float *__restrict__ points, const int64_t *__restrict__ idx,
     if (!ok && err && c == 0) atomicAdd(err, 1);
 }
 
+// 128-bit variant with U rows in flight per thread: thread (rg, cv) serves float4 column cv of rows
+// rg, rg + RG, ..., so the U index loads and then the U row loads are independent of each other (one
+// load in flight per thread left the kernel latency-bound at ~55 % of the HBM peak).
+constexpr int kGatherU = 4;
+__global__ void __launch_bounds__(kThreads)
+gather_vec_ilp_kernel(const float *__restrict__ points, const int64_t *__restrict__ idx, int N, int C, FastDiv dCV,
+                      FastDiv dM, unsigned RG, unsigned rows, int clamp, float *__restrict__ out, int *__restrict__ err)
+{
+    const unsigned t = blockIdx.x * kThreads + threadIdx.x;
+    const unsigned rg = dCV.div(t);
+    if (rg >= RG) return;
+    const int c = (int)(t - rg * dCV.d) * 4;
+    long long i[kGatherU];
+    unsigned row[kGatherU];
+    bool live[kGatherU], ok[kGatherU];
+#pragma unroll
+    for (int u = 0; u < kGatherU; ++u) {
+        row[u] = rg + u * RG;
+        live[u] = row[u] < rows;
+        i[u] = live[u] ? idx[row[u]] : 0;
+    }
+    float4 v[kGatherU];
+#pragma unroll
+    for (int u = 0; u < kGatherU; ++u) {
+        ok[u] = resolve_index(i[u], N, clamp);
+        const unsigned b = dM.div(row[u]);
+        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (live[u] && ok[u]) v[u] = __ldg(reinterpret_cast<const float4 *>(points + ((size_t)b * N + i[u]) * C + c));
+    }
+#pragma unroll
+    for (int u = 0; u < kGatherU; ++u)
+        if (live[u]) {
+            st_stream_f4(reinterpret_cast<float4 *>(out + (size_t)row[u] * C + c), v[u]);
+            if (!ok[u] && err && c == 0) atomicAdd(err, 1);
+        }
+}
+
 template <int VEC>
 __global__ void __launch_bounds__(kThreads)
 gather_bwd_kernel(const float *__restrict__ gout, const int64_t *__restrict__ idx, int N, int C, FastDiv dCV,
@@ -179,47 +216,189 @@ __device__ __forceinline__ void ldp8(const __nv_bfloat16 *p, float v[8])
 }
 
 // PT: type of the feature rows (fp32, or bf16 when the previous layer ran under autocast)
+// Thread (rg, q) serves 8-channel chunk q of rows rg, rg + RG, ... (U rows in flight: the index loads, then
+// the gathers, then the stores of the U rows are independent -- a single dependent idx -> row -> store
+// chain per thread left the kernel latency-bound at a third of the HBM peak).
+#ifndef PCB_GROUP_U
+#define PCB_GROUP_U 1
+#endif
+constexpr int kGroupU = PCB_GROUP_U;
 template <typename OT, typename PT>
 __global__ void __launch_bounds__(kThreads)
 group_points_chunk_kernel(const float *__restrict__ xyz, const PT *__restrict__ points,
                           const float *__restrict__ new_xyz, const int64_t *__restrict__ idx, int N, int D, FastDiv dQ,
-                          FastDiv dK, FastDiv dS, int xyz_first, int points_cf, int clamp, int vec_ok, unsigned total,
-                          OT *__restrict__ out)
+                          FastDiv dK, FastDiv dS, int xyz_first, int points_cf, int clamp, int vec_ok, unsigned RG,
+                          unsigned rows, OT *__restrict__ out)
 {
     // dQ.d = chunks per row = pitch / 8
     const unsigned t = blockIdx.x * kThreads + threadIdx.x;
-    if (t >= total) return;
-    const unsigned rowg = dQ.div(t);                   // (b*S + s)*K + k
-    const int c0 = (int)(t - rowg * dQ.d) * 8;
-    const unsigned bs = dK.div(rowg);
-    const unsigned b = dS.div(bs);
-    long long i = idx[rowg];
-    const bool ok = resolve_index(i, N, clamp);
-    float v[8];
+    const unsigned rg = dQ.div(t);
+    if (rg >= RG) return;
+    const int q = (int)(t - rg * dQ.d);
+    const int c0 = q * 8;
+    unsigned row[kGroupU];
+    long long i[kGroupU];
+    bool live[kGroupU];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = 0.f;
-    if (ok) {
-        const int f0 = xyz_first ? c0 - 3 : c0;        // feature channel of the chunk's first element
-        if (vec_ok && f0 >= 0 && f0 + 8 <= D && (f0 & 7) == 0) {
-            ldp8(points + ((size_t)b * N + i) * D + f0, v);
-        } else {
+    for (int u = 0; u < kGroupU; ++u) {
+        row[u] = rg + u * RG;                          // (b*S + s)*K + k
+        live[u] = row[u] < rows;
+        i[u] = live[u] ? idx[row[u]] : 0;
+    }
+    const int f0 = xyz_first ? c0 - 3 : c0;            // feature channel of the chunk's first element
+    float v[kGroupU][8];
+    if (vec_ok && f0 >= 0 && f0 + 8 <= D && (f0 & 7) == 0) {       // whole chunk inside the features: same for all rows
+#pragma unroll
+        for (int u = 0; u < kGroupU; ++u) {
+            const bool ok = resolve_index(i[u], N, clamp);
+            const unsigned b = dS.div(dK.div(row[u]));
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[u][j] = 0.f;
+            if (live[u] && ok) ldp8(points + ((size_t)b * N + i[u]) * D + f0, v[u]);
+        }
+    } else if (!xyz_first && c0 == D) {                // the [dxyz | 0 0 0 0 0] chunk that ends a [feat | dxyz] row
+        float px[kGroupU][3], qx[kGroupU][3];
+        bool ok[kGroupU];
+#pragma unroll
+        for (int u = 0; u < kGroupU; ++u) {
+            ok[u] = resolve_index(i[u], N, clamp) && live[u];
+            const unsigned bs = live[u] ? dK.div(row[u]) : 0u;
+            const unsigned b = dS.div(bs);
+            const float *p = xyz + ((size_t)b * N + (ok[u] ? i[u] : 0)) * 3;
+            const float *c = new_xyz + (size_t)bs * 3;
+#pragma unroll
+            for (int j = 0; j < 3; ++j) px[u][j] = __ldg(p + j), qx[u][j] = __ldg(c + j);
+        }
+#pragma unroll
+        for (int u = 0; u < kGroupU; ++u) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[u][j] = 0.f;
+            if (ok[u]) {
+#pragma unroll
+                for (int j = 0; j < 3; ++j) v[u][j] = __fsub_rn(px[u][j], qx[u][j]);
+            }
+        }
+    } else {
+#pragma unroll
+        for (int u = 0; u < kGroupU; ++u) {
+            const bool ok = resolve_index(i[u], N, clamp);
+            const unsigned bs = dK.div(row[u]);
+            const unsigned b = dS.div(bs);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const int c = c0 + j;
-                if (c < 3 + D) {
+                float x = 0.f;
+                if (live[u] && ok && c < 3 + D) {
                     const int cx = xyz_first ? c : c - D;
                     if (cx >= 0 && cx < 3) {
-                        v[j] = __fsub_rn(__ldg(xyz + ((size_t)b * N + i) * 3 + cx), __ldg(new_xyz + (size_t)bs * 3 + cx));
+                        x = __fsub_rn(__ldg(xyz + ((size_t)b * N + i[u]) * 3 + cx), __ldg(new_xyz + (size_t)bs * 3 + cx));
                     } else {
                         const int cf = xyz_first ? c - 3 : c;
-                        v[j] = points_cf ? ldp(points + ((size_t)b * D + cf) * N + i)
-                                         : ldp(points + ((size_t)b * N + i) * D + cf);
+                        x = points_cf ? ldp(points + ((size_t)b * D + cf) * N + i[u])
+                                      : ldp(points + ((size_t)b * N + i[u]) * D + cf);
                     }
                 }
+                v[u][j] = x;
             }
         }
     }
-    store8(out + (size_t)t * 8, v);
+#pragma unroll
+    for (int u = 0; u < kGroupU; ++u)
+        if (live[u]) store8(out + ((size_t)row[u] * dQ.d + q) * 8, v[u]);
+}
+
+// ---- row-tile variant (point-major features) ----
+// A CTA owns TR consecutive output rows.  Their neighbour indices are resolved ONCE into shared memory
+// (global row number of the source point, or -1), so the gathers of the main loop do not hang off a
+// per-thread index load, every warp runs one code path (feature chunks first, the [dxyz | 0] tail
+// chunks of the same rows right after, while their cache lines are still in L2), and four independent
+// items are in flight per thread.  VEC8: [feat | dxyz | 0] rows with D % 8 == 0 and pitch D + 8 (the
+// training layout), 16-byte loads and stores; otherwise one element per item, any layout / pitch.
+constexpr int kTileMaxRows = 128;
+constexpr int kTileU = 4;
+template <typename OT, typename PT, bool VEC8>
+__global__ void __launch_bounds__(kThreads)
+group_tile_kernel(const float *__restrict__ xyz, const PT *__restrict__ points, const float *__restrict__ new_xyz,
+                  const int64_t *__restrict__ idx, int N, int D, int C, FastDiv dK, FastDiv dS, FastDiv dW,
+                  int xyz_first, int clamp, int TR, unsigned rows, OT *__restrict__ out)
+{
+    __shared__ int s_src[kTileMaxRows];                // b * N + i of the gathered point, -1: index out of range
+    __shared__ unsigned s_bs[kTileMaxRows];            // b * S + s (centroid row)
+    const unsigned row0 = blockIdx.x * (unsigned)TR;
+    const int nr = rows - row0 < (unsigned)TR ? (int)(rows - row0) : TR;
+    for (int w = threadIdx.x; w < nr; w += kThreads) {
+        const unsigned row = row0 + w;
+        long long i = idx[row];
+        const bool ok = resolve_index(i, N, clamp);
+        const unsigned bs = dK.div(row);
+        s_bs[w] = bs;
+        s_src[w] = ok ? (int)(dS.div(bs) * (unsigned)N + (unsigned)i) : -1;
+    }
+    __syncthreads();
+    if (VEC8) {
+        const int QF = D >> 3;                         // feature chunks per row; dW.d == QF
+        const int items = nr * QF;
+        for (int w0 = threadIdx.x; w0 < items; w0 += kThreads * kTileU) {
+            float v[kTileU][8];
+            int r[kTileU], q[kTileU];
+#pragma unroll
+            for (int u = 0; u < kTileU; ++u) {
+                const int w = w0 + u * kThreads;
+                r[u] = w < items ? (int)dW.div((unsigned)w) : -1;
+                q[u] = w - r[u] * QF;
+                const int src = r[u] >= 0 ? s_src[r[u]] : -1;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[u][j] = 0.f;
+                if (src >= 0) ldp8(points + (size_t)src * D + q[u] * 8, v[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < kTileU; ++u)
+                if (r[u] >= 0) store8(out + (size_t)(row0 + r[u]) * C + q[u] * 8, v[u]);
+        }
+        for (int w = threadIdx.x; w < nr; w += kThreads) {          // tail chunk: [dx dy dz 0 0 0 0 0]
+            const int src = s_src[w];
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = 0.f;
+            if (src >= 0) {
+                const float *p = xyz + (size_t)src * 3, *c = new_xyz + (size_t)s_bs[w] * 3;
+#pragma unroll
+                for (int j = 0; j < 3; ++j) v[j] = __fsub_rn(__ldg(p + j), __ldg(c + j));
+            }
+            store8(out + (size_t)(row0 + w) * C + D, v);
+        }
+    } else {
+        // one warp per row, lanes stride over the C output columns (no per-element division), kTileU rows in
+        // flight per warp; a row is written as contiguous 128-byte segments
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        constexpr int kWarps = kThreads / 32;
+        for (int r0 = warp; r0 < nr; r0 += kWarps * kTileU) {
+            int src[kTileU];
+            unsigned bs[kTileU];
+#pragma unroll
+            for (int u = 0; u < kTileU; ++u) {
+                const int r = r0 + u * kWarps;
+                src[u] = r < nr ? s_src[r] : -2;           // -2: no such row, -1: index out of range (row of zeros)
+                bs[u] = r < nr ? s_bs[r] : 0u;
+            }
+            for (int c = lane; c < C; c += 32) {
+                const int cx = xyz_first ? c : c - D;
+                const bool is_xyz = cx >= 0 && cx < 3;
+                const int cf = xyz_first ? c - 3 : c;
+                float v[kTileU];
+#pragma unroll
+                for (int u = 0; u < kTileU; ++u) {
+                    v[u] = 0.f;
+                    if (src[u] >= 0 && c < 3 + D)
+                        v[u] = is_xyz ? __fsub_rn(__ldg(xyz + (size_t)src[u] * 3 + cx), __ldg(new_xyz + (size_t)bs[u] * 3 + cx))
+                                      : ldp(points + (size_t)src[u] * D + cf);
+                }
+#pragma unroll
+                for (int u = 0; u < kTileU; ++u)
+                    if (src[u] != -2) store_out(out + (size_t)(row0 + r0 + u * kWarps) * C + c, v[u]);
+            }
+        }
+    }
 }
 
 // backward, 4 feature channels per thread: one 128-bit reduction (red.global.add.v4.f32) per thread.
@@ -298,6 +477,55 @@ graph_feature_kernel(const float *__restrict__ x, const int64_t *__restrict__ id
             } else {
                 st_stream_f1(o1, dif[0]);
                 st_stream_f1(o2, ctr[0]);
+            }
+        }
+    }
+}
+
+// Variant with the CPT channel rows of x[b] staged in shared memory (CPT * N floats): the neighbour
+// gathers then are LDS with a few-way bank conflict instead of 32 scattered L1 sectors per warp
+// instruction, which is what held the direct-gather kernel at ~46 % of the HBM peak (L1 wavefronts, not
+// DRAM).  grid = (edge splits, channel groups, clouds); a thread owns 4 consecutive (n, j) edges.
+constexpr int kGfsCPT = 4;
+constexpr int kGfsThreads = 512;
+__global__ void __launch_bounds__(kGfsThreads)
+graph_feature_smem_kernel(const float *__restrict__ x, const int64_t *__restrict__ idx, int D, int N, FastDiv dk,
+                          unsigned NK, unsigned edges_per_split, float *__restrict__ out)
+{
+    extern __shared__ __align__(16) float s_rows[];    // [kGfsCPT][N]
+    const int b = blockIdx.z;
+    const int c0 = blockIdx.y * kGfsCPT;
+    const int nch = D - c0 < kGfsCPT ? D - c0 : kGfsCPT;
+    const float *src = x + ((size_t)b * D + c0) * N;
+    for (int i = threadIdx.x; i < nch * N; i += kGfsThreads) s_rows[i] = __ldg(src + i);
+    __syncthreads();
+    const unsigned e_beg = blockIdx.x * edges_per_split;
+    const unsigned e_end = e_beg + edges_per_split < NK ? e_beg + edges_per_split : NK;
+    const int64_t *ib = idx + (size_t)b * NK;
+    for (unsigned e = e_beg + threadIdx.x * 4; e < e_end; e += kGfsThreads * 4) {
+        int n[4], nb[4];
+        const longlong2 i01 = *reinterpret_cast<const longlong2 *>(ib + e);
+        const longlong2 i23 = *reinterpret_cast<const longlong2 *>(ib + e + 2);
+        const long long raw[4] = {i01.x, i01.y, i23.x, i23.y};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            n[u] = (int)dk.div(e + u);
+            nb[u] = (int)(raw[u] < 0 ? 0 : (raw[u] > N - 1 ? N - 1 : raw[u]));
+        }
+#pragma unroll
+        for (int cc = 0; cc < kGfsCPT; ++cc) {
+            if (cc < nch) {
+                const float *row = s_rows + cc * N;
+                float ctr[4], dif[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    ctr[u] = row[n[u]];
+                    dif[u] = __fsub_rn(row[nb[u]], ctr[u]);
+                }
+                st_stream_f4(reinterpret_cast<float4 *>(out + ((size_t)b * 2 * D + c0 + cc) * NK + e),
+                             make_float4(dif[0], dif[1], dif[2], dif[3]));
+                st_stream_f4(reinterpret_cast<float4 *>(out + ((size_t)b * 2 * D + D + c0 + cc) * NK + e),
+                             make_float4(ctr[0], ctr[1], ctr[2], ctr[3]));
             }
         }
     }
@@ -642,7 +870,12 @@ PCB_API int pcb_gather_f32(const float *points, const int64_t *idx, int B, int N
         const float *p = points + (size_t)b0 * N * C;
         const int64_t *ix = idx + (size_t)b0 * M;
         float *o = out + (size_t)b0 * M * C;
-        if (vec)
+        if (vec && (int64_t)nb * M >= 4096) {
+            const unsigned rows = (unsigned)((int64_t)nb * M);
+            const unsigned RG = (rows + kGatherU - 1) / kGatherU;
+            gather_vec_ilp_kernel<<<blocks_for((int64_t)RG * CV), kThreads, 0, st>>>(
+                p, ix, N, C, make_fastdiv(CV), make_fastdiv((unsigned)M), RG, rows, clamp, o, err_count);
+        } else if (vec)
             gather_kernel<4><<<blocks_for(total), kThreads, 0, st>>>(p, ix, N, C, make_fastdiv(CV), make_fastdiv((unsigned)M),
                                                                     total, clamp, o, err_count);
         else
@@ -695,11 +928,29 @@ static int group_points_launch(const float *xyz, const PT *points, const float *
         const unsigned total = (unsigned)((int64_t)nb * S * K * C);
         const PT *pts = points ? points + (size_t)b0 * N * D : nullptr;
         OT *o = out + (size_t)b0 * S * K * C;
+        const unsigned nrows = (unsigned)((int64_t)nb * S * K);
+        const int TR = nrows >= 128u * 2 * PCB_NUM_SMS ? 128 : (nrows >= 64u * 2 * PCB_NUM_SMS ? 64 : 32);
+        const unsigned tiles = (nrows + TR - 1) / TR;
+        const bool tile_ok = !points_cf && (int64_t)nb * N < (1ll << 31);
+        if (tile_ok && pts && C % 8 == 0 && aligned16(o) && D % 8 == 0 && !xyz_first && C == D + 8 && aligned16(pts)) {
+            group_tile_kernel<OT, PT, true><<<tiles, kThreads, 0, st>>>(
+                xyz + (size_t)b0 * N * 3, pts, new_xyz + (size_t)b0 * S * 3, idx + (size_t)b0 * S * K, N, D, C,
+                make_fastdiv(K), make_fastdiv(S), make_fastdiv(D / 8), xyz_first, clamp, TR, nrows, o);
+            continue;
+        }
+        if (tile_ok && !(C % 8 == 0 && aligned16(o))) { // any layout / pitch, one element per item
+            group_tile_kernel<OT, PT, false><<<tiles, kThreads, 0, st>>>(
+                xyz + (size_t)b0 * N * 3, pts, new_xyz + (size_t)b0 * S * 3, idx + (size_t)b0 * S * K, N, D, C,
+                make_fastdiv(K), make_fastdiv(S), make_fastdiv(C), xyz_first, clamp, TR, nrows, o);
+            continue;
+        }
         if (C % 8 == 0 && aligned16(o)) {               // padded rows: 8 channels per thread
             const int vec_ok = pts && !points_cf && D % 8 == 0 && aligned16(pts);
-            group_points_chunk_kernel<OT, PT><<<blocks_for(total / 8), kThreads, 0, st>>>(
+            const unsigned rows = (unsigned)((int64_t)nb * S * K);
+            const unsigned RG = (rows + kGroupU - 1) / kGroupU;
+            group_points_chunk_kernel<OT, PT><<<blocks_for((int64_t)RG * (C / 8)), kThreads, 0, st>>>(
                 xyz + (size_t)b0 * N * 3, pts, new_xyz + (size_t)b0 * S * 3, idx + (size_t)b0 * S * K, N, D,
-                make_fastdiv(C / 8), make_fastdiv(K), make_fastdiv(S), xyz_first, points_cf, clamp, vec_ok, total / 8, o);
+                make_fastdiv(C / 8), make_fastdiv(K), make_fastdiv(S), xyz_first, points_cf, clamp, vec_ok, RG, rows, o);
             continue;
         }
         if (sizeof(PT) != 4) return PCB_ERANGE;         // bf16 feature rows need the padded (pitch % 8 == 0) layout
@@ -786,6 +1037,25 @@ PCB_API int pcb_graph_feature_f32(const float *x, const int64_t *idx, int B, int
     PCB_REQUIRE(B > 0 && D > 0 && N > 0 && k > 0, PCB_EINVAL);
     PCB_REQUIRE(B <= 65535 && ceil_div(D, kGfCPT) <= 65535 && (int64_t)N * k < (1ll << 31), PCB_ERANGE);
     const unsigned NK = (unsigned)N * (unsigned)k;
+    const size_t smem = (size_t)kGfsCPT * N * sizeof(float);
+    if (NK % 4 == 0 && aligned16(out) && aligned16(idx) && smem <= 96 * 1024 && NK >= 16384) {
+        // edge splits: enough CTAs for ~2 waves of 3 resident CTAs per SM, each split a multiple of 4 * threads
+        const unsigned groups = (unsigned)ceil_div(D, kGfsCPT);
+        unsigned splits = (unsigned)ceil_div(6 * PCB_NUM_SMS, (int64_t)groups * B);
+        const unsigned quantum = kGfsThreads * 4;
+        unsigned eps = (unsigned)ceil_div(ceil_div(NK, splits), quantum) * quantum;
+        splits = (unsigned)ceil_div(NK, eps);
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaError_t e = cudaFuncSetAttribute(graph_feature_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 96 * 1024);
+            if (e != cudaSuccess) return (int)e;
+            attr_set = true;
+        }
+        dim3 grid(splits, groups, (unsigned)B);
+        graph_feature_smem_kernel<<<grid, kGfsThreads, smem, (cudaStream_t)stream>>>(x, idx, D, N, make_fastdiv(k), NK, eps, out);
+        PCB_RETURN_LAUNCH_STATUS();
+    }
     if (NK % 4 == 0 && aligned16(out)) {
         dim3 grid((unsigned)ceil_div(NK / 4, kThreads), (unsigned)ceil_div(D, kGfCPT), (unsigned)B);
         graph_feature_kernel<4><<<grid, kThreads, 0, (cudaStream_t)stream>>>(x, idx, D, N, make_fastdiv(k), NK, out);

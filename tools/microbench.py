@@ -100,6 +100,50 @@ def main():
     f256 = torch.randn(B, 1024, 256, device=dev)
     bri_idx = ops.ball_query(0.4, 32, l1, ops.gather(l1, ops.furthest_point_sample(l1, 512, start)))
     rec("gather_bri_sa2_c256", lambda: ops.gather(f256, bri_idx), B * (4 * 1024 * 256 + 8 * 512 * 32 + 4 * 512 * 32 * 256))
+    # --- training-path rows: padded bf16 grouping of bf16 features, its backward, FP input rows, weight gradient
+    fps_l2 = ops.furthest_point_sample(l1, 256, start)
+    for (src_xyz, q_xyz, bq, D, tag) in ((xyz, l1, ball, 9, "L1_k32_c12"), (l1, l2, ball2, 96, "L2_k32_c99")):
+        n, s, k = src_xyz.shape[1], q_xyz.shape[1], bq.shape[2]
+        feats = torch.randn(B, n, D, device=dev)
+        feats = feats.to(torch.bfloat16) if D % 8 == 0 else feats
+        pitch = -(-(3 + D) // 8) * 8
+        nb = B * (feats.element_size() * n * D + 12 * n + 12 * s + 8 * s * k + 2 * s * k * pitch)
+
+        def grp(src_xyz=src_xyz, feats=feats, q_xyz=q_xyz, bq=bq):
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                return ops.group_points(src_xyz, feats, q_xyz, bq, xyz_first=False, pad_to=8)
+        rec("group_bf16_" + tag, grp, nb)
+        if D % 8 == 0:
+            fr = feats.clone().requires_grad_(True)
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                out = ops.group_points(src_xyz, fr, q_xyz, bq, xyz_first=False, pad_to=8)
+            go = torch.randn_like(out)
+            rec("group_bwd_bf16_" + tag, lambda out=out, fr=fr, go=go: torch.autograd.grad(out, fr, go, retain_graph=True),
+                B * (4 * n * D + 8 * s * k + 2 * s * k * D))
+    big_idx = torch.randint(0, 4096, (B, 4096, 32), device=dev)
+    fbig = torch.randn(B, 4096, 64, device=dev).to(torch.bfloat16)
+
+    def grp_big():
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            return ops.group_points(xyz, fbig, xyz, big_idx, xyz_first=False, pad_to=8)
+    rec("group_bf16_big_4096x32_c67", grp_big, B * (2 * N * 64 + 24 * N + 8 * N * 32 + 2 * N * 32 * 72))
+    d3t, i3t, w3t = ops.three_nn(xyz, l1, 3)
+    p1t = torch.randn(B, N, 64, device=dev).to(torch.bfloat16)
+    p2t = torch.randn(B, 1024, 128, device=dev).to(torch.bfloat16).requires_grad_(True)
+
+    def fpc():
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            return ops.fp_concat(p1t, p2t, i3t, w3t, pad_to=8)
+    rec("fp_concat_4096_1024_d64+128", fpc, B * (2 * N * 64 + 2 * 1024 * 128 + 12 * 3 * N + 2 * N * 192))
+    outc = fpc()
+    goc = torch.randn_like(outc)
+    rec("fp_concat_bwd_4096_1024_d128", lambda: torch.autograd.grad(outc, p2t, goc, retain_graph=True),
+        B * (4 * 1024 * 128 + 12 * 3 * N + 2 * N * 128))
+    for (M, Nn, K) in ((524288, 64, 32), (131072, 128, 96), (65536, 128, 128)):
+        gy = torch.randn(M, Nn, device=dev).to(torch.bfloat16)
+        xx = torch.randn(M, K, device=dev).to(torch.bfloat16)
+        gw = torch.zeros(Nn, K, device=dev)
+        rec(f"wgrad_rows_{M}x{Nn}x{K}", lambda gy=gy, xx=xx, gw=gw, K=K: ops.wgrad_rows(gy, xx, K, out=gw), 2 * M * (Nn + K))
     # --- three-NN + interpolate
     rec("three_nn_4096_1024", lambda: ops.three_nn(xyz, l1, 3), B * (12 * N + 12 * 1024 + 12 * 3 * N), B * N * 1024, "Gpairs_per_s")
     d3, i3, w3 = ops.three_nn(xyz, l1, 3)
