@@ -181,6 +181,15 @@ int pcb_bn_bwd_rows(const void *gz, const void *y, const unsigned char *argmax, 
 int pcb_wgrad_rows_bf16(const void *gy, const void *x, int64_t M, int N, int K, int ldgy, int ldx, float *gw,
                         int ldw, pcb_stream_t stream);
 
+/* ---- section 8f rank 4 (training runner): Adam over one flat fp32 parameter buffer
+ *          Highway_bridge/train_MulSca_BriStruNet_CB.py:158-190 (torch.optim.Adam, L2 weight decay)
+ * p, g, m, v [n] fp32; `lr` [1] fp32 and `step` [1] int64 (already incremented, >= 1) are DEVICE scalars so a
+ * captured CUDA graph follows a scheduler.  shadow_index [n] int32 (may be NULL): destination element of
+ * parameter i in `shadow_bf16`, the bf16 copies of the GEMM weights ([N8, K8] zero padded), or -1. */
+int pcb_adam_flat_f32(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, int64_t n, const float *lr,
+                      float beta1, float beta2, float eps, float weight_decay, const int64_t *step,
+                      const int *shadow_index, void *shadow_bf16, pcb_stream_t stream);
+
 /* ---- a11 / section 8f rank 1: fused set-abstraction / EdgeConv block for inference
  *          pointnet_util.py:137-147, 203-217, 258-279; pointnet2_utils.py:140-154, 341-356;
  *          DGCNN.py:72-109, 134-148

@@ -36,6 +36,7 @@ _SIGNATURES = {
     "pcb_fp_concat_bf16": [_vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp],
     "pcb_fp_concat_bwd_bf16": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp],
     "pcb_wgrad_rows_bf16": [_vp, _vp, _i64, _i, _i, _i, _i, _vp, _i, _vp],
+    "pcb_adam_flat_f32": [_vp, _vp, _vp, _vp, _i64, _vp, _f, _f, _f, _f, _vp, _vp, _vp, _vp],
     "pcb_knn_f32": [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp],
     "pcb_knn_cdist_f32": [_vp, _i, _i, _i, _vp, _vp, _vp],
     "pcb_graph_feature_f32": [_vp, _vp, _i, _i, _i, _i, _vp, _vp],

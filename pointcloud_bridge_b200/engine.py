@@ -62,6 +62,50 @@ def _nll_mean(logp, labels):
     return -logp.gather(1, labels.view(-1, 1)).mean()
 
 
+class FlatAdam:
+    """torch.optim.Adam (L2 weight decay, bias-corrected) over ONE flat fp32 parameter buffer whose gradient is
+    the flat gradient bucket: a single kernel per step (csrc/adam.cu) that also rewrites the bf16 weight
+    shadows of the next step's GEMMs.  Step count and learning rate are device scalars, so the kernel can
+    sit inside a captured CUDA graph and still follow `set_lr` (ReduceLROnPlateau in the reference's
+    runner, train_MulSca_BriStruNet_CB.py:181)."""
+
+    def __init__(self, flat_param, flat_grad, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0,
+                 shadow_index=None, shadow_flat=None):
+        self.p, self.g = flat_param, flat_grad
+        self.exp_avg = torch.zeros_like(flat_param)
+        self.exp_avg_sq = torch.zeros_like(flat_param)
+        self.step_t = torch.zeros(1, dtype=torch.long, device=flat_param.device)
+        self.lr_t = torch.full((1,), float(lr), dtype=torch.float32, device=flat_param.device)
+        self.betas, self.eps, self.weight_decay = betas, eps, weight_decay
+        self.shadow_index, self.shadow_flat = shadow_index, shadow_flat
+
+    def set_lr(self, lr: float) -> None:
+        self.lr_t.fill_(float(lr))
+
+    @torch.no_grad()
+    def step(self, increment: bool = True) -> None:
+        """increment=False: the caller already advanced `step_t` (Trainer batches it with the BN counters)."""
+        if increment:
+            self.step_t.add_(1)
+        ops._call("pcb_adam_flat_f32", self.p.device, self.p.data_ptr(), self.g.data_ptr(), self.exp_avg.data_ptr(),
+                  self.exp_avg_sq.data_ptr(), self.p.numel(), self.lr_t.data_ptr(), float(self.betas[0]),
+                  float(self.betas[1]), float(self.eps), float(self.weight_decay), self.step_t.data_ptr(),
+                  self.shadow_index.data_ptr() if self.shadow_index is not None else None,
+                  self.shadow_flat.data_ptr() if self.shadow_index is not None else None,
+                  alg_bytes=self.p.numel() * 32)
+
+    def state_dict(self):
+        return {"step": self.step_t.clone(), "exp_avg": self.exp_avg.clone(), "exp_avg_sq": self.exp_avg_sq.clone(),
+                "lr": float(self.lr_t.item()), "betas": self.betas, "eps": self.eps, "weight_decay": self.weight_decay}
+
+    def load_state_dict(self, sd):
+        self.step_t.copy_(sd["step"])
+        self.exp_avg.copy_(sd["exp_avg"])
+        self.exp_avg_sq.copy_(sd["exp_avg_sq"])
+        self.set_lr(sd["lr"])
+        self.betas, self.eps, self.weight_decay = tuple(sd["betas"]), sd["eps"], sd["weight_decay"]
+
+
 class Trainer:
     """forward -> loss -> backward -> one flat NCCL all-reduce -> fused Adam.
 
@@ -88,21 +132,33 @@ class Trainer:
                 view.copy_(p.data)
                 p.data = view
                 off += n
-        self.flat_param.grad = self.bucket.flat
-        self.opt = torch.optim.Adam([self.flat_param], lr=lr, weight_decay=weight_decay, fused=True,
-                                    capturable=graph if capturable is None else capturable)
+        offsets, off = {}, 0
+        for p in self.bucket.params:
+            offsets[id(p)] = off
+            off += p.numel()
         self._ctx = ops.StepContext(net, bf16=amp,
-                                    grad_views={id(p): v for p, v in zip(self.bucket.params, self.bucket.views)})
+                                    grad_views={id(p): v for p, v in zip(self.bucket.params, self.bucket.views)},
+                                    flat_offsets=offsets, flat_numel=off)
+        self._ctx.refresh_shadows()
+        self._ctx.external_refresh = True          # from here on the Adam kernel keeps the bf16 shadows current
+        self.opt = FlatAdam(self.flat_param.detach(), self.bucket.flat, lr=lr, weight_decay=weight_decay,
+                            shadow_index=self._ctx.shadow_index, shadow_flat=self._ctx.shadow_flat)
         self._g = None                 # captured (zero, forward, loss, backward[, Adam]) graph
         self._static = None
         self._starts = FpsStartBuffers()
         self._warm = 0
         self._opt_in_graph = False
 
+    def refresh(self) -> None:
+        """Call after changing parameters from outside (net.load_state_dict, manual edits): re-derives the
+        bf16 weight shadows that the optimizer kernel otherwise keeps current."""
+        self._ctx.refresh_shadows()
+
     # -- eager pieces ---------------------------------------------------------------------
     def _fwd_bwd(self, inputs, labels, loss_inputs):
         self.bucket.zero()
         with self._ctx:
+            self._ctx.counters.append(self.opt.step_t)      # advanced with the BN counters in one multi-tensor add
             with torch.autocast("cuda", dtype=torch.bfloat16, enabled=self.amp):
                 out = self.net(*inputs)
             logits = out[0] if isinstance(out, tuple) else out
@@ -121,7 +177,7 @@ class Trainer:
         self.bucket.pack()
         if self._multi():
             self.bucket.allreduce_mean()
-        self.opt.step()
+        self.opt.step(increment=False)
         return loss
 
     # -- CUDA-graph path --------------------------------------------------------------------
@@ -141,13 +197,13 @@ class Trainer:
                 loss = self._fwd_bwd(self._static[0], self._static[1], self._static[2])
                 self.bucket.pack()
                 if self._opt_in_graph:
-                    self.opt.step()
+                    self.opt.step(increment=False)
             self._static_loss = loss
             self.kernel_launches_per_replay = _lib.launches() - n0   # libpcbridge kernels inside the graph
             if not self._opt_in_graph:                               # second graph: the optimizer alone
                 self._g_opt = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(self._g_opt, pool=self._g.pool()):
-                    self.opt.step()
+                    self.opt.step(increment=False)
         finally:
             self._starts.mode = "off"
             ops.set_fps_start_provider(None)

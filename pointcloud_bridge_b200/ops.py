@@ -634,36 +634,61 @@ class StepContext:
     weights are ONE multi-tensor copy on entry into persistent shadows that `linear_rows` picks up
     (autocast would cast each weight on use, forward and again backward)."""
 
-    def __init__(self, module: torch.nn.Module, bf16: bool, grad_views: dict | None = None):
+    def __init__(self, module: torch.nn.Module, bf16: bool, grad_views: dict | None = None,
+                 flat_offsets: dict | None = None, flat_numel: int = 0):
         self.counters = []
         # id(parameter) -> fp32 view of the runner's flat gradient buffer (zeroed at the start of every
         # step): the weight-gradient kernel accumulates straight into it, the parameter's .grad stays None
         self.grad_views = grad_views or {}
+        p0 = next(module.parameters(), None)
         params = [p for p in module.parameters() if p.dim() >= 2] if bf16 else []
-        # shadows are [N, K rounded up to 8] with zero pad columns (written once, here): the padded
-        # ones match the zero-padded rows of group_points(pad_to=8)
+        # shadows are [n rounded up to 8, k rounded up to 8], zero padded (written once, here), all carved out
+        # of ONE bf16 buffer: pad columns match the zero-padded rows of group_points(pad_to=8), pad rows make
+        # the OUTPUT rows 16-byte aligned (196 -> 200 channels) when linear_rows(pad_n=True)
+        shapes = [(p.shape[0], p[0].numel()) for p in params]
+        sizes = [(-(-n // 8) * 8) * (-(-k // 8) * 8) for n, k in shapes]
+        total = sum(sizes)
+        self.shadow_flat = torch.zeros(max(total, 1), dtype=torch.bfloat16, device=p0.device) if params else None
         self.dense, self.dense_shadows, self.ragged = [], [], []
         self.by_id = {}
-        for p in params:
-            n, k = p.shape[0], p[0].numel()
-            # [n rounded up to 8, k rounded up to 8], zero padded: pad columns match zero-padded input rows,
-            # pad rows make the OUTPUT rows 16-byte aligned (196 -> 200 channels) when linear_rows(pad_n=True)
-            sh = torch.zeros(-(-n // 8) * 8, -(-k // 8) * 8, dtype=torch.bfloat16, device=p.device)
+        # element i of the runner's flat parameter buffer -> element of shadow_flat (or -1): lets the fused
+        # Adam kernel (csrc/adam.cu) refresh the shadows while it writes the updated parameters
+        self.shadow_index = None
+        index = None
+        if params and flat_offsets is not None:
+            import numpy as np
+            index = np.full(flat_numel, -1, dtype=np.int32)
+        off = 0
+        for p, (n, k), size in zip(params, shapes, sizes):
+            k8 = -(-k // 8) * 8
+            sh = self.shadow_flat[off:off + size].view(-1, k8)
             self.by_id[id(p)] = sh
-            if sh.shape[1] == k:
+            if k8 == k:
                 self.dense.append(p)
                 self.dense_shadows.append(sh[:n])
             else:
                 self.ragged.append((p, sh[:n, :k]))
+            if index is not None and id(p) in flat_offsets:
+                j = np.arange(n * k, dtype=np.int64)
+                index[flat_offsets[id(p)]:flat_offsets[id(p)] + n * k] = (off + (j // k) * k8 + (j % k)).astype(np.int32)
+            off += size
+        if index is not None:
+            self.shadow_index = torch.from_numpy(index).to(p0.device)
+        self.external_refresh = False      # True: the optimizer kernel keeps the shadows current (engine.Trainer)
 
-    def __enter__(self):
-        global _step_ctx
-        self.counters = []
+    def refresh_shadows(self):
+        """fp32 parameters -> bf16 shadows (one multi-tensor copy + one copy per ragged weight)."""
         with torch.no_grad():
             if self.dense:
                 torch._foreach_copy_(self.dense_shadows, [p.detach().flatten(1) for p in self.dense])
             for p, view in self.ragged:
                 view.copy_(p.detach().flatten(1))
+
+    def __enter__(self):
+        global _step_ctx
+        self.counters = []
+        if not self.external_refresh:
+            self.refresh_shadows()
         _step_ctx = self
         return self
 

@@ -137,3 +137,35 @@ def test_linear_rows_padded_output_channels():
     for a, b in zip(gp, gr):
         assert a.shape == b.shape
         assert ((a.float() - b.float()).norm() / b.float().norm()).item() <= 2e-2
+
+
+def test_flat_adam_matches_torch_adam_and_refreshes_shadows():
+    """engine.FlatAdam (csrc/adam.cu) against torch.optim.Adam over 5 steps with weight decay, and the bf16
+    shadow of a [12, 10] weight inside the flat buffer (zero-padded to [16, 16]) after every step."""
+    from pointcloud_bridge_b200.engine import FlatAdam
+    torch.manual_seed(0)
+    n = 100_003
+    p0 = torch.randn(n, device=DEV)
+    ref = p0.clone().requires_grad_(True)
+    opt_ref = torch.optim.Adam([ref], lr=1e-2, weight_decay=1e-2)
+    p, g = p0.clone(), torch.zeros(n, device=DEV)
+    off, rows, k, k8 = 777, 12, 10, 16
+    index = torch.full((n,), -1, dtype=torch.int32, device=DEV)
+    j = torch.arange(rows * k, device=DEV)
+    index[off:off + rows * k] = ((j // k) * k8 + (j % k)).int()
+    shadow = torch.zeros(16 * k8, dtype=torch.bfloat16, device=DEV)
+    opt = FlatAdam(p, g, lr=1e-2, weight_decay=1e-2, shadow_index=index, shadow_flat=shadow)
+    for it in range(5):
+        grad = torch.randn(n, device=DEV) * (1 + it)
+        g.copy_(grad)
+        ref.grad = grad.clone()
+        if it == 3:
+            opt.set_lr(3e-3)
+            opt_ref.param_groups[0]["lr"] = 3e-3
+        opt.step()
+        opt_ref.step()
+        torch.testing.assert_close(p, ref.detach(), rtol=2e-5, atol=2e-6)
+        sh = shadow.view(16, k8)
+        assert torch.equal(sh[:rows, :k], p[off:off + rows * k].view(rows, k).to(torch.bfloat16))
+        assert not sh[rows:].any() and not sh[:, k:].any()
+    assert int(opt.step_t) == 5
