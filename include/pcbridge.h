@@ -57,6 +57,11 @@ int pcb_square_distance_f32(const float *src, const float *dst, int B, int N, in
  * ascending order, padded with the first one; empty ball -> N. */
 int pcb_ball_query_f32(const float *xyz, const float *new_xyz, int B, int N, int S,
                        float radius2, int nsample, int64_t *out_idx, pcb_stream_t stream);
+/* the same for `nscales` (<= 4) radii around the same centroids in one scan (multi-scale grouping,
+ * pointnet_util.py:241-284; pointnet2_utils.py:326-360): radius2 / nsample / out_idx are HOST arrays of
+ * length nscales, out_idx[k] a device pointer to [B,S,nsample[k]].  Results equal nscales separate calls. */
+int pcb_ball_query_multi_f32(const float *xyz, const float *new_xyz, int B, int N, int S, int nscales,
+                             const float *radius2, const int *nsample, int64_t *const *out_idx, pcb_stream_t stream);
 
 /* ---- a4  index_points                     pointnet_util.py:46-63 (errors on idx >= N)
  *                                           pointnet2_utils.py:17-39 (clamps to [0,N-1])

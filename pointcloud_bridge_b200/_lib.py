@@ -24,6 +24,7 @@ _SIGNATURES = {
     "pcb_fps_f32": [_vp, _i, _i, _vp, _i, _vp, _vp],
     "pcb_square_distance_f32": [_vp, _vp, _i, _i, _i, _i, _vp, _vp],
     "pcb_ball_query_f32": [_vp, _vp, _i, _i, _i, _f, _i, _vp, _vp],
+    "pcb_ball_query_multi_f32": [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp],
     "pcb_gather_f32": [_vp, _vp, _i, _i, _i, _i64, _i, _vp, _vp, _vp],
     "pcb_gather_bwd_f32": [_vp, _vp, _i, _i, _i, _i64, _i, _vp, _vp],
     "pcb_group_points_f32": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp],

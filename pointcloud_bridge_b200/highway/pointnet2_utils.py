@@ -148,8 +148,10 @@ class MultiScaleSetAbstraction(nn.Module):
         S = self.npoint
         new_xyz = index_points(xyz, farthest_point_sample(xyz, S))
         outs = []
+        # every radius in one scan of the cloud (the reference calls query_ball_point once per radius)
+        idxs = ops.ball_query_multi(self.radius_list, self.nsample_list, xyz, new_xyz)
         for i, (radius, K) in enumerate(zip(self.radius_list, self.nsample_list)):
-            idx = query_ball_point(radius, K, xyz, new_xyz)
+            idx = idxs[i]
             if ops.fused_inference_enabled() and not self.bn_blocks[i][0].training and K <= 128:
                 pk = ops.packed_mlp(self, i, self.conv_blocks[i], self.bn_blocks[i],
                                     3 + (pts.shape[2] if pts is not None else 0))

@@ -14,7 +14,7 @@ import torch
 from . import _lib
 
 __all__ = [
-    "furthest_point_sample", "ball_query", "square_distance", "gather", "group_points",
+    "furthest_point_sample", "ball_query", "ball_query_multi", "square_distance", "gather", "group_points",
     "three_nn", "three_interpolate", "knn", "knn_cdist", "graph_feature", "check_index_errors",
 ]
 
@@ -161,6 +161,28 @@ def ball_query(radius: float, nsample: int, xyz: torch.Tensor, new_xyz: torch.Te
     _call("pcb_ball_query_f32", xyz.device, xyz.data_ptr(), new_xyz.data_ptr(), B, N, S, r2, int(nsample),
           out.data_ptr(), alg_bytes=B * (12 * N + 12 * S + 8 * S * nsample))
     return out
+
+
+@torch.no_grad()
+def ball_query_multi(radii, nsamples, xyz: torch.Tensor, new_xyz: torch.Tensor) -> list:
+    """query_ball_point for several (radius, nsample) pairs around the same centroids in one scan of the
+    cloud; returns one LongTensor [B,S,nsample_k] per pair, equal to separate ball_query calls."""
+    import ctypes
+    radii, nsamples = list(radii), [int(n) for n in nsamples]
+    if len(radii) == 1 or len(radii) > 4:
+        return [ball_query(r, n, xyz, new_xyz) for r, n in zip(radii, nsamples)]
+    xyz = _f32(xyz, "xyz")
+    new_xyz = _f32(new_xyz, "new_xyz")
+    B, N, _ = xyz.shape
+    S = new_xyz.shape[1]
+    k = len(radii)
+    r2 = (ctypes.c_float * k)(*[float(torch.tensor(float(r) ** 2, dtype=torch.float32).item()) for r in radii])
+    ns = (ctypes.c_int * k)(*nsamples)
+    outs = [torch.empty(B, S, n, dtype=torch.long, device=xyz.device) for n in nsamples]
+    ptrs = (ctypes.c_void_p * k)(*[o.data_ptr() for o in outs])
+    _call("pcb_ball_query_multi_f32", xyz.device, xyz.data_ptr(), new_xyz.data_ptr(), B, N, S, k, r2, ns, ptrs,
+          alg_bytes=B * (12 * N + 12 * S + 8 * S * sum(nsamples)))
+    return outs
 
 
 @torch.no_grad()

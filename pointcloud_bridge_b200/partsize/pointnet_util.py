@@ -219,9 +219,11 @@ class PointNetSetAbstractionMsg(nn.Module):
         S = self.npoint
         new_xyz = index_points(xyz_r, farthest_point_sample(xyz_r, S))
         outs = []
+        # every radius in one scan of the cloud (the reference calls query_ball_point once per radius, :250)
+        idxs = ops.ball_query_multi(self.radius_list, self.nsample_list, xyz_r, new_xyz)
         for i, radius in enumerate(self.radius_list):
             K = self.nsample_list[i]
-            idx = query_ball_point(radius, K, xyz_r, new_xyz)
+            idx = idxs[i]
             if ops.fused_inference_enabled() and not self.bn_blocks[i][0].training and K <= 128:
                 pk = ops.packed_mlp(self, i, self.conv_blocks[i], self.bn_blocks[i],
                                     3 + (pts_r.shape[2] if pts_r is not None else 0))

@@ -361,3 +361,16 @@ def test_group_points_takes_bf16_feature_rows(D):
     (gb,) = torch.autograd.grad(p32[bi, idx], p32, g[..., :D].float())
     assert ga.dtype == torch.bfloat16
     torch.testing.assert_close(ga.float(), gb, rtol=1e-2, atol=1e-2)
+
+
+@pytest.mark.parametrize("N,S", [(4096, 1024), (1024, 256), (5000, 300), (8200, 64), (33, 7)])
+def test_ball_query_multi_equals_separate_queries(N, S):
+    """The one-scan multi-radius kernel returns exactly what one ball_query per radius returns (which is
+    checked against the oracle and the reference's golden vectors above), incl. empty and overfull balls."""
+    xyz_np = synthetic.bridge_batch(5, 3, N)[0]
+    xyz = cu(xyz_np)
+    new = cu(xyz_np[:, ::max(1, N // S)][:, :S] + np.float32(0.001))
+    for radii, ns in (((0.05, 0.1), (16, 32)), ((0.2, 0.4, 0.01), (16, 32, 8)), ((0.1, 0.2, 0.4, 0.8), (64, 32, 16, 8))):
+        multi = ops.ball_query_multi(radii, ns, xyz, new)
+        for r, n, m in zip(radii, ns, multi):
+            assert torch.equal(m, ops.ball_query(r, n, xyz, new)), (r, n)
