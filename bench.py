@@ -158,17 +158,19 @@ def run_reference(a):
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
-KERNEL_OF = {                                         # C-ABI entry point -> device kernel it launches
-    "pcb_fps_f32": "fps_reg_kernel", "pcb_ball_query_f32": "ball_query_kernel",
-    "pcb_group_points_f32": "group_points_kernel", "pcb_group_points_bwd_f32": "group_points_bwd_kernel",
+KERNEL_OF = {                                         # C-ABI entry point -> device kernel it launches in this workload
+    "pcb_fps_f32": "fps_pair_kernel", "pcb_ball_query_f32": "ball_query_kernel",
+    "pcb_ball_query_multi_f32": "ball_query_multi_kernel",
+    "pcb_group_points_f32": "group_tile_kernel", "pcb_group_points_bwd_f32": "group_points_bwd_vec_kernel",
     "pcb_gather_f32": "gather_kernel", "pcb_gather_bwd_f32": "gather_bwd_kernel",
     "pcb_three_nn_f32": "three_nn_kernel", "pcb_interpolate_f32": "interp_rows_kernel",
     "pcb_interpolate_bwd_f32": "interp_bwd_kernel", "pcb_knn_f32": "knn_kernel",
-    "pcb_knn_cdist_f32": "knn_xyz_kernel", "pcb_graph_feature_f32": "graph_feature_kernel",
-    "pcb_graph_feature_bwd_f32": "graph_feature_bwd_kernel", "pcb_group_points_bf16": "group_points_kernel",
-    "pcb_group_points_bwd_bf16": "group_points_bwd_kernel", "pcb_bn_fwd_rows": "bn_fwd_fused_kernel",
-    "pcb_bn_bwd_rows": "bn_bwd_fused_kernel",
-    "pcb_sa_fused_bf16": "sa_fused_kernel"}
+    "pcb_knn_cdist_f32": "knn_xyz_kernel", "pcb_graph_feature_f32": "graph_feature_smem_kernel",
+    "pcb_graph_feature_bwd_f32": "graph_feature_bwd_kernel", "pcb_group_points_bf16": "group_tile_kernel",
+    "pcb_group_points_bwd_bf16": "group_points_bwd_vec_kernel", "pcb_bn_fwd_rows": "bn_fwd_fused_kernel",
+    "pcb_bn_bwd_rows": "bn_bwd_fused_kernel", "pcb_fp_concat_bf16": "fp_concat_chunk_kernel",
+    "pcb_fp_concat_bwd_bf16": "fp_concat_bwd_vec_kernel", "pcb_wgrad_rows_bf16": "wgrad_rows_kernel",
+    "pcb_adam_flat_f32": "adam_flat_kernel", "pcb_sa_fused_bf16": "sa_fused_kernel"}
 
 
 def run_ours(a):
@@ -253,8 +255,8 @@ def run_ours(a):
     barrier()
     e2e_s = pdist.max_over_ranks(time.perf_counter() - t0, dev)
     e2e = {"value": world * B * NPTS * a.steps / e2e_s, "unit": UNIT,
-           "h2d_bytes_per_step": int(host[0][0].numel() * 4 + host[0][1].numel() * 8),
-           "d2h_bytes_per_step": 4, "ms_per_step": e2e_s / a.steps * 1e3}
+           "h2d_bytes_per_step": world * int(host[0][0].numel() * 4 + host[0][1].numel() * 8),    # all ranks
+           "d2h_bytes_per_step": world * 4, "ms_per_step": e2e_s / a.steps * 1e3}
 
     # ---- instrumented pass: per-launch CUDA events around every kernel of ours ----
     sink = []

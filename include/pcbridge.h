@@ -186,6 +186,35 @@ int pcb_bn_bwd_rows(const void *gz, const void *y, const unsigned char *argmax, 
 int pcb_wgrad_rows_bf16(const void *gy, const void *x, int64_t M, int N, int K, int ldgy, int ldx, float *gw,
                         int ldw, pcb_stream_t stream);
 
+/* ---- section 8f rank 2: whole-scene tiling and vote scatter-back
+ *          ScannetDatasetWholeScene.__getitem__  Highway_bridge/utils/BridgeDataLoader.py:214-277
+ *          add_vote / argmax                     Partsize-identical/test_sem_seg.py:58-65, 162
+ * points [P, point_stride] fp32 rows (x, y, z, r, g, b, ...).  Windows: index (iy, ix), closed membership
+ * intervals lo_x/hi_x [grid_x], lo_y/hi_y [grid_y] (device arrays of doubles, padding included, computed by
+ * the host in float64 as the reference does); x0, y0, stride locate the candidate windows of a point and
+ * `reach` = ceil(block_size / stride) + 1 bounds how far below floor((x - x0) / stride) they can start.
+ *   count : counts[iy*grid_x + ix] += 1 per member point (counts zeroed by the caller)
+ *   fill  : members[offsets[w] + k] = point index, k handed out through cursor[w] (zeroed); offsets = exclusive
+ *           prefix sum of counts
+ *   blocks: block b takes entries (blk_first[b] + j) mod blk_cnt[b], j < block_points, of the member segment at
+ *           blk_off[b] (cyclic padding) -> data [nblocks, block_points, 9] = (x - cx, y - cy, z, r, g, b,
+ *           x/ext_x, y/ext_y, z/ext_z) computed in double and rounded to fp32, point_idx [nblocks, block_points]
+ *   vote  : pool[point_idx[t] * num_classes + pred[t]] += 1;  vote_argmax: first maximum per point */
+int pcb_scene_window_count_f32(const float *points, int64_t P, int point_stride, int grid_x, int grid_y,
+                               const double *lo_x, const double *hi_x, const double *lo_y, const double *hi_y, double x0,
+                               double y0, double stride, int reach, int *counts, pcb_stream_t stream);
+int pcb_scene_window_fill_f32(const float *points, int64_t P, int point_stride, int grid_x, int grid_y,
+                              const double *lo_x, const double *hi_x, const double *lo_y, const double *hi_y, double x0,
+                              double y0, double stride, int reach, const int64_t *offsets, int *cursor, int *members,
+                              pcb_stream_t stream);
+int pcb_scene_blocks_f32(const float *points, int point_stride, const int *members, const int64_t *blk_off,
+                         const int *blk_cnt, const int64_t *blk_first, const double *blk_center, int64_t nblocks,
+                         int block_points, double ext_x, double ext_y, double ext_z, float *data, int64_t *point_idx,
+                         pcb_stream_t stream);
+int pcb_scene_vote(const int64_t *point_idx, const unsigned char *pred, int64_t total, int64_t P, int num_classes,
+                   int *pool, pcb_stream_t stream);
+int pcb_scene_vote_argmax(const int *pool, int64_t P, int num_classes, unsigned char *labels, pcb_stream_t stream);
+
 /* ---- section 8f rank 4 (training runner): Adam over one flat fp32 parameter buffer
  *          Highway_bridge/train_MulSca_BriStruNet_CB.py:158-190 (torch.optim.Adam, L2 weight decay)
  * p, g, m, v [n] fp32; `lr` [1] fp32 and `step` [1] int64 (already incremented, >= 1) are DEVICE scalars so a

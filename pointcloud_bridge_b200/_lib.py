@@ -18,6 +18,7 @@ _vp = ctypes.c_void_p
 _i = ctypes.c_int
 _i64 = ctypes.c_int64
 _f = ctypes.c_float
+_d = ctypes.c_double
 
 # name -> argtypes (all return int)
 _SIGNATURES = {
@@ -38,6 +39,11 @@ _SIGNATURES = {
     "pcb_fp_concat_bwd_bf16": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp],
     "pcb_wgrad_rows_bf16": [_vp, _vp, _i64, _i, _i, _i, _i, _vp, _i, _vp],
     "pcb_adam_flat_f32": [_vp, _vp, _vp, _vp, _i64, _vp, _f, _f, _f, _f, _vp, _vp, _vp, _vp],
+    "pcb_scene_window_count_f32": [_vp, _i64, _i, _i, _i, _vp, _vp, _vp, _vp, _d, _d, _d, _i, _vp, _vp],
+    "pcb_scene_window_fill_f32": [_vp, _i64, _i, _i, _i, _vp, _vp, _vp, _vp, _d, _d, _d, _i, _vp, _vp, _vp, _vp],
+    "pcb_scene_blocks_f32": [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i64, _i, _d, _d, _d, _vp, _vp, _vp],
+    "pcb_scene_vote": [_vp, _vp, _i64, _i64, _i, _vp, _vp],
+    "pcb_scene_vote_argmax": [_vp, _i64, _i, _vp, _vp],
     "pcb_knn_f32": [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp],
     "pcb_knn_cdist_f32": [_vp, _i, _i, _i, _vp, _vp, _vp],
     "pcb_graph_feature_f32": [_vp, _vp, _i, _i, _i, _i, _vp, _vp],
