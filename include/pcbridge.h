@@ -215,6 +215,20 @@ int pcb_scene_vote(const int64_t *point_idx, const unsigned char *pred, int64_t 
                    int *pool, pcb_stream_t stream);
 int pcb_scene_vote_argmax(const int *pool, int64_t P, int num_classes, unsigned char *labels, pcb_stream_t stream);
 
+/* ---- section 8f rank 4 (training runner): mean NLL of the segmentation head on logits rows
+ *          pointnet2_sem_seg.py:46-47, 56 (F.log_softmax + F.nll_loss, mean, no class weights)
+ * logits [M, pitch] fp32 (dtype 0) or bf16 (1), `classes` (<= 32) real columns, `bias` [classes] fp32 added to them
+ * (NULL: none -- the classifier GEMM runs bias-free); labels [M] int64.
+ * fwd: partial[b] (b < pcb_nll_rows_blocks(M)) = sum of (logsumexp(x) - x[label]) over the rows of CTA b;
+ *      loss = sum(partial) / M (reduced by the caller in a fixed order).
+ * bwd: grad_logits[r, c] = (softmax(x[r])[c] - [c == label]) * grad_loss[0] / M, pad columns 0;
+ *      grad_bias[c] += column sums of grad_logits (may be NULL). */
+int pcb_nll_rows_blocks(int64_t M);
+int pcb_nll_rows_fwd(const void *logits, int dtype, const float *bias, const int64_t *labels, int64_t M, int classes,
+                     int pitch, float *partial, pcb_stream_t stream);
+int pcb_nll_rows_bwd(const void *logits, int dtype, const float *bias, const int64_t *labels, int64_t M, int classes,
+                     int pitch, const float *grad_loss, void *grad_logits, float *grad_bias, pcb_stream_t stream);
+
 /* ---- section 8f rank 4 (training runner): Adam over one flat fp32 parameter buffer
  *          Highway_bridge/train_MulSca_BriStruNet_CB.py:158-190 (torch.optim.Adam, L2 weight decay)
  * p, g, m, v [n] fp32; `lr` [1] fp32 and `step` [1] int64 (already incremented, >= 1) are DEVICE scalars so a

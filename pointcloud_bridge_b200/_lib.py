@@ -44,6 +44,8 @@ _SIGNATURES = {
     "pcb_scene_blocks_f32": [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i64, _i, _d, _d, _d, _vp, _vp, _vp],
     "pcb_scene_vote": [_vp, _vp, _i64, _i64, _i, _vp, _vp],
     "pcb_scene_vote_argmax": [_vp, _i64, _i, _vp, _vp],
+    "pcb_nll_rows_fwd": [_vp, _i, _vp, _vp, _i64, _i, _i, _vp, _vp],
+    "pcb_nll_rows_bwd": [_vp, _i, _vp, _vp, _i64, _i, _i, _vp, _vp, _vp, _vp],
     "pcb_knn_f32": [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp],
     "pcb_knn_cdist_f32": [_vp, _i, _i, _i, _vp, _vp, _vp],
     "pcb_graph_feature_f32": [_vp, _vp, _i, _i, _i, _i, _vp, _vp],
@@ -53,7 +55,7 @@ _SIGNATURES = {
     "pcb_bn_bwd_rows": [_vp, _vp, _vp, _i, _i64, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp],
 }
 
-EXPORTS = ["pcb_version", "pcb_error_string", "pcb_bn_work_floats", *_SIGNATURES]
+EXPORTS = ["pcb_version", "pcb_error_string", "pcb_bn_work_floats", "pcb_nll_rows_blocks", *_SIGNATURES]
 
 
 class PcbError(RuntimeError):
@@ -75,6 +77,8 @@ def lib():
         l.pcb_error_string.argtypes = [_i]
         l.pcb_bn_work_floats.restype = _i64
         l.pcb_bn_work_floats.argtypes = [_i]
+        l.pcb_nll_rows_blocks.restype = _i
+        l.pcb_nll_rows_blocks.argtypes = [_i64]
         for name, args in _SIGNATURES.items():
             fn = getattr(l, name)
             fn.restype = _i

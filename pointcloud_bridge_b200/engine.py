@@ -159,10 +159,16 @@ class Trainer:
         self.bucket.zero()
         with self._ctx:
             self._ctx.counters.append(self.opt.step_t)      # advanced with the BN counters in one multi-tensor add
-            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=self.amp):
-                out = self.net(*inputs)
+            if self.loss_fn is None:       # plain mean NLL: the heads hand their logits rows to the loss kernel
+                with ops.head_logits_mode(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=self.amp):
+                    out = self.net(*inputs)
+            else:
+                with torch.autocast("cuda", dtype=torch.bfloat16, enabled=self.amp):
+                    out = self.net(*inputs)
             logits = out[0] if isinstance(out, tuple) else out
-            if self.loss_fn is None:       # sem-seg nets return log-probabilities [B,N,C]
+            if isinstance(logits, ops.LogitRows):
+                loss = ops.nll_logit_rows(logits, labels)
+            elif self.loss_fn is None:     # sem-seg nets return log-probabilities [B,N,C]
                 loss = _nll_mean(logits.float().reshape(-1, logits.shape[-1]), labels.reshape(-1))
             else:
                 loss = self.loss_fn(logits.float(), labels, *loss_inputs)

@@ -554,6 +554,78 @@ def bn_rows_supported(y, bn, pool_k=1) -> bool:
 
 
 # ---------------------------------------------------------------------------------------------
+# mean NLL of the segmentation head straight from the classifier's logits rows
+# ---------------------------------------------------------------------------------------------
+class LogitRows:
+    """What a segmentation head hands back instead of log-probabilities while `head_logits_mode` is on: the
+    bias-free classifier rows [M, pitch] (zero pad columns), the classifier bias and the real class count."""
+
+    def __init__(self, rows, bias, classes, B, N):
+        self.rows, self.bias, self.classes, self.B, self.N = rows, bias, classes, B, N
+
+    def log_probs(self):
+        x = self.rows[:, :self.classes].float()
+        if self.bias is not None:
+            x = x + self.bias
+        return torch.log_softmax(x, dim=-1).view(self.B, self.N, -1)
+
+
+_head_logits = False
+
+
+class head_logits_mode:
+    """Context in which the drop-in segmentation heads return `LogitRows` (training runner: the loss kernel
+    consumes the logits directly; log_softmax, the slice copy and ATen's NLL kernels disappear)."""
+
+    def __enter__(self):
+        global _head_logits
+        self._prev, _head_logits = _head_logits, True
+
+    def __exit__(self, *exc):
+        global _head_logits
+        _head_logits = self._prev
+        return False
+
+
+def head_logits_enabled() -> bool:
+    return _head_logits
+
+
+class _NllRows(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, rows, bias, labels, classes):
+        rows = rows if rows.is_contiguous() else rows.contiguous()
+        labels = _i64(labels.reshape(-1), "labels")
+        M, pitch = rows.shape
+        dt = _act_dtype(rows)
+        b32 = bias.float().contiguous() if bias is not None else None
+        nblk = _lib.lib().pcb_nll_rows_blocks(M)
+        partial = torch.empty(nblk, dtype=torch.float32, device=rows.device)
+        _call("pcb_nll_rows_fwd", rows.device, rows.data_ptr(), dt, b32.data_ptr() if b32 is not None else None,
+              labels.data_ptr(), M, int(classes), pitch, partial.data_ptr(), alg_bytes=rows.numel() * rows.element_size() + 8 * M)
+        ctx.save_for_backward(rows, b32, labels)
+        ctx.meta = (M, pitch, dt, int(classes))
+        return partial.sum() * (1.0 / M)
+
+    @staticmethod
+    def backward(ctx, g):
+        rows, b32, labels = ctx.saved_tensors
+        M, pitch, dt, classes = ctx.meta
+        g = g.reshape(1).float().contiguous()
+        dx = torch.empty_like(rows)
+        gb = torch.zeros(classes, dtype=torch.float32, device=rows.device) if b32 is not None else None
+        _call("pcb_nll_rows_bwd", rows.device, rows.data_ptr(), dt, b32.data_ptr() if b32 is not None else None,
+              labels.data_ptr(), M, classes, pitch, g.data_ptr(), dx.data_ptr(), gb.data_ptr() if gb is not None else None,
+              alg_bytes=2 * rows.numel() * rows.element_size() + 8 * M)
+        return dx, gb, None, None
+
+
+def nll_logit_rows(lr: "LogitRows", labels: torch.Tensor) -> torch.Tensor:
+    """mean_r( -log_softmax(rows[r, :classes] + bias)[labels[r]] ) -- F.nll_loss(F.log_softmax(logits), labels)."""
+    return _NllRows.apply(lr.rows, lr.bias, labels, lr.classes)
+
+
+# ---------------------------------------------------------------------------------------------
 # fused set-abstraction / EdgeConv block for inference (tcgen05 tensor cores)
 # ---------------------------------------------------------------------------------------------
 def _ru16(n: int) -> int:

@@ -5,6 +5,7 @@ same parameter names, same [B,9,N] -> ([B,N,num_classes] log-probabilities, l4_p
 import torch.nn as nn
 import torch.nn.functional as F
 
+from .. import ops
 from .pointnet_util import PointNetFeaturePropagation, PointNetSetAbstraction, _rows, conv_bn_relu_rows
 
 
@@ -46,6 +47,10 @@ def _seg_head(net, feats_bcn):
     x = net.drop1(conv_bn_relu_rows(x.reshape(B * N, C), net.conv1, net.bn1))
     w, b = net.conv2.weight.flatten(1), net.conv2.bias
     nc = w.shape[0]
+    if ops.head_logits_enabled() and x.is_cuda and nc <= 32:
+        # training runner: bias-free classifier rows (zero-padded to 8 columns when a bf16 shadow exists) go
+        # straight into the loss kernel, which adds the bias (ops.nll_logit_rows)
+        return ops.LogitRows(ops.linear_rows(x, w, pad_n=True), b, nc, B, N)
     pad = (-nc) % 8 if x.is_cuda else 0
     if pad:                        # [M,5] bf16 rows are not 16-byte aligned: cuBLAS falls back to legacy kernels
         x = F.linear(x, F.pad(w, (0, 0, 0, pad)), F.pad(b, (0, pad)) if b is not None else None)[:, :nc]

@@ -169,3 +169,28 @@ def test_flat_adam_matches_torch_adam_and_refreshes_shadows():
         assert torch.equal(sh[:rows, :k], p[off:off + rows * k].view(rows, k).to(torch.bfloat16))
         assert not sh[rows:].any() and not sh[:, k:].any()
     assert int(opt.step_t) == 5
+
+
+@pytest.mark.parametrize("dtype,pitch", [(torch.bfloat16, 8), (torch.float32, 5), (torch.float32, 16)])
+def test_nll_logit_rows_matches_log_softmax_nll(dtype, pitch):
+    """Loss kernel of the segmentation head (csrc/loss.cu) against F.nll_loss(F.log_softmax(logits + bias))."""
+    import torch.nn.functional as F
+    torch.manual_seed(3)
+    M, nc = 70_001, 5
+    rows = torch.zeros(M, pitch, device=DEV, dtype=dtype)
+    rows[:, :nc] = (torch.randn(M, nc, device=DEV) * 3).to(dtype)
+    bias = torch.randn(nc, device=DEV)
+    labels = torch.randint(0, nc, (M,), device=DEV)
+    ra, ba = rows.clone().requires_grad_(True), bias.clone().requires_grad_(True)
+    rb, bb = rows.clone().requires_grad_(True), bias.clone().requires_grad_(True)
+    la = ops.nll_logit_rows(ops.LogitRows(ra, ba, nc, 1, M), labels)
+    lb = F.nll_loss(F.log_softmax(rb[:, :nc].float() + bb, dim=-1), labels)
+    assert abs(la.item() - lb.item()) <= 2e-6 * abs(lb.item()) + 1e-6
+    (la * 2.5).backward()
+    (lb * 2.5).backward()
+    tol = 1e-6 if dtype == torch.float32 else 1e-2
+    assert (ra.grad[:, :nc].float() - rb.grad[:, :nc].float()).abs().max().item() <= tol * rb.grad.abs().max().item() + 1e-12
+    assert not ra.grad[:, nc:].any()
+    torch.testing.assert_close(ba.grad, bb.grad, rtol=1e-4, atol=1e-7)
+    assert torch.equal(ops.LogitRows(rows, bias, nc, 1, M).log_probs().view(M, nc),
+                       torch.log_softmax(rows[:, :nc].float() + bias, -1))
