@@ -110,5 +110,8 @@ class FlatGradBucket:
     def allreduce_mean(self) -> None:
         if not is_dist() or dist.get_world_size() == 1:
             return
-        dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
-        self.flat.mul_(1.0 / dist.get_world_size())
+        if dist.get_backend() == "nccl":
+            dist.all_reduce(self.flat, op=dist.ReduceOp.AVG)           # the mean in the collective itself
+        else:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
+            self.flat.mul_(1.0 / dist.get_world_size())

@@ -6,6 +6,8 @@ process per GPU.
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.nn.functional as F
 
@@ -191,7 +193,9 @@ class Trainer:
         """Capture one step with static input buffers.  With several ranks the NCCL all-reduce and
         the optimizer stay outside the graph (zero + forward + loss + backward are captured)."""
         self._static = ([t.clone() for t in inputs], labels.clone(), [t.clone() for t in loss_inputs])
-        self._opt_in_graph = not self._multi()
+        # several ranks: the NCCL all-reduce is captured into the same graph (one launch per step) unless
+        # PCB_GRAPH_ALLREDUCE=0, in which case it runs eagerly between two graphs
+        self._opt_in_graph = (not self._multi()) or os.environ.get("PCB_GRAPH_ALLREDUCE", "1") != "0"
         self._starts.allocate()
         ops.set_fps_start_provider(self._starts.provider)
         self._starts.mode = "record"
@@ -203,6 +207,8 @@ class Trainer:
                 loss = self._fwd_bwd(self._static[0], self._static[1], self._static[2])
                 self.bucket.pack()
                 if self._opt_in_graph:
+                    if self._multi():
+                        self.bucket.allreduce_mean()
                     self.opt.step(increment=False)
             self._static_loss = loss
             self.kernel_launches_per_replay = _lib.launches() - n0   # libpcbridge kernels inside the graph
