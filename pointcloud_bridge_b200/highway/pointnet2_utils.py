@@ -14,7 +14,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .. import ops
-from ..partsize.pointnet_util import _bn_rows, _cf_view, _rows, mlp_rows
+from ..partsize.pointnet_util import _bn_rows, _cf_view, _rows, conv_bn_relu_rows, mlp_rows
 
 __all__ = [
     "square_distance", "index_points", "sample_and_group", "farthest_point_sample", "query_ball_point",
@@ -66,17 +66,65 @@ def three_interpolate(points2, idx, dist):
     return ops.three_interpolate(points2, idx, weight, channels_first=True)
 
 
-def seq_rows(seq: nn.Sequential, x):
-    """Evaluate a Sequential of Conv1d(1x1)/BatchNorm1d/activations on point-major rows [M,C]."""
+def _seq_rows_plain(seq: nn.Sequential, x):
+    """Layer-by-layer evaluation with library ops (the pre-fusion form; kept as the comparison path of the tests)."""
     for layer in seq:
         if isinstance(layer, (nn.Conv1d, nn.Conv2d)):
             x = F.linear(x, layer.weight.flatten(1), layer.bias)
         elif isinstance(layer, (nn.BatchNorm1d, nn.BatchNorm2d)):
             x = _bn_rows(layer, x)
+        else:
+            x = layer(x)
+    return x
+
+
+def seq_rows(seq: nn.Sequential, x):
+    """Evaluate a Sequential of Conv1d(1x1)/BatchNorm1d/activations on point-major rows [M,C].
+    In training mode every Conv -> BatchNorm -> ReLU triple runs through the fused row kernels
+    (`conv_bn_relu_rows`: bias-free GEMM, one BN+ReLU kernel, row weight gradient), and inside a step runner
+    the remaining convolutions use its bf16 weight shadows with output rows padded to 8 channels -- the 3-,
+    6- and 9-channel layers of the BriStruNet encoders otherwise send M = 2 M-row GEMMs to cuBLAS's
+    unaligned legacy kernels.  Zero pad columns are carried between layers and dropped at the end."""
+    layers = list(seq)
+    true_c = x.shape[1]
+    i = 0
+    while i < len(layers):
+        layer = layers[i]
+        if isinstance(layer, (nn.Conv1d, nn.Conv2d)):
+            w = layer.weight.flatten(1)
+            nxt = layers[i + 1] if i + 1 < len(layers) else None
+            nxt2 = layers[i + 2] if i + 2 < len(layers) else None
+            if isinstance(nxt, (nn.BatchNorm1d, nn.BatchNorm2d)) and type(nxt2) is nn.ReLU and nxt.training and x.is_cuda:
+                x = conv_bn_relu_rows(x, layer, nxt)
+                true_c = w.shape[0]
+                i += 3
+                continue
+            if ops._step_ctx is not None and x.is_cuda and ops._step_ctx.shadow(w) is not None:
+                y = ops.linear_rows(x, w, pad_n=True)                    # [M, n8], pad columns zero
+                if layer.bias is not None:
+                    y = y + F.pad(layer.bias, (0, y.shape[1] - w.shape[0])).to(y.dtype)
+                x = y
+            else:
+                if x.shape[1] != w.shape[1]:                             # zero pad columns from the previous layer
+                    w = F.pad(w, (0, x.shape[1] - w.shape[1]))
+                x = F.linear(x, w, layer.bias)
+            true_c = layer.weight.shape[0]
+        elif isinstance(layer, (nn.BatchNorm1d, nn.BatchNorm2d)):
+            if x.shape[1] != true_c:
+                x = x[:, :true_c].contiguous()
+            x = _bn_rows(layer, x)
         elif isinstance(layer, nn.Linear):
+            if x.shape[1] != true_c:
+                x = x[:, :true_c]
             x = layer(x)
-        else:                                   # ReLU / LeakyReLU / Sigmoid / Dropout
+            true_c = x.shape[1]
+        else:                                   # ReLU / LeakyReLU / Sigmoid / Dropout: pad columns may become non-zero,
+            if x.shape[1] != true_c and not isinstance(layer, (nn.ReLU, nn.LeakyReLU, nn.Dropout)):
+                x = x[:, :true_c].contiguous()  # drop them first unless the activation maps 0 -> 0
             x = layer(x)
+        i += 1
+    if x.shape[1] != true_c:
+        x = x[:, :true_c].contiguous()
     return x
 
 
