@@ -215,6 +215,12 @@ int pcb_scene_vote(const int64_t *point_idx, const unsigned char *pred, int64_t 
                    int *pool, pcb_stream_t stream);
 int pcb_scene_vote_argmax(const int *pool, int64_t P, int num_classes, unsigned char *labels, pcb_stream_t stream);
 
+/* ---- section 8f rank 3: eigenvalues of batched symmetric 3x3 matrices (BriStruNet structure statistics)
+ *          torch.linalg.eigvalsh(cov), Highway_bridge/models/attention_modules.py:628-640
+ * a [M,3,3] fp32 (lower triangle read), out [M,3] fp32 ascending; float64 closed form, no host synchronisation
+ * (cuSOLVER's batched solver checks `info` on the host, which prevents CUDA-graph capture of the train step). */
+int pcb_eigvalsh3_f32(const float *a, int64_t M, float *out, pcb_stream_t stream);
+
 /* ---- section 8f rank 4 (training runner): mean NLL of the segmentation head on logits rows
  *          pointnet2_sem_seg.py:46-47, 56 (F.log_softmax + F.nll_loss, mean, no class weights)
  * logits [M, pitch] fp32 (dtype 0) or bf16 (1), `classes` (<= 32) real columns, `bias` [classes] fp32 added to them

@@ -106,6 +106,19 @@ class EnhancedPointNet2(nn.Module):
         return _cf_view(seq_rows(self.final_fusion, mix.reshape(B * N, C)), B, N)
 
 
+def _weighted_smoothed_ce(x, target, weight, label_smoothing):
+    """F.cross_entropy(x, target, weight=weight, label_smoothing=ls) with mean reduction, written out with
+    fixed-shape ops: ATen's version divides by `weight.gather(0, target.masked_select(~ignore_mask)).sum()`,
+    and masked_select synchronises with the host (not CUDA-graph capturable).  Same arithmetic:
+    (1 - ls) * sum_i w[y_i] * (-logp[i, y_i]) / W  +  ls / C * sum_i sum_c w[c] * (-logp[i, c]) / W,  W = sum_i w[y_i]."""
+    logp = F.log_softmax(x, dim=1)
+    wy = weight[target]
+    den = wy.sum()
+    nll = -(wy * logp.gather(1, target.view(-1, 1)).squeeze(1)).sum() / den
+    smooth = -(logp * weight.view(1, -1)).sum() / den
+    return (1 - label_smoothing) * nll + smooth * (label_smoothing / x.shape[1])
+
+
 class BridgeStructureLoss(nn.Module):
     """Label-smoothed cross entropy whose class weights grow when the predicted classes violate
     the vertical ordering abutment < girder < deck < parapet (model.py:169-263).  Plain PyTorch,
@@ -134,26 +147,23 @@ class BridgeStructureLoss(nn.Module):
         B = labels.shape[0]
         preds = logits.argmax(dim=-1)
         w = self.base_weights_buffer.repeat(B, 1).to(logits.device)
-        present = {c: bool(((labels == c).float().sum(dim=1) > 0).any()) for c in (1, 2, 3, 4)}
-        height = {}
-        for c in (1, 2, 3, 4):
-            m = preds == c
-            height[c] = self._mean_height(points, m) if bool(m.any()) else torch.zeros(B, device=logits.device)
+        # The reference branches in Python on `present` / `m.any()` (model.py:204-230), i.e. one host sync per
+        # class; the same arithmetic with 0/1 factors instead: a class that is absent contributes +0, and
+        # _mean_height of an empty mask is exactly 0 (p = 0, rel = 0 / 1e-7, divided by clamp(0, 1) = 1).
+        present = {c: (labels == c).any().to(w.dtype) for c in (1, 2, 3, 4)}
+        height = {c: self._mean_height(points, preds == c) for c in (1, 2, 3, 4)}
         for c, rel in self.ORDER.items():
             for lower in rel.get("above", []):
-                if present[lower]:
-                    v = F.relu(-(height[c] - height[lower]) + self.rel_margin)
-                    w[:, c] += self.alpha * v
-                    w[:, lower] += self.alpha * v * 0.5
+                v = F.relu(-(height[c] - height[lower]) + self.rel_margin) * present[lower]
+                w[:, c] += self.alpha * v
+                w[:, lower] += self.alpha * v * 0.5
             for upper in rel.get("below", []):
-                if present[upper]:
-                    v = F.relu(-(height[upper] - height[c]) + self.rel_margin)
-                    w[:, c] += self.alpha * v
-                    w[:, upper] += self.alpha * v * 0.3
+                v = F.relu(-(height[upper] - height[c]) + self.rel_margin) * present[upper]
+                w[:, c] += self.alpha * v
+                w[:, upper] += self.alpha * v * 0.3
         w[:, 0] += self.alpha * (1 - (preds == 0).float().mean(dim=1))
-        freq = torch.bincount(labels.view(-1), minlength=5).float().clamp(min=1)
+        freq = (labels.view(-1, 1) == torch.arange(5, device=labels.device)).sum(dim=0).float().clamp(min=1)   # bincount
         cw = (1 / freq.sqrt()).to(logits.device)
         cw[1] *= 2.0
         cw[4] *= 2.0
-        return F.cross_entropy(logits.reshape(-1, 5), labels.reshape(-1), weight=w.mean(dim=0) * cw,
-                               label_smoothing=0.2)
+        return _weighted_smoothed_ce(logits.reshape(-1, 5), labels.reshape(-1), w.mean(dim=0) * cw, 0.2)

@@ -553,6 +553,19 @@ def bn_rows_supported(y, bn, pool_k=1) -> bool:
             and y.shape[0] > 1 and pool_k <= 255 and y.numel() // 4 < 2 ** 31)
 
 
+@torch.no_grad()
+def eigvalsh3(a: torch.Tensor) -> torch.Tensor:
+    """torch.linalg.eigvalsh for a batch of symmetric 3x3 matrices [...,3,3] -> [...,3] ascending, without the
+    host synchronisation of the cuSOLVER path (CUDA-graph capturable); float64 closed form per matrix."""
+    a = _f32(a, "a")
+    if a.shape[-2:] != (3, 3):
+        raise ValueError("eigvalsh3 expects [...,3,3]")
+    M = a.numel() // 9
+    out = torch.empty(*a.shape[:-2], 3, dtype=torch.float32, device=a.device)
+    _call("pcb_eigvalsh3_f32", a.device, a.data_ptr(), M, out.data_ptr(), alg_bytes=48 * M)
+    return out
+
+
 # ---------------------------------------------------------------------------------------------
 # mean NLL of the segmentation head straight from the classifier's logits rows
 # ---------------------------------------------------------------------------------------------

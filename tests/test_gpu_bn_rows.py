@@ -194,3 +194,20 @@ def test_nll_logit_rows_matches_log_softmax_nll(dtype, pitch):
     torch.testing.assert_close(ba.grad, bb.grad, rtol=1e-4, atol=1e-7)
     assert torch.equal(ops.LogitRows(rows, bias, nc, 1, M).log_probs().view(M, nc),
                        torch.log_softmax(rows[:, :nc].float() + bias, -1))
+
+
+def test_eigvalsh3_matches_torch():
+    """Closed-form float64 eigenvalues of symmetric 3x3 matrices against torch.linalg.eigvalsh (float64 reference):
+    covariance-like, near-planar (one tiny eigenvalue), diagonal and repeated-eigenvalue cases."""
+    torch.manual_seed(0)
+    M = 20_000
+    x = torch.randn(M, 32, 3, device=DEV) * torch.tensor([1.0, 0.3, 0.002], device=DEV)     # near-planar patches
+    cov = torch.bmm(x.transpose(1, 2), x) / 31
+    cov[:100] = torch.diag_embed(torch.rand(100, 3, device=DEV))                             # diagonal
+    cov[100:200] = torch.eye(3, device=DEV) * torch.rand(100, 1, 1, device=DEV)              # triple eigenvalue
+    ev = ops.eigvalsh3(cov)
+    ref = torch.linalg.eigvalsh(cov.double())
+    assert ev.shape == (M, 3) and (ev[:, 1:] >= ev[:, :-1]).all()
+    scale = ref.abs().amax(dim=1, keepdim=True)
+    assert ((ev.double() - ref).abs() / scale).max().item() <= 2e-7        # fp32 rounding of the result only
+    assert ops.eigvalsh3(cov.view(100, 200, 3, 3)).shape == (100, 200, 3)

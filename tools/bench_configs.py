@@ -88,7 +88,7 @@ def main():
         torch.manual_seed(0)
         net = hb_model.EnhancedPointNet2(5).to(dev).train()
         crit = hb_model.BridgeStructureLoss(num_classes=5, alpha=80, rel_margin=0.3).to(dev)
-        tr = Trainer(net, loss_fn=lambda out, labels, pts: crit(out, labels, pts), amp=True, graph=False)
+        tr = Trainer(net, loss_fn=lambda out, labels, pts: crit(out, labels, pts), amp=True, graph=True)
 
         def f():
             tr.step(txyz, trgb, labels=tlab, loss_inputs=(txyz,))
