@@ -92,7 +92,7 @@ def main():
 
         def f():
             tr.step(txyz, trgb, labels=tlab, loss_inputs=(txyz,))
-        ms = timed(f, a.iters, 3, dev)
+        ms = timed(f, a.iters, 6, dev)                    # 3 eager steps + graph capture, then replays
         emit(config="c4 BriStruNet train step (DDP, flat NCCL all-reduce)", batch_per_gpu=B, ms=round(ms, 3),
              points_per_s=round(world * B * N / ms * 1e3), n_gpus=world, grad_bucket_mb=round(tr.bucket.nbytes / 1e6, 1))
     if "c5" in want:
