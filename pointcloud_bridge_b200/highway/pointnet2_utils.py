@@ -100,6 +100,8 @@ def seq_rows(seq: nn.Sequential, x):
                 i += 3
                 continue
             if ops._step_ctx is not None and x.is_cuda and ops._step_ctx.shadow(w) is not None:
+                if x.shape[1] % 8:
+                    x = F.pad(x, (0, -x.shape[1] % 8))                   # aligned rows for forward / dgrad / wgrad
                 y = ops.linear_rows(x, w, pad_n=True)                    # [M, n8], pad columns zero
                 if layer.bias is not None:
                     y = y + F.pad(layer.bias, (0, y.shape[1] - w.shape[0])).to(y.dtype)

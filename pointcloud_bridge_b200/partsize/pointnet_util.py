@@ -120,6 +120,11 @@ def conv_bn_relu_rows(x, conv, bn, pool_k=1):
     half runs in libpcbridge's fused row kernels (csrc/bn_rows.cu): the conv bias is folded into
     the normalisation and ReLU / max-pool happen in the same pass."""
     w = conv.weight.flatten(1)
+    if ops._step_ctx is not None and x.is_cuda and x.shape[1] % 8 and bn.training:
+        # inside a step runner: rows that are not a multiple of 8 channels wide (3 xyz / 9 / 259 concatenated
+        # features in the BriStruNet modules) get zero pad columns once, so that the forward, dgrad and weight
+        # gradient GEMMs all see 16-byte aligned rows (otherwise cuBLAS's unaligned legacy kernels)
+        x = F.pad(x, (0, -x.shape[1] % 8))
     padded = x.shape[1] != w.shape[1]                     # zero pad columns from group_points(pad_to=8)
     if bn.training and x.is_cuda and bn.momentum is not None and bn.affine \
             and x.shape[0] % pool_k == 0 and 1 < pool_k + 1 <= 256 and x.shape[0] > 1:
