@@ -45,6 +45,7 @@ def main():
     ap.add_argument("--only", default="c1,c3,c4,c5")
     ap.add_argument("--blocks", type=int, default=1526)
     ap.add_argument("--iters", type=int, default=10)
+    ap.add_argument("--batch-blocks", type=int, default=128, help="c5: blocks per captured inference batch")
     a = ap.parse_args()
     rank, world, local = pdist.init_from_env()
     dev = torch.device("cuda", local)
@@ -110,17 +111,19 @@ def main():
             def __getitem__(self, s):
                 return shard[s.start - rng.start:s.stop - rng.start]
         from pointcloud_bridge_b200.engine import BlockInference
-        infer = BlockInference(net, batch_blocks=32, amp=True, graph=True)
+        infer = BlockInference(net, batch_blocks=a.batch_blocks, amp=True, graph=True)
         for _ in range(1):
-            run_sharded_scene(net, _Shifted(), rank, world, dev, infer=infer)          # warm-up (captures the graph)
+            run_sharded_scene(net, _Shifted(), rank, world, dev, infer=infer,
+                              chunk_blocks=max(512, 4 * a.batch_blocks))               # warm-up (captures the graph)
         if world > 1:
             torch.distributed.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        r, labels = run_sharded_scene(net, _Shifted(), rank, world, dev, infer=infer)
+        r, labels = run_sharded_scene(net, _Shifted(), rank, world, dev, infer=infer,
+                                      chunk_blocks=max(512, 4 * a.batch_blocks))
         torch.cuda.synchronize()
         dt = pdist.max_over_ranks(time.perf_counter() - t0, dev)
-        emit(config="c5 block-sharded scene inference (PN++ SSG), host->device->host", blocks_per_gpu=a.blocks,
+        emit(config="c5 block-sharded scene inference (PN++ SSG), host->device->host", blocks_per_gpu=a.blocks, batch_blocks=a.batch_blocks,
              points_total=nb_total * N, seconds=round(dt, 4), points_per_s=round(nb_total * N / dt), n_gpus=world,
              collectives_on_data_path=0)
     if world > 1:
