@@ -153,6 +153,19 @@ class Trainer:
         self._starts = FpsStartBuffers()
         self._warm = 0
         self._opt_in_graph = False
+        self._last_logits = None
+
+    @torch.no_grad()
+    def last_pred(self, class_dim: int = 1) -> torch.Tensor:
+        """Predicted labels [B,N] of the step that just ran (for running accuracy, as the reference's loop computes
+        `outputs.max(1)[1]`, train_MulSca_BriStruNet_CB.py:181).  In graph mode this reads the graph's static output."""
+        lg = self._last_logits
+        if isinstance(lg, ops.LogitRows):
+            x = lg.rows[:, :lg.classes].float()
+            if lg.bias is not None:
+                x = x + lg.bias
+            return x.argmax(dim=1).view(lg.B, lg.N)
+        return lg.argmax(dim=class_dim)
 
     def refresh(self) -> None:
         """Call after changing parameters from outside (net.load_state_dict, manual edits): re-derives the
@@ -171,6 +184,7 @@ class Trainer:
                 with torch.autocast("cuda", dtype=torch.bfloat16, enabled=self.amp):
                     out = self.net(*inputs)
             logits = out[0] if isinstance(out, tuple) else out
+            self._last_logits = logits if isinstance(logits, ops.LogitRows) else logits.detach()
             if isinstance(logits, ops.LogitRows):
                 loss = ops.nll_logit_rows(logits, labels)
             elif self.loss_fn is None:     # sem-seg nets return log-probabilities [B,N,C]
