@@ -168,13 +168,16 @@ int pcb_graph_feature_bwd_f32(const float *grad_out, const int64_t *idx, int B, 
  *                     work[2C:3C] = gradient of the folded conv bias
  * C is the row pitch, Cv <= C the number of real channels: columns Cv..C-1 of y are zero padding that keeps
  * rows 16-byte aligned (196 -> 200 channels in the MSG network); parameter arrays have Cv entries, mean /
- * invstd / work are sized for C, and the padded columns of out / gy are written as zeros. */
+ * invstd / work are sized for C, and the padded columns of out / gy are written as zeros.
+ * out_pitch / gz_pitch (elements, 0 = C): `out` resp. `gz` may be a column slice of a wider row-major buffer -- the
+ * scales of a multi-scale module write straight into their concatenated output and read their slice of its gradient. */
 int64_t pcb_bn_work_floats(int C);
 int pcb_bn_fwd_rows(const void *y, int dtype, int64_t M, int C, int Cv, int pool_k, const float *bias, const float *gamma,
                     const float *beta, float eps, float momentum, float *running_mean, float *running_var, int relu,
-                    float *mean, float *invstd, void *out, unsigned char *argmax, float *work, pcb_stream_t stream);
-int pcb_bn_bwd_rows(const void *gz, const void *y, const unsigned char *argmax, int dtype, int64_t M, int C,
-                    int Cv, int pool_k, const float *mean, const float *invstd, const float *gamma, const float *beta,
+                    float *mean, float *invstd, void *out, int64_t out_pitch, unsigned char *argmax, float *work,
+                    pcb_stream_t stream);
+int pcb_bn_bwd_rows(const void *gz, int64_t gz_pitch, const void *y, const unsigned char *argmax, int dtype, int64_t M,
+                    int C, int Cv, int pool_k, const float *mean, const float *invstd, const float *gamma, const float *beta,
                     int relu, float *work, void *gy, pcb_stream_t stream);
 
 /* ---- a11 (training, backward of the 1x1 convolutions on rows)

@@ -51,9 +51,9 @@ _SIGNATURES = {
     "pcb_knn_cdist_f32": [_vp, _i, _i, _i, _vp, _vp, _vp],
     "pcb_graph_feature_f32": [_vp, _vp, _i, _i, _i, _i, _vp, _vp],
     "pcb_graph_feature_bwd_f32": [_vp, _vp, _i, _i, _i, _i, _vp, _vp],
-    "pcb_bn_fwd_rows": [_vp, _i, _i64, _i, _i, _i, _vp, _vp, _vp, _f, _f, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp],
+    "pcb_bn_fwd_rows": [_vp, _i, _i64, _i, _i, _i, _vp, _vp, _vp, _f, _f, _vp, _vp, _i, _vp, _vp, _vp, _i64, _vp, _vp, _vp],
     "pcb_sa_fused_bf16": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp, _f, _vp, _i, _vp],
-    "pcb_bn_bwd_rows": [_vp, _vp, _vp, _i, _i64, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp],
+    "pcb_bn_bwd_rows": [_vp, _i64, _vp, _vp, _i, _i64, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp],
 }
 
 EXPORTS = ["pcb_version", "pcb_error_string", "pcb_bn_work_floats", "pcb_nll_rows_blocks", *_SIGNATURES]

@@ -326,6 +326,7 @@ struct FwdApply {
     const float *mean, *invstd, *gamma, *beta;
     const float *s_const;                                  // shared copy [sc | sh] of all C channels, or nullptr
     int C, relu;
+    int64_t opitch;                                        // row pitch of `out` (>= C: a column slice of a wider buffer)
     float sc[V], sh[V];
     __device__ __forceinline__ void init(int c)
     {
@@ -350,7 +351,7 @@ struct FwdApply {
             v[i] = fmaf(v[i], sc[i], sh[i]);
             if (relu) v[i] = fmaxf(v[i], 0.f);
         }
-        VecIO<T, V>::store(out + r * C + c, v);
+        VecIO<T, V>::store(out + r * opitch + c, v);
     }
 };
 
@@ -386,7 +387,7 @@ struct FwdApplyPooled : FwdApply<T, V> {
                     }
                 }
         }
-        VecIO<T, V>::store(this->out + g * this->C + c, best);
+        VecIO<T, V>::store(this->out + g * this->opitch + c, best);
         if (argmax) AmIO<V>::st(argmax + g * this->C + c, bi);
     }
 };
@@ -399,6 +400,7 @@ struct BnFwdArgs {
     float *running_mean, *running_var, *mean, *invstd, *work;
     int64_t M, upc;
     int C, Cv, pool_k, relu, nparts;                   // C = row pitch (multiple of 4), Cv <= C real channels
+    int64_t out_pitch;                                 // row pitch of out (C, or wider when out is a column slice)
     float eps, momentum;
 };
 
@@ -467,12 +469,12 @@ bn_fwd_fused_kernel(const BnFwdArgs a)
     if (a.pool_k > 1) {
         FwdApplyPooled<T, V, 8> f;
         f.y = y, f.out = (T *)a.out, f.mean = a.mean, f.invstd = a.invstd, f.gamma = a.gamma, f.beta = a.beta;
-        f.C = C, f.relu = a.relu, f.argmax = a.argmax, f.pool_k = a.pool_k, f.s_const = s_const;
+        f.C = C, f.relu = a.relu, f.argmax = a.argmax, f.pool_k = a.pool_k, f.s_const = s_const, f.opitch = a.out_pitch;
         row_stream<V, 1>(f, a.M / a.pool_k, C);
     } else {
         FwdApply<T, V> f;
         f.y = y, f.out = (T *)a.out, f.mean = a.mean, f.invstd = a.invstd, f.gamma = a.gamma, f.beta = a.beta;
-        f.C = C, f.relu = a.relu, f.s_const = s_const;
+        f.C = C, f.relu = a.relu, f.s_const = s_const, f.opitch = a.out_pitch;
         row_stream<V, PCB_BN_U>(f, a.M, C);
     }
     BN_STAMP(5);
@@ -490,6 +492,7 @@ struct BwdBase {
     const float *mean, *invstd, *gamma, *beta, *sums;
     const float *s_const;                                  // shared [nm | is | sc | sh | a0 | a1] x C, or nullptr
     int C, Cv, relu, pool_k;
+    int64_t gpitch;                                        // row pitch of gz (C, or wider: column slice of a concatenated gradient)
     float invM;
     float nm[V], is[V], sc[V], sh[V], a0[V], a1[V];      // nm = -mean * invstd: yhat = fma(y, is, nm)
     __device__ __forceinline__ void consts(int c, bool with_sums)
@@ -563,7 +566,7 @@ struct BwdRows : BwdBase<T, V> {
     {
         Pack p;
         p.y = VecIO<T, V>::ldraw(this->y + r * this->C + c);
-        p.g = VecIO<T, V>::ldraw(this->gz + r * this->C + c);
+        p.g = VecIO<T, V>::ldraw(this->gz + r * this->gpitch + c);
         return p;
     }
     __device__ __forceinline__ void use(const Pack &p, int64_t, int, float acc[3][V]) const
@@ -593,7 +596,7 @@ struct BwdGroups : BwdBase<T, V> {
     __device__ __forceinline__ Pack load(int64_t g, int c) const
     {
         Pack p;
-        p.g = VecIO<T, V>::ldraw(this->gz + g * this->C + c);
+        p.g = VecIO<T, V>::ldraw(this->gz + g * this->gpitch + c);
         p.am = AmIO<V>::ld(this->argmax + g * this->C + c);
         return p;
     }
@@ -634,7 +637,7 @@ struct BnBwdArgs {
     void *gy;
     const float *mean, *invstd, *gamma, *beta;
     float *work;
-    int64_t M, upc;
+    int64_t M, upc, gz_pitch;
     int C, Cv, pool_k, relu, nparts;
 };
 
@@ -643,7 +646,7 @@ __device__ __forceinline__ void bwd_fill(F &f, const BnBwdArgs &a)
 {
     f.y = (const T *)a.y, f.gz = (const T *)a.gz, f.argmax = a.argmax, f.gy = (T *)a.gy;
     f.mean = a.mean, f.invstd = a.invstd, f.gamma = a.gamma, f.beta = a.beta, f.sums = a.work;
-    f.C = a.C, f.Cv = a.Cv, f.relu = a.relu, f.pool_k = a.pool_k, f.invM = 1.f / (float)a.M;
+    f.C = a.C, f.Cv = a.Cv, f.relu = a.relu, f.pool_k = a.pool_k, f.invM = 1.f / (float)a.M, f.gpitch = a.gz_pitch;
     f.s_const = nullptr;
 }
 
@@ -819,7 +822,7 @@ PCB_API int64_t pcb_bn_work_floats(int C) { return 3 * (int64_t)C * (1 + kBnMaxP
 
 PCB_API int pcb_bn_fwd_rows(const void *y, int dtype, int64_t M, int C, int Cv, int pool_k, const float *bias,
                             const float *gamma, const float *beta, float eps, float momentum, float *running_mean,
-                            float *running_var, int relu, float *mean, float *invstd, void *out,
+                            float *running_var, int relu, float *mean, float *invstd, void *out, int64_t out_pitch,
                             unsigned char *argmax, float *work, pcb_stream_t stream)
 {
     PCB_REQUIRE(y && gamma && beta && mean && invstd && out && work, PCB_EINVAL);
@@ -830,15 +833,16 @@ PCB_API int pcb_bn_fwd_rows(const void *y, int dtype, int64_t M, int C, int Cv, 
     a.y = y, a.out = out, a.argmax = argmax, a.bias = bias, a.gamma = gamma, a.beta = beta;
     a.running_mean = running_mean, a.running_var = running_var;
     a.mean = mean, a.invstd = invstd, a.work = work, a.M = M, a.C = C, a.Cv = Cv, a.pool_k = pool_k, a.relu = relu;
-    a.eps = eps, a.momentum = momentum, a.upc = 0, a.nparts = 0;
+    a.eps = eps, a.momentum = momentum, a.upc = 0, a.nparts = 0, a.out_pitch = out_pitch > 0 ? out_pitch : C;
+    PCB_REQUIRE(a.out_pitch >= C && a.out_pitch % 4 == 0, PCB_ERANGE);
     cudaStream_t st = (cudaStream_t)stream;
     if (!dtype) return bn_fwd_launch<float, 4>(a, st);
-    if (C % 8 == 0 && al16(y) && al16(out)) return bn_fwd_launch<__nv_bfloat16, 8>(a, st);
+    if (C % 8 == 0 && a.out_pitch % 8 == 0 && al16(y) && al16(out)) return bn_fwd_launch<__nv_bfloat16, 8>(a, st);
     return bn_fwd_launch<__nv_bfloat16, 4>(a, st);
 }
 
-PCB_API int pcb_bn_bwd_rows(const void *gz, const void *y, const unsigned char *argmax, int dtype, int64_t M, int C,
-                            int Cv, int pool_k, const float *mean, const float *invstd, const float *gamma, const float *beta,
+PCB_API int pcb_bn_bwd_rows(const void *gz, int64_t gz_pitch, const void *y, const unsigned char *argmax, int dtype,
+                            int64_t M, int C, int Cv, int pool_k, const float *mean, const float *invstd, const float *gamma, const float *beta,
                             int relu, float *work, void *gy, pcb_stream_t stream)
 {
     PCB_REQUIRE(gz && y && mean && invstd && gamma && beta && work && gy, PCB_EINVAL);
@@ -848,8 +852,10 @@ PCB_API int pcb_bn_bwd_rows(const void *gz, const void *y, const unsigned char *
     BnBwdArgs a;
     a.gz = gz, a.y = y, a.argmax = argmax, a.gy = gy, a.mean = mean, a.invstd = invstd, a.gamma = gamma, a.beta = beta;
     a.work = work, a.M = M, a.C = C, a.Cv = Cv, a.pool_k = pool_k, a.relu = relu, a.upc = 0, a.nparts = 0;
+    a.gz_pitch = gz_pitch > 0 ? gz_pitch : C;
+    PCB_REQUIRE(a.gz_pitch >= C && a.gz_pitch % 4 == 0, PCB_ERANGE);
     cudaStream_t st = (cudaStream_t)stream;
     if (!dtype) return bn_bwd_launch<float, 4>(a, st);
-    if (C % 8 == 0 && al16(y) && al16(gz) && al16(gy)) return bn_bwd_launch<__nv_bfloat16, 8>(a, st);
+    if (C % 8 == 0 && a.gz_pitch % 8 == 0 && al16(y) && al16(gz) && al16(gy)) return bn_bwd_launch<__nv_bfloat16, 8>(a, st);
     return bn_bwd_launch<__nv_bfloat16, 4>(a, st);
 }

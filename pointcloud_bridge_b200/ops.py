@@ -491,7 +491,9 @@ class _BnReluRows(torch.autograd.Function):
     One cooperative kernel forward, one backward."""
 
     @staticmethod
-    def forward(ctx, y, bias, gamma, beta, running_mean, running_var, momentum, eps, relu, pool_k):
+    def forward(ctx, y, bias, gamma, beta, running_mean, running_var, momentum, eps, relu, pool_k, out=None):
+        # out: optional [M/pool_k, C] column slice (unit column stride) of a wider buffer to write into -- the
+        # scales of a multi-scale module fill their concatenated output directly (`join_columns`)
         if not y.is_contiguous():
             y = y.contiguous()
         M, C = y.shape                    # C: row pitch; Cv real channels (y may carry zero pad columns)
@@ -500,7 +502,8 @@ class _BnReluRows(torch.autograd.Function):
         dev = y.device
         stats = torch.empty(2, C, dtype=torch.float32, device=dev)          # mean, invstd of bias-free y
         Mout = M // pool_k
-        out = torch.empty(Mout, C, dtype=y.dtype, device=dev)
+        if out is None:
+            out = torch.empty(Mout, C, dtype=y.dtype, device=dev)
         argmax = torch.empty(Mout, C, dtype=torch.uint8, device=dev) if pool_k > 1 else None
         g32, b32 = gamma.float(), beta.float()
         work = _bn_work(C, dev)
@@ -509,7 +512,7 @@ class _BnReluRows(torch.autograd.Function):
               bias.data_ptr() if bias is not None else None, g32.data_ptr(), b32.data_ptr(), float(eps),
               float(momentum), running_mean.data_ptr() if running_mean is not None else None,
               running_var.data_ptr() if running_var is not None else None, int(relu), stats[0].data_ptr(),
-              stats[1].data_ptr(), out.data_ptr(), argmax.data_ptr() if argmax is not None else None,
+              stats[1].data_ptr(), out.data_ptr(), out.stride(0), argmax.data_ptr() if argmax is not None else None,
               work.data_ptr(), alg_bytes=(y.numel() + out.numel()) * esz + (Mout * C if pool_k > 1 else 0))
         ctx.save_for_backward(y, stats, g32, b32, argmax)
         ctx.meta = (M, C, Cv, dt, int(relu), int(pool_k), bias is not None)
@@ -519,22 +522,48 @@ class _BnReluRows(torch.autograd.Function):
     def backward(ctx, gz):
         y, stats, g32, b32, argmax = ctx.saved_tensors
         M, C, Cv, dt, relu, pool_k, has_bias = ctx.meta
-        gz = gz.contiguous()
         if gz.dtype != y.dtype:
             gz = gz.to(y.dtype)
+        if not (gz.dim() == 2 and gz.stride(1) == 1 and gz.stride(0) >= C and gz.stride(0) % 8 == 0
+                and gz.data_ptr() % 16 == 0):
+            gz = gz.contiguous()          # a column slice of a concatenated gradient is read in place (gz_pitch)
         gy = torch.empty_like(y)
         work = _bn_work(C, y.device)
-        _call("pcb_bn_bwd_rows", y.device, gz.data_ptr(), y.data_ptr(), argmax.data_ptr() if argmax is not None else None,
+        _call("pcb_bn_bwd_rows", y.device, gz.data_ptr(), gz.stride(0), y.data_ptr(),
+              argmax.data_ptr() if argmax is not None else None,
               dt, M, C, Cv, pool_k, stats[0].data_ptr(), stats[1].data_ptr(), g32.data_ptr(), b32.data_ptr(), relu,
               work.data_ptr(), gy.data_ptr(),
               alg_bytes=(2 * y.numel() + gz.numel()) * y.element_size() + (gz.numel() if pool_k > 1 else 0))
         s = work[:3 * C].view(3, C)
         # s[2] = d/d(conv bias) = sum_rows gy: zero up to rounding, as in the reference, where the bias of a
         # conv that feeds a training-mode BN gets a noise gradient
-        return gy, (s[2, :Cv] if has_bias else None), s[1, :Cv], s[0, :Cv], None, None, None, None, None, None
+        return gy, (s[2, :Cv] if has_bias else None), s[1, :Cv], s[0, :Cv], None, None, None, None, None, None, None
 
 
-def bn_relu_rows(y, bias, bn, relu=True, pool_k=1):
+class _JoinColumns(torch.autograd.Function):
+    """buf [M, C_total] whose column slices were filled by the given parts (bn_relu_rows(out=buf[:, a:b])): returns
+    buf with the parts as its autograd inputs -- torch.cat without the copy; backward hands each part its column
+    slice of the gradient as a view."""
+
+    @staticmethod
+    def forward(ctx, buf, *parts):
+        ctx.widths = [p.shape[1] for p in parts]
+        return buf
+
+    @staticmethod
+    def backward(ctx, g):
+        outs, off = [None], 0
+        for w in ctx.widths:
+            outs.append(g[:, off:off + w])
+            off += w
+        return tuple(outs)
+
+
+def join_columns(buf, parts):
+    return _JoinColumns.apply(buf, *parts)
+
+
+def bn_relu_rows(y, bias, bn, relu=True, pool_k=1, out=None):
     """BatchNorm with batch statistics (+ReLU, + max over groups of `pool_k` consecutive rows) of
     the bias-free GEMM output y [M,C]; updates bn's running statistics like nn.BatchNorm does."""
     if bn.track_running_stats and bn.num_batches_tracked is not None:
@@ -544,7 +573,10 @@ def bn_relu_rows(y, bias, bn, relu=True, pool_k=1):
             bn.num_batches_tracked.add_(1)
     rm = bn.running_mean if bn.track_running_stats else None
     rv = bn.running_var if bn.track_running_stats else None
-    return _BnReluRows.apply(y, bias, bn.weight, bn.bias, rm, rv, bn.momentum, bn.eps, bool(relu), int(pool_k))
+    if out is not None and not (out.dtype == y.dtype and out.shape == (y.shape[0] // pool_k, y.shape[1])
+                                and out.stride(1) == 1 and out.stride(0) % 8 == 0 and out.data_ptr() % 16 == 0):
+        out = None
+    return _BnReluRows.apply(y, bias, bn.weight, bn.bias, rm, rv, bn.momentum, bn.eps, bool(relu), int(pool_k), out)
 
 
 def bn_rows_supported(y, bn, pool_k=1) -> bool:

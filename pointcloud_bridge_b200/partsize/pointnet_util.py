@@ -114,7 +114,7 @@ def _bn_rows(bn, x):
                         use_batch, mom, bn.eps)
 
 
-def conv_bn_relu_rows(x, conv, bn, pool_k=1):
+def conv_bn_relu_rows(x, conv, bn, pool_k=1, out=None):
     """One shared-MLP layer on rows: 1x1 conv -> BN -> ReLU, optionally followed by the max over
     groups of `pool_k` consecutive rows (the neighbour axis).  In training mode the elementwise
     half runs in libpcbridge's fused row kernels (csrc/bn_rows.cu): the conv bias is folded into
@@ -133,7 +133,7 @@ def conv_bn_relu_rows(x, conv, bn, pool_k=1):
         # 392-byte rows would send the neighbouring GEMMs to cuBLAS's unaligned legacy kernels
         y = ops.linear_rows(x, w, pad_n=True)
         if ops.bn_rows_supported(y, bn, pool_k):
-            return ops.bn_relu_rows(y, conv.bias, bn, relu=True, pool_k=pool_k)
+            return ops.bn_relu_rows(y, conv.bias, bn, relu=True, pool_k=pool_k, out=out)   # out: see mlp_rows
         y = y[:, :w.shape[0]]
         x = y if conv.bias is None else y + conv.bias
     else:
@@ -144,12 +144,14 @@ def conv_bn_relu_rows(x, conv, bn, pool_k=1):
     return x
 
 
-def mlp_rows(x, convs, bns, pool_k=1):
+def mlp_rows(x, convs, bns, pool_k=1, out=None):
     """x [M,Cin] -> [M/pool_k,Cout]: (1x1 conv -> BN -> ReLU) per layer (pointnet_util.py:213-215), the
-    last layer followed by the max over `pool_k` neighbours (:217)."""
+    last layer followed by the max over `pool_k` neighbours (:217).  `out`: optional [M/pool_k, Cout] column
+    slice of a wider buffer that the last layer's fused kernel writes into when it can (training mode; the
+    result then IS `out`, which the caller checks by data pointer)."""
     n = len(convs)
     for i, (conv, bn) in enumerate(zip(convs, bns)):
-        x = conv_bn_relu_rows(x, conv, bn, pool_k if i == n - 1 else 1)
+        x = conv_bn_relu_rows(x, conv, bn, pool_k if i == n - 1 else 1, out if i == n - 1 else None)
     if x.shape[1] != convs[-1].weight.shape[0]:          # zero pad columns of the last layer are dropped
         x = x[:, :convs[-1].weight.shape[0]].contiguous()
     return x
@@ -223,7 +225,7 @@ class PointNetSetAbstractionMsg(nn.Module):
         B = xyz_r.shape[0]
         S = self.npoint
         new_xyz = index_points(xyz_r, farthest_point_sample(xyz_r, S))
-        outs = []
+        outs, joined = [], None
         # every radius in one scan of the cloud (the reference calls query_ball_point once per radius, :250)
         idxs = ops.ball_query_multi(self.radius_list, self.nsample_list, xyz_r, new_xyz)
         for i, radius in enumerate(self.radius_list):
@@ -236,8 +238,18 @@ class PointNetSetAbstractionMsg(nn.Module):
                     outs.append(ops.sa_fused(xyz_r, pts_r, new_xyz, idx, pk, xyz_first=False))
                     continue
             grouped = ops.group_points(xyz_r, pts_r, new_xyz, idx, xyz_first=False, pad_to=8)   # [feat | dxyz | 0]
-            outs.append(mlp_rows(grouped.view(B * S * K, -1), self.conv_blocks[i], self.bn_blocks[i], pool_k=K))
-        y = torch.cat(outs, dim=1)
+            if joined is None and self.training and grouped.is_cuda:
+                # the scales write their pooled rows straight into the concatenated output (no torch.cat copy)
+                widths = [blk[-1].weight.shape[0] for blk in self.conv_blocks]
+                joined = torch.empty(B * S, sum(widths), dtype=grouped.dtype, device=grouped.device)
+            off = sum(o.shape[1] for o in outs)
+            slot = joined[:, off:off + self.conv_blocks[i][-1].weight.shape[0]] if joined is not None else None
+            outs.append(mlp_rows(grouped.view(B * S * K, -1), self.conv_blocks[i], self.bn_blocks[i], pool_k=K, out=slot))
+        if joined is not None and all(o.data_ptr() == joined.data_ptr() + joined.element_size() * sum(p.shape[1] for p in outs[:j])
+                                      and o.stride(0) == joined.stride(0) for j, o in enumerate(outs)):
+            y = ops.join_columns(joined, outs)
+        else:
+            y = torch.cat(outs, dim=1)
         return new_xyz.permute(0, 2, 1), _cf_view(y, B, S)
 
 

@@ -25,10 +25,10 @@ for (M, C, K) in [(524288, 64, 32), (131072, 96, 1), (524288, 32, 1)]:
     for _ in range(2):
         flush.fill_(0)
         assert lib.pcb_bn_fwd_rows(y.data_ptr(), 1, M, C, C, K, None, g.data_ptr(), b.data_ptr(), 1e-5, 0.1, None, None, 1,
-                                   stats[0].data_ptr(), stats[1].data_ptr(), out.data_ptr(),
+                                   stats[0].data_ptr(), stats[1].data_ptr(), out.data_ptr(), 0,
                                    am.data_ptr() if K > 1 else None, work.data_ptr(), st) == 0
         flush.fill_(0)
-        assert lib.pcb_bn_bwd_rows(gz.data_ptr(), y.data_ptr(), am.data_ptr() if K > 1 else None, 1, M, C, C, K,
+        assert lib.pcb_bn_bwd_rows(gz.data_ptr(), 0, y.data_ptr(), am.data_ptr() if K > 1 else None, 1, M, C, C, K,
                                    stats[0].data_ptr(), stats[1].data_ptr(), g.data_ptr(), b.data_ptr(), 1,
                                    work.data_ptr(), gy.data_ptr(), st) == 0
     torch.cuda.synchronize()

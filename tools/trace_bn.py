@@ -42,14 +42,14 @@ for (M, C, K) in SHAPES:
     for it in range(3):
         buf[:] = 0
         lib.pcb_bn_fwd_rows(y.data_ptr(), 1, M, C, C, K, None, g.data_ptr(), b.data_ptr(), 1e-5, 0.1, None, None, 1,
-                            stats[0].data_ptr(), stats[1].data_ptr(), out.data_ptr(), am.data_ptr() if K > 1 else None,
+                            stats[0].data_ptr(), stats[1].data_ptr(), out.data_ptr(), 0, am.data_ptr() if K > 1 else None,
                             work.data_ptr(), st)
         torch.cuda.synchronize()
         if it == 2:
             assert lib.pcb_bn_debug_trace(buf.ctypes.data_as(ctypes.c_void_p)) == 0
             n = int((buf.reshape(1024, 8)[:, 0] > 0).sum())
             report(f"fwd M={M} C={C} K={K}", n)
-        lib.pcb_bn_bwd_rows(gz.data_ptr(), y.data_ptr(), am.data_ptr() if K > 1 else None, 1, M, C, C, K,
+        lib.pcb_bn_bwd_rows(gz.data_ptr(), 0, y.data_ptr(), am.data_ptr() if K > 1 else None, 1, M, C, C, K,
                             stats[0].data_ptr(), stats[1].data_ptr(), g.data_ptr(), b.data_ptr(), 1,
                             work.data_ptr(), gy.data_ptr(), st)
         torch.cuda.synchronize()
@@ -61,9 +61,9 @@ for (M, C, K) in SHAPES:
     # back-to-back launch time (warm L2 for the small shapes), CUDA events
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     for name, fn in (("fwd", lambda: lib.pcb_bn_fwd_rows(y.data_ptr(), 1, M, C, C, K, None, g.data_ptr(), b.data_ptr(), 1e-5, 0.1, None, None, 1,
-                                                        stats[0].data_ptr(), stats[1].data_ptr(), out.data_ptr(),
+                                                        stats[0].data_ptr(), stats[1].data_ptr(), out.data_ptr(), 0,
                                                         am.data_ptr() if K > 1 else None, work.data_ptr(), st)),
-                     ("bwd", lambda: lib.pcb_bn_bwd_rows(gz.data_ptr(), y.data_ptr(), am.data_ptr() if K > 1 else None, 1, M, C, C, K,
+                     ("bwd", lambda: lib.pcb_bn_bwd_rows(gz.data_ptr(), 0, y.data_ptr(), am.data_ptr() if K > 1 else None, 1, M, C, C, K,
                                                         stats[0].data_ptr(), stats[1].data_ptr(), g.data_ptr(), b.data_ptr(), 1,
                                                         work.data_ptr(), gy.data_ptr(), st))):
         for _ in range(5):
