@@ -154,6 +154,7 @@ class Trainer:
         self._warm = 0
         self._opt_in_graph = False
         self._last_logits = None
+        self._pf_stream = self._pf_bufs = self._pf_ready = self._pf_consumed = None
 
     @torch.no_grad()
     def last_pred(self, class_dim: int = 1) -> torch.Tensor:
@@ -236,6 +237,36 @@ class Trainer:
         finally:
             self._starts.mode = "off"
             ops.set_fps_start_provider(None)
+
+    # -- input prefetch: the host->device copy of the NEXT batch overlaps the current step ------------------
+    def prefetch(self, *inputs, labels, loss_inputs=()):
+        """Start copying the next step's batch (pinned host or device tensors) into staging buffers on a side
+        stream; `step_prefetched()` then only needs device-to-device copies.  Call it right after launching a
+        step: the H2D transfer runs while that step computes."""
+        dev = self.bucket.flat.device
+        if self._pf_stream is None:
+            self._pf_stream = torch.cuda.Stream(device=dev)
+        srcs = list(inputs) + [labels] + list(loss_inputs)
+        if self._pf_bufs is None or [tuple(b.shape) for b in self._pf_bufs] != [tuple(t.shape) for t in srcs]:
+            self._pf_bufs = [torch.empty(t.shape, dtype=t.dtype, device=dev) for t in srcs]
+        if self._pf_consumed is not None:
+            self._pf_stream.wait_event(self._pf_consumed)          # the previous step has read the staging buffers
+        with torch.cuda.stream(self._pf_stream):
+            for b, t in zip(self._pf_bufs, srcs):
+                b.copy_(t, non_blocking=True)
+            self._pf_ready = torch.cuda.Event()
+            self._pf_ready.record(self._pf_stream)
+        self._pf_counts = (len(inputs), len(loss_inputs))
+
+    def step_prefetched(self):
+        """`step` on the batch handed to `prefetch`."""
+        torch.cuda.current_stream().wait_event(self._pf_ready)
+        ni, nl = self._pf_counts
+        bufs = self._pf_bufs
+        loss = self.step(*bufs[:ni], labels=bufs[ni], loss_inputs=tuple(bufs[ni + 1:ni + 1 + nl]))
+        self._pf_consumed = torch.cuda.Event()
+        self._pf_consumed.record()          # (graph mode copies the staging buffers into the static inputs first)
+        return loss
 
     def step(self, *inputs, labels, loss_inputs=()):
         """One optimisation step on this rank's batch; returns the (device) loss tensor."""
