@@ -45,3 +45,22 @@ def test_vote_matches_reference():
     pool = so.add_vote(np.zeros(g["pool"].shape), g["index"], g["pred"])
     assert np.array_equal(pool.astype(np.int32), g["pool"])
     assert np.array_equal(so.vote_argmax(pool).astype(np.uint8), g["labels"])
+
+
+def test_product_window_bounds_equal_oracle_windows():
+    """scene.window_bounds (host side of the CUDA tiler, float64) reproduces the reference's window starts / ends
+    exactly, including the clamped last windows and scenes barely larger than one block."""
+    from pointcloud_bridge_b200 import scene
+    rng = np.random.default_rng(0)
+    for ext in (6.3, 1.0004, 1.5, 0.7, 12.0 + 1e-3):
+        pts = np.zeros((50, 6))
+        pts[:, 0] = rng.uniform(0, ext, 50)
+        pts[:, 1] = rng.uniform(0, 3.2, 50)
+        pts[0, 0], pts[1, 0] = 0.0, ext
+        wins, grid, cmin, cmax = so.tile_windows(pts.astype(np.float32))
+        cmin, cmax = np.amin(pts.astype(np.float32).astype(np.float64), 0), np.amax(pts.astype(np.float32).astype(np.float64), 0)
+        sx, ex, lox, hix = scene.window_bounds(cmin[0], cmax[0], 1.0, 0.5, 0.001)
+        sy, ey, loy, hiy = scene.window_bounds(cmin[1], cmax[1], 1.0, 0.5, 0.001)
+        assert (len(sx), len(sy)) == grid
+        for w, s_x, s_y, idx in wins:
+            assert sx[w % grid[0]] == s_x and sy[w // grid[0]] == s_y
