@@ -331,6 +331,49 @@ class _GroupPoints(torch.autograd.Function):
         return None, gpoints, None, None, None, None, None, None
 
 
+class _GroupPointsMulti(torch.autograd.Function):
+    """group_points for several neighbour lists around the same centroids (the scales of a multi-scale module):
+    forward = one grouping kernel per list; backward = ONE zero-filled fp32 gradient that every list's
+    scatter-add kernel accumulates into (instead of a zero fill + dtype cast + add per list)."""
+
+    @staticmethod
+    def forward(ctx, xyz, points, new_xyz, xyz_first, points_cf, clamp, pad_to, *idxs):
+        outs, metas = [], []
+        for idx in idxs:
+            sub = type("ctx", (), {})()
+            sub.save_for_backward = lambda *a, sub=sub: setattr(sub, "saved", a)
+            outs.append(_GroupPoints.forward(sub, xyz, points, new_xyz, idx, xyz_first, points_cf, clamp, pad_to))
+            metas.append(sub.meta)
+        ctx.save_for_backward(*[_i64(i, "idx") for i in idxs])
+        ctx.metas = metas
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *gouts):
+        idxs = ctx.saved_tensors
+        gpoints = None
+        if ctx.needs_input_grad[1] and ctx.metas[0][4]:
+            B, N, _, _, D, xyz_first, points_cf, clamp, _ = ctx.metas[0]
+            dev = idxs[0].device
+            gpoints = torch.zeros((B, D, N) if points_cf else (B, N, D), dtype=torch.float32, device=dev)
+            for idx, gout, meta in zip(idxs, gouts, ctx.metas):
+                if gout is None:
+                    continue
+                _, _, S, K, _, _, _, _, pitch = meta
+                bf16 = gout.dtype == torch.bfloat16
+                gout = gout.contiguous() if bf16 else _f32(gout, "grad")
+                _call("pcb_group_points_bwd_bf16" if bf16 else "pcb_group_points_bwd_f32", dev, gout.data_ptr(), idx.data_ptr(),
+                      B, N, S, K, D, xyz_first, points_cf, clamp, pitch, gpoints.data_ptr(),
+                      alg_bytes=B * (4 * N * D + 8 * S * K + gout.element_size() * S * K * D))
+        return (None, gpoints, None, None, None, None, None) + (None,) * len(idxs)
+
+
+def group_points_multi(xyz, points, new_xyz, idxs, xyz_first: bool = True, points_cf: bool = False,
+                       clamp: bool = False, pad_to: int = 1):
+    """[group_points(xyz, points, new_xyz, idx, ...) for idx in idxs] with one shared gradient buffer for `points`."""
+    return _GroupPointsMulti.apply(xyz, points, new_xyz, bool(xyz_first), bool(points_cf), bool(clamp), int(pad_to), *idxs)
+
+
 def group_points(xyz, points, new_xyz, idx, xyz_first: bool = True, points_cf: bool = False,
                  clamp: bool = False, pad_to: int = 1) -> torch.Tensor:
     """Fused index_points(xyz, idx) - new_xyz, index_points(points, idx) and concat:

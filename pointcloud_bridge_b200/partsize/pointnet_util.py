@@ -228,6 +228,10 @@ class PointNetSetAbstractionMsg(nn.Module):
         outs, joined = [], None
         # every radius in one scan of the cloud (the reference calls query_ball_point once per radius, :250)
         idxs = ops.ball_query_multi(self.radius_list, self.nsample_list, xyz_r, new_xyz)
+        groupeds = None
+        if self.training and xyz_r.is_cuda and pts_r is not None and pts_r.requires_grad:
+            # all scales grouped by one autograd node: their scatter-add backward shares one gradient buffer
+            groupeds = ops.group_points_multi(xyz_r, pts_r, new_xyz, idxs, xyz_first=False, pad_to=8)
         for i, radius in enumerate(self.radius_list):
             K = self.nsample_list[i]
             idx = idxs[i]
@@ -237,7 +241,8 @@ class PointNetSetAbstractionMsg(nn.Module):
                 if pk.ok:
                     outs.append(ops.sa_fused(xyz_r, pts_r, new_xyz, idx, pk, xyz_first=False))
                     continue
-            grouped = ops.group_points(xyz_r, pts_r, new_xyz, idx, xyz_first=False, pad_to=8)   # [feat | dxyz | 0]
+            grouped = groupeds[i] if groupeds is not None else \
+                ops.group_points(xyz_r, pts_r, new_xyz, idx, xyz_first=False, pad_to=8)          # [feat | dxyz | 0]
             if joined is None and self.training and grouped.is_cuda:
                 # the scales write their pooled rows straight into the concatenated output (no torch.cat copy)
                 widths = [blk[-1].weight.shape[0] for blk in self.conv_blocks]
