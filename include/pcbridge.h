@@ -242,10 +242,48 @@ int pcb_nll_rows_bwd(const void *logits, int dtype, const float *bias, const int
  *          Highway_bridge/train_MulSca_BriStruNet_CB.py:158-190 (torch.optim.Adam, L2 weight decay)
  * p, g, m, v [n] fp32; `lr` [1] fp32 and `step` [1] int64 (already incremented, >= 1) are DEVICE scalars so a
  * captured CUDA graph follows a scheduler.  shadow_index [n] int32 (may be NULL): destination element of
- * parameter i in `shadow_bf16`, the bf16 copies of the GEMM weights ([N8, K8] zero padded), or -1. */
+ * parameter i in `shadow_bf16`, the bf16 copies of the GEMM weights ([N8, K8] zero padded), or -1;
+ * shadow_index_t [n] (may be NULL): where the same element goes in the TRANSPOSED copy ([K8, N8], the operand of the
+ * data-gradient GEMM), read only where shadow_index[i] >= 0. */
 int pcb_adam_flat_f32(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, int64_t n, const float *lr,
                       float beta1, float beta2, float eps, float weight_decay, const int64_t *step,
-                      const int *shadow_index, void *shadow_bf16, pcb_stream_t stream);
+                      const int *shadow_index, const int *shadow_index_t, void *shadow_bf16, pcb_stream_t stream);
+
+/* ---- a11 (training): shared-MLP contractions on the tcgen05 tensor cores, BatchNorm statistics in the epilogue
+ *          pointnet_util.py:213-217, 275-277, 343-345; pointnet2_sem_seg.py:43-46; pointnet2_utils.py:150-154, 353-356;
+ *          DGCNN.py:134-148  (1x1 Conv2d / Conv1d = [M,K] x [K,N] on point-major rows)
+ * y[M, N] = x[M, K] . w[Nw, K]^T with bf16 operands (row-major, leading dimensions ldx / ldw / ldy in elements,
+ * multiples of 8, 16-byte aligned bases), fp32 accumulation in TMEM, bf16 result; N, K multiples of 8; rows >= Nw of
+ * w count as zero.  Persistent warp-specialised kernel (cp.async producers -> tcgen05.mma -> TMEM -> epilogue).
+ *   pcb_linear_rows_bf16          plain product (forward of a conv without BatchNorm; data gradient with w = W^T)
+ *   pcb_linear_bn_stats_rows_bf16 + training-mode BatchNorm statistics of the result: mean / invstd [N] (biased
+ *                                 variance, eps) of the bias-free output, running_mean / running_var [Cv] updated with
+ *                                 `momentum` (unbiased variance; `bias` [Cv], may be NULL, is added to the running mean
+ *                                 only).  Column sums are shifted by running_mean - bias as read on entry.  Cv <= N real
+ *                                 channels.  work: pcb_gemm_work_floats(M, N, K) floats of scratch; tickets:
+ *                                 pcb_gemm_tickets() zeroed 32-bit words (left zeroed).  Deterministic two-stage sums.
+ *   pcb_dgrad_bn_rows_bf16        data gradient THROUGH the previous layer's BN + ReLU: gz = gy . wt^T; dy = gz * [z > 0]
+ *                                 with z = BN(yprev) recomputed from yprev [M, ldyp] and mean / invstd / gamma / beta;
+ *                                 writes dy [M, lddy] and sums [3][N] = (sum dy, sum dy * yhat, 0)
+ *   pcb_bn_apply_rows             out = [max over pool_k rows of] act(BN(y)) with given statistics (ordinary launch)
+ *   pcb_bn_bwd_apply_rows         gy = gamma * invstd * (dy - sums[0] / M - yhat * sums[1] / M); gy may alias dy */
+int64_t pcb_gemm_work_floats(int64_t M, int N, int K);
+int pcb_gemm_tickets(void);
+int pcb_linear_rows_bf16(const void *x, int64_t ldx, const void *w, int64_t ldw, int64_t M, int N, int Nw, int K, void *y,
+                         int64_t ldy, pcb_stream_t stream);
+int pcb_linear_bn_stats_rows_bf16(const void *x, int64_t ldx, const void *w, int64_t ldw, int64_t M, int N, int Nw, int K,
+                                  void *y, int64_t ldy, int Cv, const float *bias, float eps, float momentum,
+                                  float *running_mean, float *running_var, float *mean, float *invstd, float *work,
+                                  unsigned *tickets, pcb_stream_t stream);
+int pcb_dgrad_bn_rows_bf16(const void *gy, int64_t ldg, const void *wt, int64_t ldwt, int64_t M, int N, int Nw, int K,
+                           const void *yprev, int64_t ldyp, const float *mean, const float *invstd, const float *gamma,
+                           const float *beta, int Cv, int relu, void *dy, int64_t lddy, float *sums, float *work,
+                           unsigned *tickets, pcb_stream_t stream);
+int pcb_bn_apply_rows(const void *y, int dtype, int64_t M, int C, int Cv, int pool_k, const float *mean,
+                      const float *invstd, const float *gamma, const float *beta, int relu, void *out, int64_t out_pitch,
+                      unsigned char *argmax, pcb_stream_t stream);
+int pcb_bn_bwd_apply_rows(const void *dy, const void *y, int dtype, int64_t M, int C, int Cv, const float *mean,
+                          const float *invstd, const float *gamma, const float *sums, void *gy, pcb_stream_t stream);
 
 /* ---- a11 / section 8f rank 1: fused set-abstraction / EdgeConv block for inference
  *          pointnet_util.py:137-147, 203-217, 258-279; pointnet2_utils.py:140-154, 341-356;

@@ -38,7 +38,14 @@ _SIGNATURES = {
     "pcb_fp_concat_bf16": [_vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp],
     "pcb_fp_concat_bwd_bf16": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp],
     "pcb_wgrad_rows_bf16": [_vp, _vp, _i64, _i, _i, _i, _i, _vp, _i, _vp],
-    "pcb_adam_flat_f32": [_vp, _vp, _vp, _vp, _i64, _vp, _f, _f, _f, _f, _vp, _vp, _vp, _vp],
+    "pcb_adam_flat_f32": [_vp, _vp, _vp, _vp, _i64, _vp, _f, _f, _f, _f, _vp, _vp, _vp, _vp, _vp],
+    "pcb_linear_rows_bf16": [_vp, _i64, _vp, _i64, _i64, _i, _i, _i, _vp, _i64, _vp],
+    "pcb_linear_bn_stats_rows_bf16": [_vp, _i64, _vp, _i64, _i64, _i, _i, _i, _vp, _i64, _i, _vp, _f, _f, _vp, _vp, _vp, _vp,
+                                      _vp, _vp, _vp],
+    "pcb_dgrad_bn_rows_bf16": [_vp, _i64, _vp, _i64, _i64, _i, _i, _i, _vp, _i64, _vp, _vp, _vp, _vp, _i, _i, _vp, _i64,
+                               _vp, _vp, _vp, _vp],
+    "pcb_bn_apply_rows": [_vp, _i, _i64, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _i64, _vp, _vp],
+    "pcb_bn_bwd_apply_rows": [_vp, _vp, _i, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp],
     "pcb_scene_window_count_f32": [_vp, _i64, _i, _i, _i, _vp, _vp, _vp, _vp, _d, _d, _d, _i, _vp, _vp],
     "pcb_scene_window_fill_f32": [_vp, _i64, _i, _i, _i, _vp, _vp, _vp, _vp, _d, _d, _d, _i, _vp, _vp, _vp, _vp],
     "pcb_scene_blocks_f32": [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i64, _i, _d, _d, _d, _vp, _vp, _vp],
@@ -56,7 +63,8 @@ _SIGNATURES = {
     "pcb_bn_bwd_rows": [_vp, _i64, _vp, _vp, _i, _i64, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp],
 }
 
-EXPORTS = ["pcb_version", "pcb_error_string", "pcb_bn_work_floats", "pcb_nll_rows_blocks", *_SIGNATURES]
+EXPORTS = ["pcb_version", "pcb_error_string", "pcb_bn_work_floats", "pcb_nll_rows_blocks", "pcb_gemm_work_floats",
+           "pcb_gemm_tickets", *_SIGNATURES]
 
 
 class PcbError(RuntimeError):
@@ -80,6 +88,10 @@ def lib():
         l.pcb_bn_work_floats.argtypes = [_i]
         l.pcb_nll_rows_blocks.restype = _i
         l.pcb_nll_rows_blocks.argtypes = [_i64]
+        l.pcb_gemm_work_floats.restype = _i64
+        l.pcb_gemm_work_floats.argtypes = [_i64, _i, _i]
+        l.pcb_gemm_tickets.restype = _i
+        l.pcb_gemm_tickets.argtypes = []
         for name, args in _SIGNATURES.items():
             fn = getattr(l, name)
             fn.restype = _i

@@ -16,7 +16,7 @@ __global__ void __launch_bounds__(256)
 adam_flat_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m, float *__restrict__ v,
                  int64_t n, const float *__restrict__ lr_ptr, float beta1, float beta2, float eps, float weight_decay,
                  const int64_t *__restrict__ step_ptr, const int *__restrict__ shadow_index,
-                 __nv_bfloat16 *__restrict__ shadow)
+                 const int *__restrict__ shadow_index_t, __nv_bfloat16 *__restrict__ shadow)
 {
     const float step = (float)step_ptr[0];
     const float lr = lr_ptr[0];
@@ -35,7 +35,11 @@ adam_flat_kernel(float *__restrict__ p, const float *__restrict__ g, float *__re
         p[i] = pi, m[i] = mi, v[i] = vi;
         if (shadow_index) {
             const int s = shadow_index[i];
-            if (s >= 0) shadow[s] = __float2bfloat16(pi);
+            if (s >= 0) {
+                const __nv_bfloat16 b = __float2bfloat16(pi);
+                shadow[s] = b;
+                if (shadow_index_t) shadow[shadow_index_t[i]] = b;            // transposed copy (dgrad operand)
+            }
         }
     }
 }
@@ -44,7 +48,8 @@ adam_flat_kernel(float *__restrict__ p, const float *__restrict__ g, float *__re
 
 PCB_API int pcb_adam_flat_f32(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, int64_t n,
                               const float *lr, float beta1, float beta2, float eps, float weight_decay,
-                              const int64_t *step, const int *shadow_index, void *shadow_bf16, pcb_stream_t stream)
+                              const int64_t *step, const int *shadow_index, const int *shadow_index_t, void *shadow_bf16,
+                              pcb_stream_t stream)
 {
     using namespace pcb;
     PCB_REQUIRE(param && grad && exp_avg && exp_avg_sq && lr && step, PCB_EINVAL);
@@ -54,6 +59,6 @@ PCB_API int pcb_adam_flat_f32(float *param, const float *grad, float *exp_avg, f
     if (blocks > cap) blocks = cap;
     adam_flat_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2,
                                                                         eps, weight_decay, step, shadow_index,
-                                                                        (__nv_bfloat16 *)shadow_bf16);
+                                                                        shadow_index_t, (__nv_bfloat16 *)shadow_bf16);
     PCB_RETURN_LAUNCH_STATUS();
 }

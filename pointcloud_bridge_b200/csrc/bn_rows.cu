@@ -729,6 +729,124 @@ bn_bwd_fused_kernel(const BnBwdArgs a)
 }
 
 // ---------------------------------------------------------------------------------------------
+// Elementwise halves on their own (ordinary launches, no grid barrier): used when the per-channel statistics come
+// out of the epilogue of the tensor-core GEMM that produced y (gemm_rows.cu: EPI_STATS forward, EPI_BNBWD backward).
+// ---------------------------------------------------------------------------------------------
+template <typename T, int V>
+__global__ void __launch_bounds__(kBnThreads)
+bn_apply_rows_kernel(const BnFwdArgs a)
+{
+    const int C = a.C;
+    __shared__ float s_buf[2][kBnThreads][V];
+    float *s_const = nullptr;
+    if (C <= kBnThreads * V) {
+        s_const = &s_buf[0][0][0];
+        for (int c = threadIdx.x; c < C; c += kBnThreads) {
+            const bool real = c < a.Cv;                     // pad channels (zero columns of y) produce zeros
+            const float sc = real ? a.invstd[c] * a.gamma[c] : 0.f;
+            s_const[c] = sc;
+            s_const[C + c] = real ? a.beta[c] - a.mean[c] * sc : 0.f;
+        }
+        __syncthreads();
+    }
+    if (a.pool_k > 1) {
+        FwdApplyPooled<T, V, 8> f;
+        f.y = (const T *)a.y, f.out = (T *)a.out, f.mean = a.mean, f.invstd = a.invstd, f.gamma = a.gamma, f.beta = a.beta;
+        f.C = C, f.relu = a.relu, f.argmax = a.argmax, f.pool_k = a.pool_k, f.s_const = s_const, f.opitch = a.out_pitch;
+        row_stream<V, 1>(f, a.M / a.pool_k, C);
+    } else {
+        FwdApply<T, V> f;
+        f.y = (const T *)a.y, f.out = (T *)a.out, f.mean = a.mean, f.invstd = a.invstd, f.gamma = a.gamma, f.beta = a.beta;
+        f.C = C, f.relu = a.relu, f.s_const = s_const, f.opitch = a.out_pitch;
+        row_stream<V, PCB_BN_U>(f, a.M, C);
+    }
+}
+
+// gy = gamma * invstd * (dy - sum_dy / M - yhat * sum_dy_yhat / M) from the masked gradient dy (gy may alias dy)
+template <typename T, int V>
+struct BwdApplyDy {
+    struct Pack {
+        typename VecIO<T, V>::Raw y, d;
+    };
+    const T *y, *dy;
+    T *gy;
+    const float *s_const;                                   // shared [nm | is | g_is | a0 | a1] x C
+    int C;
+    float nm[V], is[V], gi[V], a0[V], a1[V];
+    __device__ __forceinline__ void init(int c)
+    {
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+            nm[i] = s_const[c + i], is[i] = s_const[C + c + i], gi[i] = s_const[2 * C + c + i];
+            a0[i] = s_const[3 * C + c + i], a1[i] = s_const[4 * C + c + i];
+        }
+    }
+    __device__ __forceinline__ Pack load(int64_t r, int c) const
+    {
+        Pack p;
+        p.y = VecIO<T, V>::ldraw(y + r * C + c);
+        p.d = VecIO<T, V>::ldraw(dy + r * C + c);
+        return p;
+    }
+    __device__ __forceinline__ void emit(const Pack &p, int64_t r, int c) const
+    {
+        float v[V], d[V], o[V];
+        VecIO<T, V>::cvt(p.y, v);
+        VecIO<T, V>::cvt(p.d, d);
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+            const float yh = fmaf(v[i], is[i], nm[i]);
+            o[i] = gi[i] * fmaf(-yh, a1[i], d[i] - a0[i]);
+        }
+        VecIO<T, V>::store(gy + r * C + c, o);
+    }
+};
+
+struct BnBwdApplyArgs {
+    const void *dy, *y;
+    void *gy;
+    const float *mean, *invstd, *gamma, *sums;              // sums: [>= 2][C] = sum dy, sum dy*yhat
+    int64_t M;
+    int C, Cv;
+};
+
+constexpr int kBnApplyMaxC = 1024;
+
+template <typename T, int V>
+__global__ void __launch_bounds__(kBnThreads)
+bn_bwd_apply_rows_kernel(const BnBwdApplyArgs a)
+{
+    const int C = a.C;
+    __shared__ float s_const[5 * kBnApplyMaxC];
+    const float invM = 1.f / (float)a.M;
+    for (int c = threadIdx.x; c < C; c += kBnThreads) {
+        const bool real = c < a.Cv;                         // pad channel: every constant zero -> gy = 0
+        const float is = real ? a.invstd[c] : 0.f;
+        s_const[c] = real ? -a.mean[c] * is : 0.f;
+        s_const[C + c] = is;
+        s_const[2 * C + c] = real ? is * a.gamma[c] : 0.f;
+        s_const[3 * C + c] = real ? a.sums[c] * invM : 0.f;
+        s_const[4 * C + c] = real ? a.sums[C + c] * invM : 0.f;
+    }
+    __syncthreads();
+    BwdApplyDy<T, V> f;
+    f.y = (const T *)a.y, f.dy = (const T *)a.dy, f.gy = (T *)a.gy, f.s_const = s_const, f.C = C;
+    row_stream<V, PCB_BN_UB>(f, a.M, C);
+}
+
+// grid of an elementwise launch: every thread row gets work, at most 8 CTAs per SM
+static int stream_grid(int64_t units, int C, int V)
+{
+    const int CV = C / V;
+    const int TX = CV < kBnThreads ? CV : kBnThreads;
+    const int TY = kBnThreads / TX;
+    const int64_t want = ceil_div(units, (int64_t)TY * 4);
+    const int64_t cap = (int64_t)PCB_NUM_SMS * 8;
+    const int64_t g = want < cap ? want : cap;
+    return g < 1 ? 1 : (int)g;
+}
+
+// ---------------------------------------------------------------------------------------------
 // launch
 // ---------------------------------------------------------------------------------------------
 // co-resident CTAs of `kernel` on the current device (cooperative launch limit), capped at
@@ -858,4 +976,51 @@ PCB_API int pcb_bn_bwd_rows(const void *gz, int64_t gz_pitch, const void *y, con
     if (!dtype) return bn_bwd_launch<float, 4>(a, st);
     if (C % 8 == 0 && a.gz_pitch % 8 == 0 && al16(y) && al16(gz) && al16(gy)) return bn_bwd_launch<__nv_bfloat16, 8>(a, st);
     return bn_bwd_launch<__nv_bfloat16, 4>(a, st);
+}
+
+// Elementwise half of the forward pass with given statistics (mean / invstd from the GEMM epilogue):
+// out = [max over pool_k rows of] act(BN(y)); ordinary launch.
+PCB_API int pcb_bn_apply_rows(const void *y, int dtype, int64_t M, int C, int Cv, int pool_k, const float *mean,
+                              const float *invstd, const float *gamma, const float *beta, int relu, void *out,
+                              int64_t out_pitch, unsigned char *argmax, pcb_stream_t stream)
+{
+    PCB_REQUIRE(y && gamma && beta && mean && invstd && out, PCB_EINVAL);
+    PCB_BN_CHECK(M, C, pool_k);
+    PCB_REQUIRE(Cv > 0 && Cv <= C && (Cv == C || C <= 1024), PCB_ERANGE);
+    BnFwdArgs a = {};
+    a.y = y, a.out = out, a.argmax = argmax, a.gamma = gamma, a.beta = beta;
+    a.mean = const_cast<float *>(mean), a.invstd = const_cast<float *>(invstd), a.M = M, a.C = C, a.Cv = Cv;
+    a.pool_k = pool_k, a.relu = relu, a.out_pitch = out_pitch > 0 ? out_pitch : C;
+    PCB_REQUIRE(a.out_pitch >= C && a.out_pitch % 4 == 0, PCB_ERANGE);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t units = M / pool_k;
+    if (!dtype) {
+        bn_apply_rows_kernel<float, 4><<<stream_grid(units, C, 4), kBnThreads, 0, st>>>(a);
+    } else if (C % 8 == 0 && a.out_pitch % 8 == 0 && al16(y) && al16(out)) {
+        bn_apply_rows_kernel<__nv_bfloat16, 8><<<stream_grid(units, C, 8), kBnThreads, 0, st>>>(a);
+    } else {
+        bn_apply_rows_kernel<__nv_bfloat16, 4><<<stream_grid(units, C, 4), kBnThreads, 0, st>>>(a);
+    }
+    PCB_RETURN_LAUNCH_STATUS();
+}
+
+// Elementwise half of the backward pass: gy = gamma * invstd * (dy - sums[0] / M - yhat * sums[1] / M) from the masked
+// gradient dy and the column sums that the data-gradient GEMM's epilogue produced (pcb_dgrad_bn_rows_bf16).  gy may be dy.
+PCB_API int pcb_bn_bwd_apply_rows(const void *dy, const void *y, int dtype, int64_t M, int C, int Cv, const float *mean,
+                                  const float *invstd, const float *gamma, const float *sums, void *gy, pcb_stream_t stream)
+{
+    PCB_REQUIRE(dy && y && mean && invstd && gamma && sums && gy, PCB_EINVAL);
+    PCB_REQUIRE(M > 0 && C > 0 && C % 4 == 0 && C <= kBnApplyMaxC && (dtype == 0 || dtype == 1), PCB_ERANGE);
+    PCB_REQUIRE(Cv > 0 && Cv <= C, PCB_ERANGE);
+    BnBwdApplyArgs a;
+    a.dy = dy, a.y = y, a.gy = gy, a.mean = mean, a.invstd = invstd, a.gamma = gamma, a.sums = sums, a.M = M, a.C = C, a.Cv = Cv;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!dtype) {
+        bn_bwd_apply_rows_kernel<float, 4><<<stream_grid(M, C, 4), kBnThreads, 0, st>>>(a);
+    } else if (C % 8 == 0 && al16(y) && al16(dy) && al16(gy)) {
+        bn_bwd_apply_rows_kernel<__nv_bfloat16, 8><<<stream_grid(M, C, 8), kBnThreads, 0, st>>>(a);
+    } else {
+        bn_bwd_apply_rows_kernel<__nv_bfloat16, 4><<<stream_grid(M, C, 4), kBnThreads, 0, st>>>(a);
+    }
+    PCB_RETURN_LAUNCH_STATUS();
 }

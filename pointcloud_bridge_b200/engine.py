@@ -75,14 +75,14 @@ class FlatAdam:
     runner, train_MulSca_BriStruNet_CB.py:181)."""
 
     def __init__(self, flat_param, flat_grad, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0,
-                 shadow_index=None, shadow_flat=None):
+                 shadow_index=None, shadow_flat=None, shadow_index_t=None):
         self.p, self.g = flat_param, flat_grad
         self.exp_avg = torch.zeros_like(flat_param)
         self.exp_avg_sq = torch.zeros_like(flat_param)
         self.step_t = torch.zeros(1, dtype=torch.long, device=flat_param.device)
         self.lr_t = torch.full((1,), float(lr), dtype=torch.float32, device=flat_param.device)
         self.betas, self.eps, self.weight_decay = betas, eps, weight_decay
-        self.shadow_index, self.shadow_flat = shadow_index, shadow_flat
+        self.shadow_index, self.shadow_flat, self.shadow_index_t = shadow_index, shadow_flat, shadow_index_t
 
     def set_lr(self, lr: float) -> None:
         self.lr_t.fill_(float(lr))
@@ -96,6 +96,7 @@ class FlatAdam:
                   self.exp_avg_sq.data_ptr(), self.p.numel(), self.lr_t.data_ptr(), float(self.betas[0]),
                   float(self.betas[1]), float(self.eps), float(self.weight_decay), self.step_t.data_ptr(),
                   self.shadow_index.data_ptr() if self.shadow_index is not None else None,
+                  self.shadow_index_t.data_ptr() if self.shadow_index_t is not None and self.shadow_index is not None else None,
                   self.shadow_flat.data_ptr() if self.shadow_index is not None else None,
                   alg_bytes=self.p.numel() * 32)
 
@@ -147,7 +148,8 @@ class Trainer:
         self._ctx.refresh_shadows()
         self._ctx.external_refresh = True          # from here on the Adam kernel keeps the bf16 shadows current
         self.opt = FlatAdam(self.flat_param.detach(), self.bucket.flat, lr=lr, weight_decay=weight_decay,
-                            shadow_index=self._ctx.shadow_index, shadow_flat=self._ctx.shadow_flat)
+                            shadow_index=self._ctx.shadow_index, shadow_flat=self._ctx.shadow_flat,
+                            shadow_index_t=self._ctx.shadow_index_t)
         self._g = None                 # captured (zero, forward, loss, backward[, Adam]) graph
         self._static = None
         self._starts = FpsStartBuffers()

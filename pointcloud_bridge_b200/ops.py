@@ -830,9 +830,13 @@ class StepContext:
         shapes = [(p.shape[0], p[0].numel()) for p in params]
         sizes = [(-(-n // 8) * 8) * (-(-k // 8) * 8) for n, k in shapes]
         total = sum(sizes)
-        self.shadow_flat = torch.zeros(max(total, 1), dtype=torch.bfloat16, device=p0.device) if params else None
+        # second half of the buffer: the same weights transposed ([k8, n8]) -- the B operand of the data-gradient
+        # GEMM (csrc/gemm_rows.cu reads both operands K-major)
+        self.shadow_flat = torch.zeros(max(2 * total, 1), dtype=torch.bfloat16, device=p0.device) if params else None
         self.dense, self.dense_shadows, self.ragged = [], [], []
-        self.by_id = {}
+        self.by_id, self.by_id_t = {}, {}
+        self.shadow_index_t = None
+        index_t = None
         # element i of the runner's flat parameter buffer -> element of shadow_flat (or -1): lets the fused
         # Adam kernel (csrc/adam.cu) refresh the shadows while it writes the updated parameters
         self.shadow_index = None
@@ -840,11 +844,14 @@ class StepContext:
         if params and flat_offsets is not None:
             import numpy as np
             index = np.full(flat_numel, -1, dtype=np.int32)
+            index_t = np.full(flat_numel, -1, dtype=np.int32)
         off = 0
         for p, (n, k), size in zip(params, shapes, sizes):
             k8 = -(-k // 8) * 8
+            n8 = -(-n // 8) * 8
             sh = self.shadow_flat[off:off + size].view(-1, k8)
             self.by_id[id(p)] = sh
+            self.by_id_t[id(p)] = self.shadow_flat[total + off:total + off + size].view(k8, n8)
             if k8 == k:
                 self.dense.append(p)
                 self.dense_shadows.append(sh[:n])
@@ -853,9 +860,12 @@ class StepContext:
             if index is not None and id(p) in flat_offsets:
                 j = np.arange(n * k, dtype=np.int64)
                 index[flat_offsets[id(p)]:flat_offsets[id(p)] + n * k] = (off + (j // k) * k8 + (j % k)).astype(np.int32)
+                index_t[flat_offsets[id(p)]:flat_offsets[id(p)] + n * k] = \
+                    (total + off + (j % k) * n8 + (j // k)).astype(np.int32)
             off += size
         if index is not None:
             self.shadow_index = torch.from_numpy(index).to(p0.device)
+            self.shadow_index_t = torch.from_numpy(index_t).to(p0.device)
         self.external_refresh = False      # True: the optimizer kernel keeps the shadows current (engine.Trainer)
 
     def refresh_shadows(self):
@@ -865,6 +875,9 @@ class StepContext:
                 torch._foreach_copy_(self.dense_shadows, [p.detach().flatten(1) for p in self.dense])
             for p, view in self.ragged:
                 view.copy_(p.detach().flatten(1))
+            for pid, sh in self.by_id.items():
+                t = self.by_id_t[pid]
+                t.copy_(sh.t())
 
     def __enter__(self):
         global _step_ctx
@@ -884,6 +897,10 @@ class StepContext:
     def shadow(self, w):
         base = w._base if w._base is not None else w
         return self.by_id.get(id(base))
+
+    def shadow_t(self, w):
+        base = w._base if w._base is not None else w
+        return self.by_id_t.get(id(base))
 
     def grad_view(self, w):
         base = w._base if w._base is not None else w
@@ -918,11 +935,72 @@ def wgrad_rows(gy, x, k: int | None = None, out: torch.Tensor | None = None, n: 
     return out
 
 
+# ---------------------------------------------------------------------------------------------
+# tensor-core GEMMs on rows (csrc/gemm_rows.cu): tcgen05.mma, fp32 accumulation in TMEM, BatchNorm sums in the epilogue
+# ---------------------------------------------------------------------------------------------
+_OWN_GEMM = os.environ.get("PCB_NO_OWN_GEMM", "0") != "1"     # debugging aid: library GEMM + cooperative BN kernels
+_ticket_pool: dict[int, list] = {}
+
+
+def _tickets(dev: torch.device) -> torch.Tensor:
+    """Zeroed counter words for one statistics GEMM (the kernel leaves them zeroed).  4096 slots handed out round
+    robin: launches that could overlap never share a slot.  Created on first use -- before any graph capture, because
+    the warm-up steps of a runner are eager."""
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    st = _ticket_pool.get(key)
+    if st is None:
+        n = _lib.lib().pcb_gemm_tickets()
+        st = [torch.zeros(4096 * n, dtype=torch.int32, device=dev), 0, n]
+        _ticket_pool[key] = st
+    buf, pos, n = st
+    st[1] = (pos + 1) % 4096
+    return buf[pos * n:(pos + 1) * n]
+
+
+def _ru8(n: int) -> int:
+    return -(-n // 8) * 8
+
+
+def _weight_pair(w: torch.Tensor):
+    """(w as bf16 [n8, k8], its transpose [k8, n8]), zero padded: the step runner's shadows, or cast on the spot."""
+    w2 = w.flatten(1)
+    if _step_ctx is not None:
+        a, b = _step_ctx.shadow(w), _step_ctx.shadow_t(w)
+        if a is not None and b is not None:
+            return a, b
+    n, k = w2.shape
+    a = torch.zeros(_ru8(n), _ru8(k), dtype=torch.bfloat16, device=w.device)
+    a[:n, :k] = w2.detach()
+    return a, a.t().contiguous()
+
+
+def _rows_ok(t: torch.Tensor) -> bool:
+    return (t.is_cuda and t.dtype == torch.bfloat16 and t.dim() == 2 and t.stride(1) == 1 and t.stride(0) % 8 == 0
+            and t.stride(0) >= t.shape[1] and t.data_ptr() % 16 == 0 and t.shape[1] % 8 == 0)
+
+
+def own_gemm_supported(x: torch.Tensor) -> bool:
+    return _OWN_GEMM and _rows_ok(x) and x.shape[0] > 0
+
+
+@torch.no_grad()
+def gemm_rows(x, w, n_out: int, out: torch.Tensor | None = None) -> torch.Tensor:
+    """x [M, K] @ w [Nw, Kw]^T -> [M, n_out] bf16 (contraction over min(K, Kw) columns; rows of w beyond Nw count as
+    zero).  x, w: bf16 rows, 16-byte aligned, multiples of 8 columns."""
+    M = x.shape[0]
+    if out is None:
+        out = torch.empty(M, n_out, dtype=torch.bfloat16, device=x.device)
+    K = min(x.shape[1], w.shape[1])
+    _call("pcb_linear_rows_bf16", x.device, x.data_ptr(), x.stride(0), w.data_ptr(), w.stride(0), M, int(n_out),
+          min(w.shape[0], n_out), K, out.data_ptr(), out.stride(0), alg_bytes=2 * M * (K + n_out) + 2 * w.numel())
+    return out
+
+
 class _LinearRows(torch.autograd.Function):
-    """F.linear without bias for x [M,K], W [N,K] with M in the 10^5..10^6 range.  The weight
-    gradient gy^T x reduces over M: reducing 2048-row chunks as one batched GEMM and summing the
-    chunk results keeps every SM busy with short reductions.  x may carry zero pad columns beyond
-    K (`group_points(pad_to=8)`): the weight is padded to match and its gradient sliced back."""
+    """F.linear without bias for x [M,K], W [N,K] with M in the 10^5..10^6 range: forward and data gradient on the
+    tcgen05 GEMM of csrc/gemm_rows.cu (bf16), weight gradient on the row kernel of csrc/wgrad.cu (the contraction over
+    M).  x may carry zero pad columns beyond K (`group_points(pad_to=8)`): the weight is padded to match.  fp32 inputs
+    (parity mode) go to the library GEMM."""
 
     @staticmethod
     def forward(ctx, x, w, w_lp, gview=None, pad_n=False):
@@ -931,6 +1009,14 @@ class _LinearRows(torch.autograd.Function):
         # pad_n: emit n8 output columns (zero pad columns) instead of n
         ctx.gview = gview
         n = w.shape[0]
+        ctx.kw = w.shape[1]
+        ctx.n = n
+        n_out = _ru8(n) if pad_n else n
+        ctx.own = own_gemm_supported(x) and n_out % 8 == 0
+        if ctx.own:
+            wl, wt = _weight_pair(w)
+            ctx.save_for_backward(x, wt)
+            return gemm_rows(x, wl, n_out)
         if w_lp is not None:
             wl = w_lp if pad_n else w_lp[:n]
         else:
@@ -940,19 +1026,17 @@ class _LinearRows(torch.autograd.Function):
         elif wl.shape[1] < x.shape[1]:
             wl = torch.nn.functional.pad(wl, (0, x.shape[1] - wl.shape[1]))
         ctx.save_for_backward(x, wl)
-        ctx.kw = w.shape[1]
-        ctx.n = n
         return torch.mm(x, wl.t())
 
     @staticmethod
     def backward(ctx, gy):
-        x, wl = ctx.saved_tensors
+        x, wl = ctx.saved_tensors                         # own path: wl is the transposed weight [k8, n8]
         gx = gw = None
         gy = gy.contiguous()
         if gy.dtype != x.dtype:
             gy = gy.to(x.dtype)
         if ctx.needs_input_grad[0]:
-            gx = torch.mm(gy, wl)
+            gx = gemm_rows(gy, wl, x.shape[1]) if ctx.own else torch.mm(gy, wl)
         if ctx.needs_input_grad[1]:
             M = x.shape[0]
             c = _WGRAD_CHUNK
@@ -982,4 +1066,174 @@ def linear_rows(x, w, pad_n: bool = False):
         x = x if x.dtype == dt else x.to(dt)
     w_lp = _step_ctx.shadow(w) if (_step_ctx is not None and x.dtype == torch.bfloat16) else None
     gview = _step_ctx.grad_view(w) if (_step_ctx is not None and x.dtype == torch.bfloat16) else None
-    return _LinearRows.apply(x, w, w_lp, gview, bool(pad_n and w_lp is not None and _PAD_N))
+    pad = bool(pad_n and _PAD_N and (w_lp is not None or (own_gemm_supported(x) and x.dtype == torch.bfloat16)))
+    return _LinearRows.apply(x, w, w_lp, gview, pad)
+
+
+# ---------------------------------------------------------------------------------------------
+# shared MLP on rows in training mode: (1x1 conv -> BatchNorm -> ReLU) x L [-> max over pool_k rows], one autograd node
+# ---------------------------------------------------------------------------------------------
+def mlp_rows_fused_supported(x, convs, bns, pool_k: int = 1) -> bool:
+    """bf16 training path of the tensor-core GEMMs: CUDA rows under bf16 autocast, every layer a training-mode
+    affine BatchNorm with momentum."""
+    if not (_OWN_GEMM and x.is_cuda and x.dim() == 2 and x.shape[0] > 1 and x.shape[0] % pool_k == 0 and 1 <= pool_k <= 255):
+        return False
+    if not (x.dtype == torch.bfloat16 or (torch.is_autocast_enabled() and torch.get_autocast_dtype("cuda") == torch.bfloat16)):
+        return False
+    if x.shape[1] > 8192 or x.numel() // 4 >= 2 ** 31:
+        return False
+    for conv, bn in zip(convs, bns):
+        if not (bn.training and bn.affine and bn.momentum is not None and _ru8(conv.weight.shape[0]) <= 1024):
+            return False
+    k0 = convs[0].weight[0].numel()
+    return k0 <= x.shape[1] <= _ru8(k0)
+
+
+class _MlpRows(torch.autograd.Function):
+    """x [M, K0] -> out [M / pool_k, n8_L]: L layers of (bias-free 1x1 conv on the tcgen05 GEMM with the BatchNorm
+    statistics in its epilogue) + (normalise + ReLU [+ max over pool_k rows on the last layer] as one elementwise
+    kernel).  Backward: BatchNorm backward of the last layer (cooperative row kernel), then per layer the weight
+    gradient (row kernel) and the data gradient GEMM whose epilogue applies the previous layer's ReLU mask and produces
+    the two BatchNorm sums, followed by one elementwise kernel.  Replaces pointnet_util.py:213-217 / 273-279 / 343-345
+    in training mode.  Tensor arguments after `x`: per layer conv.weight, conv.bias | None, bn.weight, bn.bias."""
+
+    @staticmethod
+    def forward(ctx, x, pool_k, out, layers, *params):
+        L = len(layers)
+        dev = x.device
+        ctx.in_cols, ctx.in_dtype = x.shape[1], x.dtype
+        if x.dtype != torch.bfloat16:
+            x = x.to(torch.bfloat16)
+        if x.shape[1] % 8:
+            x = torch.nn.functional.pad(x, (0, -x.shape[1] % 8))
+        if not _rows_ok(x):
+            x = x.contiguous()
+        M = x.shape[0]
+        lib = _lib.lib()
+        saved, metas = [x], []
+        cur = x
+        for l, (conv, bn) in enumerate(layers):
+            w = conv.weight
+            n = w.shape[0]
+            n8 = _ru8(n)
+            wl, wt = _weight_pair(w)
+            K = min(cur.shape[1], wl.shape[1])
+            y = torch.empty(M, n8, dtype=torch.bfloat16, device=dev)
+            stats = torch.empty(2, n8, dtype=torch.float32, device=dev)
+            work = torch.empty(max(int(lib.pcb_gemm_work_floats(M, n8, K)), 1), dtype=torch.float32, device=dev)
+            tick = _tickets(dev)
+            track = bn.track_running_stats
+            if track and bn.num_batches_tracked is not None:
+                if _step_ctx is not None:
+                    _step_ctx.counters.append(bn.num_batches_tracked)
+                else:
+                    bn.num_batches_tracked.add_(1)
+            g32, b32 = params[4 * l + 2].detach().float(), params[4 * l + 3].detach().float()
+            bias = params[4 * l + 1]
+            _call("pcb_linear_bn_stats_rows_bf16", dev, cur.data_ptr(), cur.stride(0), wl.data_ptr(), wl.stride(0), M, n8,
+                  min(wl.shape[0], n8), K, y.data_ptr(), y.stride(0), n,
+                  bias.data_ptr() if bias is not None else None, float(bn.eps), float(bn.momentum),
+                  bn.running_mean.data_ptr() if track else None, bn.running_var.data_ptr() if track else None,
+                  stats[0].data_ptr(), stats[1].data_ptr(), work.data_ptr(), tick.data_ptr(),
+                  alg_bytes=2 * M * (K + n8) + 2 * wl.numel())
+            last = l == L - 1
+            pk = pool_k if last else 1
+            Mo = M // pk
+            z = None
+            if last and out is not None and out.dtype == torch.bfloat16 and tuple(out.shape) == (Mo, n8) \
+                    and out.stride(1) == 1 and out.stride(0) % 8 == 0 and out.data_ptr() % 16 == 0:
+                z = out
+            if z is None:
+                z = torch.empty(Mo, n8, dtype=torch.bfloat16, device=dev)
+            argmax = torch.empty(Mo, n8, dtype=torch.uint8, device=dev) if pk > 1 else None
+            _call("pcb_bn_apply_rows", dev, y.data_ptr(), 1, M, n8, n, pk, stats[0].data_ptr(), stats[1].data_ptr(),
+                  g32.data_ptr(), b32.data_ptr(), 1, z.data_ptr(), z.stride(0),
+                  argmax.data_ptr() if argmax is not None else None,
+                  alg_bytes=2 * (M + Mo) * n8 + (Mo * n8 if pk > 1 else 0))
+            saved += [y, stats, g32, b32, wt]
+            if not last:
+                saved.append(z)
+            else:
+                saved.append(argmax if argmax is not None else stats)      # placeholder keeps the layout regular
+            metas.append((n, n8, K, bias is not None, _step_ctx.grad_view(w) if _step_ctx is not None else None,
+                          tuple(w.shape)))
+            cur = z
+        ctx.save_for_backward(*saved)
+        ctx.metas, ctx.pool_k, ctx.M = metas, int(pool_k), M
+        return cur
+
+    @staticmethod
+    def backward(ctx, gout):
+        sv = ctx.saved_tensors
+        x0 = sv[0]
+        L = len(ctx.metas)
+        M, pool_k = ctx.M, ctx.pool_k
+        dev = x0.device
+        lib = _lib.lib()
+        grads = [None] * (4 * L)
+        lay = lambda l: sv[1 + 6 * l:1 + 6 * (l + 1)]          # y, stats, gamma, beta, w^T, z | argmax
+        # ---- last layer: BatchNorm (+ ReLU, + max-pool routing) backward from the incoming gradient
+        y, stats, g32, b32, wt, extra = lay(L - 1)
+        n, n8, K, has_bias, gview, wshape = ctx.metas[L - 1]
+        argmax = extra if pool_k > 1 else None
+        gz = gout if gout.dtype == torch.bfloat16 else gout.to(torch.bfloat16)
+        if not (gz.dim() == 2 and gz.stride(1) == 1 and gz.stride(0) >= n8 and gz.stride(0) % 8 == 0
+                and gz.data_ptr() % 16 == 0):
+            gz = gz.contiguous()
+        gy = torch.empty_like(y)
+        work = _bn_work(n8, dev)
+        _call("pcb_bn_bwd_rows", dev, gz.data_ptr(), gz.stride(0), y.data_ptr(),
+              argmax.data_ptr() if argmax is not None else None, 1, M, n8, n, pool_k, stats[0].data_ptr(),
+              stats[1].data_ptr(), g32.data_ptr(), b32.data_ptr(), 1, work.data_ptr(), gy.data_ptr(),
+              alg_bytes=(2 * y.numel() + gz.numel()) * 2 + (gz.numel() if pool_k > 1 else 0))
+        sums = work[:3 * n8].view(3, n8)
+        for l in range(L - 1, -1, -1):
+            n, n8, K, has_bias, gview, wshape = ctx.metas[l]
+            wt = lay(l)[4]
+            xin = lay(l - 1)[5] if l > 0 else x0
+            grads[4 * l + 1] = sums[2, :n] if has_bias else None
+            grads[4 * l + 2] = sums[1, :n]
+            grads[4 * l + 3] = sums[0, :n]
+            # weight gradient: gy^T xin over the rows
+            kw = 1
+            for d in wshape[1:]:
+                kw *= d
+            if gview is not None:
+                wgrad_rows(gy, xin, kw, out=gview.view(n, kw), n=n)
+            else:
+                grads[4 * l] = wgrad_rows(gy, xin, kw, n=n).view(wshape)
+            if l > 0:
+                # data gradient through the previous layer's BN + ReLU: dy and its two column sums from the GEMM epilogue
+                yp, statsp, gp, bp, _, _ = lay(l - 1)
+                npv, np8 = ctx.metas[l - 1][0], ctx.metas[l - 1][1]
+                dy = torch.empty_like(yp)
+                sums = torch.empty(3, np8, dtype=torch.float32, device=dev)
+                Kc = min(gy.shape[1], wt.shape[1])
+                work = torch.empty(max(int(lib.pcb_gemm_work_floats(M, np8, Kc)), 1), dtype=torch.float32, device=dev)
+                tick = _tickets(dev)
+                _call("pcb_dgrad_bn_rows_bf16", dev, gy.data_ptr(), gy.stride(0), wt.data_ptr(), wt.stride(0), M, np8,
+                      min(wt.shape[0], np8), Kc, yp.data_ptr(), yp.stride(0), statsp[0].data_ptr(), statsp[1].data_ptr(),
+                      gp.data_ptr(), bp.data_ptr(), npv, 1, dy.data_ptr(), dy.stride(0), sums.data_ptr(), work.data_ptr(),
+                      tick.data_ptr(), alg_bytes=2 * M * (Kc + 2 * np8) + 2 * wt.numel())
+                _call("pcb_bn_bwd_apply_rows", dev, dy.data_ptr(), yp.data_ptr(), 1, M, np8, npv, statsp[0].data_ptr(),
+                      statsp[1].data_ptr(), gp.data_ptr(), sums.data_ptr(), dy.data_ptr(), alg_bytes=6 * M * np8)
+                gy = dy
+        gx = None
+        if ctx.needs_input_grad[0]:
+            wt = lay(0)[4]
+            gx = gemm_rows(gy, wt, x0.shape[1])
+            if ctx.in_cols != gx.shape[1]:
+                gx = gx[:, :ctx.in_cols]
+            if gx.dtype != ctx.in_dtype:
+                gx = gx.to(ctx.in_dtype)
+        return (gx, None, None, None, *grads)
+
+
+def mlp_rows_fused(x, convs, bns, pool_k: int = 1, out=None):
+    """(1x1 conv -> BN(train) -> ReLU) per layer on rows, the last layer followed by the max over `pool_k` consecutive
+    rows; returns [M / pool_k, n8] bf16 with the last layer's width rounded up to 8 (zero pad columns)."""
+    layers = list(zip(convs, bns))
+    params = []
+    for conv, bn in layers:
+        params += [conv.weight, conv.bias, bn.weight, bn.bias]
+    return _MlpRows.apply(x, int(pool_k), out, layers, *params)

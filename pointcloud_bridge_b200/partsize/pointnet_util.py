@@ -119,6 +119,9 @@ def conv_bn_relu_rows(x, conv, bn, pool_k=1, out=None):
     groups of `pool_k` consecutive rows (the neighbour axis).  In training mode the elementwise
     half runs in libpcbridge's fused row kernels (csrc/bn_rows.cu): the conv bias is folded into
     the normalisation and ReLU / max-pool happen in the same pass."""
+    if ops.mlp_rows_fused_supported(x, [conv], [bn], pool_k):
+        # bf16 training: tcgen05 GEMM with the BatchNorm statistics in its epilogue + one elementwise kernel
+        return ops.mlp_rows_fused(x, [conv], [bn], pool_k, out)
     w = conv.weight.flatten(1)
     if ops._step_ctx is not None and x.is_cuda and x.shape[1] % 8 and bn.training:
         # inside a step runner: rows that are not a multiple of 8 channels wide (3 xyz / 9 / 259 concatenated
@@ -150,8 +153,11 @@ def mlp_rows(x, convs, bns, pool_k=1, out=None):
     slice of a wider buffer that the last layer's fused kernel writes into when it can (training mode; the
     result then IS `out`, which the caller checks by data pointer)."""
     n = len(convs)
-    for i, (conv, bn) in enumerate(zip(convs, bns)):
-        x = conv_bn_relu_rows(x, conv, bn, pool_k if i == n - 1 else 1, out if i == n - 1 else None)
+    if ops.mlp_rows_fused_supported(x, convs, bns, pool_k):
+        x = ops.mlp_rows_fused(x, convs, bns, pool_k, out)        # the whole stack as one autograd node
+    else:
+        for i, (conv, bn) in enumerate(zip(convs, bns)):
+            x = conv_bn_relu_rows(x, conv, bn, pool_k if i == n - 1 else 1, out if i == n - 1 else None)
     if x.shape[1] != convs[-1].weight.shape[0]:          # zero pad columns of the last layer are dropped
         x = x[:, :convs[-1].weight.shape[0]].contiguous()
     return x

@@ -1,0 +1,226 @@
+"""tcgen05 training GEMMs (csrc/gemm_rows.cu) and the BatchNorm halves around them against their PyTorch
+composition (fp32 reference of the same op on the same bf16 operands).
+
+Tolerances: the kernels accumulate in fp32 and round once to bf16, so a product must be within one bf16 ulp
+(2^-8 relative) + fp32 summation-order noise of the fp32 reference; statistics are compared with the statistics of
+the kernel's own bf16 output (they are defined on the stored values)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from pointcloud_bridge_b200 import _lib, ops
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+SHAPES = [  # (M, K, N): K, N multiples of 8
+    (129, 8, 8), (1000, 16, 16), (65536, 32, 64), (4173, 104, 200), (1024, 1536, 256), (300, 520, 512),
+    (8192, 264, 128), (128, 64, 1024), (40000, 200, 256), (77, 72, 24),
+]
+
+
+def bf16_close(a, ref, what=""):
+    a, ref = a.float(), ref.float()
+    tol = ref.abs() * 2.0 ** -7 + 2e-3 * ref.abs().max().clamp_min(1e-6) * 2.0 ** -7 + 1e-6
+    bad = (a - ref).abs() > tol
+    assert not bad.any(), (what, int(bad.sum()), float((a - ref).abs().max()), float(ref.abs().max()))
+
+
+@pytest.mark.parametrize("M,K,N", SHAPES)
+def test_gemm_rows_matches_fp32_matmul(M, K, N):
+    g = torch.Generator(device=DEV).manual_seed(M + K + N)
+    x = torch.randn(M, K, device=DEV, generator=g).to(torch.bfloat16)
+    w = (torch.randn(N, K, device=DEV, generator=g) / K ** 0.5).to(torch.bfloat16)
+    y = ops.gemm_rows(x, w, N)
+    ref = x.float() @ w.float().t()
+    bf16_close(y, ref, "plain")
+    # fewer weight rows than output columns: the missing rows count as zero; pitched operands
+    xw = torch.zeros(M, K + 16, device=DEV, dtype=torch.bfloat16)
+    xw[:, :K] = x
+    y2 = ops.gemm_rows(xw[:, :K], w[:max(N - 8, 8)], N)
+    ref2 = ref.clone()
+    ref2[:, max(N - 8, 8):] = 0
+    bf16_close(y2, ref2, "pitched / short weight")
+
+
+def _bn(n, seed):
+    bn = nn.BatchNorm1d(n).to(DEV).train()
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    with torch.no_grad():
+        bn.weight.copy_(torch.rand(n, generator=g) + 0.5)
+        bn.bias.copy_(torch.randn(n, generator=g) * 0.3)
+        bn.running_mean.copy_(torch.randn(n, generator=g) * 0.1)
+        bn.running_var.copy_(torch.rand(n, generator=g) + 0.5)
+    return bn
+
+
+@pytest.mark.parametrize("M,K,N", [(1000, 16, 16), (65536, 32, 64), (4173, 104, 200), (1024, 1536, 256), (300, 520, 512)])
+def test_linear_bn_stats_epilogue(M, K, N):
+    lib = _lib.lib()
+    g = torch.Generator(device=DEV).manual_seed(7 * M + K)
+    Cv = N - 4 if N == 200 else N                        # 196 real channels carried as 200
+    x = (torch.randn(M, K, device=DEV, generator=g) + 0.3).to(torch.bfloat16)
+    w = torch.zeros(N, K, device=DEV)
+    w[:Cv] = torch.randn(Cv, K, device=DEV, generator=g) / K ** 0.5
+    w = w.to(torch.bfloat16)
+    bias = torch.randn(Cv, device=DEV, generator=g)
+    rm0 = torch.randn(Cv, device=DEV, generator=g) * 0.1
+    rv0 = torch.rand(Cv, device=DEV, generator=g) + 0.5
+    outs = []
+    for rep in range(2):
+        rm, rv = rm0.clone(), rv0.clone()
+        y = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+        stats = torch.full((2, N), float("nan"), device=DEV)
+        work = torch.empty(max(int(lib.pcb_gemm_work_floats(M, N, K)), 1), device=DEV)
+        tick = ops._tickets(torch.device(DEV))
+        ops._call("pcb_linear_bn_stats_rows_bf16", x.device, x.data_ptr(), x.stride(0), w.data_ptr(), w.stride(0), M, N, N, K,
+                  y.data_ptr(), y.stride(0), Cv, bias.data_ptr(), 1e-5, 0.1, rm.data_ptr(), rv.data_ptr(),
+                  stats[0].data_ptr(), stats[1].data_ptr(), work.data_ptr(), tick.data_ptr())
+        torch.cuda.synchronize()
+        assert int(tick.abs().sum()) == 0                 # tickets are left zeroed
+        outs.append((y, stats, rm, rv))
+    y, stats, rm, rv = outs[0]
+    bf16_close(y, x.float() @ w.float().t(), "y")
+    yf = y.float()[:, :Cv]
+    mean, var = yf.mean(0), yf.var(0, unbiased=False)
+    assert torch.allclose(stats[0, :Cv], mean, rtol=1e-4, atol=1e-5 * float(yf.abs().max()))
+    assert torch.allclose(stats[1, :Cv], torch.rsqrt(var + 1e-5), rtol=2e-4)
+    assert torch.allclose(rm, 0.9 * rm0 + 0.1 * (mean + bias), rtol=1e-4, atol=1e-5)
+    assert torch.allclose(rv, 0.9 * rv0 + 0.1 * yf.var(0, unbiased=True), rtol=2e-4, atol=1e-6)
+    if Cv < N:
+        assert float(stats[:, Cv:].abs().max()) == 0.0
+    # deterministic: same bits on the second run
+    assert torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][0], outs[1][0])
+
+
+@pytest.mark.parametrize("M,K,N,relu", [(1000, 16, 16, 1), (65536, 64, 32, 1), (4173, 256, 200, 1), (300, 512, 520, 1),
+                                         (2048, 128, 128, 0)])
+def test_dgrad_bn_epilogue_and_apply(M, K, N, relu):
+    """gz = gy . wt^T through the previous layer's BN + ReLU: dy, the two column sums and the final gy."""
+    lib = _lib.lib()
+    g = torch.Generator(device=DEV).manual_seed(3 * M + N)
+    Cv = N - 4 if N == 200 else N
+    gy = torch.randn(M, K, device=DEV, generator=g).to(torch.bfloat16)
+    wt = torch.zeros(N, K, device=DEV)
+    wt[:Cv] = torch.randn(Cv, K, device=DEV, generator=g) / K ** 0.5
+    wt = wt.to(torch.bfloat16)
+    yprev = torch.zeros(M, N, device=DEV)
+    yprev[:, :Cv] = torch.randn(M, Cv, device=DEV, generator=g) * 1.3 + 0.2
+    yprev = yprev.to(torch.bfloat16)
+    yf = yprev.float()[:, :Cv]
+    mean, invstd = yf.mean(0).contiguous(), torch.rsqrt(yf.var(0, unbiased=False) + 1e-5).contiguous()
+    gamma = (torch.rand(Cv, device=DEV, generator=g) + 0.5).contiguous()
+    beta = (torch.randn(Cv, device=DEV, generator=g) * 0.3).contiguous()
+    dy = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+    sums = torch.full((3, N), float("nan"), device=DEV)
+    work = torch.empty(max(int(lib.pcb_gemm_work_floats(M, N, K)), 1), device=DEV)
+    tick = ops._tickets(torch.device(DEV))
+    ops._call("pcb_dgrad_bn_rows_bf16", gy.device, gy.data_ptr(), gy.stride(0), wt.data_ptr(), wt.stride(0), M, N, N, K,
+              yprev.data_ptr(), yprev.stride(0), mean.data_ptr(), invstd.data_ptr(), gamma.data_ptr(), beta.data_ptr(), Cv,
+              relu, dy.data_ptr(), dy.stride(0), sums.data_ptr(), work.data_ptr(), tick.data_ptr())
+    torch.cuda.synchronize()
+    gz = gy.float() @ wt.float().t()
+    yh = (yf - mean) * invstd
+    z = yh * gamma + beta
+    mask = (z > 0) if relu else torch.ones_like(z, dtype=torch.bool)
+    ref_dy = torch.zeros(M, N, device=DEV)
+    ref_dy[:, :Cv] = gz[:, :Cv] * mask
+    # elements whose activation sits within rounding of zero may be masked either way
+    edge = torch.zeros(M, N, device=DEV, dtype=torch.bool)
+    edge[:, :Cv] = z.abs() < 1e-5 * (1 + yf.abs())
+    d = dy.float()
+    tol = ref_dy.abs() * 2.0 ** -7 + 1e-5 * float(gz.abs().max())
+    assert not (((d - ref_dy).abs() > tol) & ~edge).any()
+    dq = d[:, :Cv]
+    assert torch.allclose(sums[0, :Cv], dq.sum(0), rtol=1e-4, atol=1e-4 * float(dq.abs().sum(0).max()))
+    assert torch.allclose(sums[1, :Cv], (dq * yh).sum(0), rtol=1e-4, atol=1e-4 * float((dq * yh).abs().sum(0).max()))
+    assert float(sums[2].abs().max()) == 0.0
+    if Cv < N:
+        assert float(sums[:, Cv:].abs().max()) == 0.0 and float(d[:, Cv:].abs().max()) == 0.0
+    # elementwise half, in place
+    out = dy.clone()
+    ops._call("pcb_bn_bwd_apply_rows", gy.device, out.data_ptr(), yprev.data_ptr(), 1, M, N, Cv, mean.data_ptr(),
+              invstd.data_ptr(), gamma.data_ptr(), sums.data_ptr(), out.data_ptr())
+    ref = gamma * invstd * (dq - sums[0, :Cv] / M - yh * sums[1, :Cv] / M)
+    o = out.float()
+    assert torch.allclose(o[:, :Cv], ref, rtol=2.0 ** -7, atol=2.0 ** -8 * float(ref.abs().max()))
+    if Cv < N:
+        assert float(o[:, Cv:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("M,C,Cv,pool_k", [(4096, 64, 64, 1), (8192, 200, 196, 32), (1024, 512, 512, 16), (300, 8, 5, 1)])
+def test_bn_apply_rows(M, C, Cv, pool_k):
+    g = torch.Generator(device=DEV).manual_seed(M + C)
+    y = torch.zeros(M, C, device=DEV)
+    y[:, :Cv] = torch.randn(M, Cv, device=DEV, generator=g)
+    y = y.to(torch.bfloat16)
+    mean = torch.randn(C, device=DEV, generator=g) * 0.2
+    invstd = torch.rand(C, device=DEV, generator=g) + 0.5
+    gamma = torch.rand(Cv, device=DEV, generator=g) + 0.5
+    beta = torch.randn(Cv, device=DEV, generator=g) * 0.3
+    wide = torch.full((M // pool_k, C + 16), 7.0, device=DEV, dtype=torch.bfloat16)
+    out = wide[:, 8:8 + C]
+    am = torch.empty(M // pool_k, C, device=DEV, dtype=torch.uint8) if pool_k > 1 else None
+    ops._call("pcb_bn_apply_rows", y.device, y.data_ptr(), 1, M, C, Cv, pool_k, mean.data_ptr(), invstd.data_ptr(),
+              gamma.data_ptr(), beta.data_ptr(), 1, out.data_ptr(), out.stride(0), am.data_ptr() if am is not None else None)
+    z = torch.relu((y.float()[:, :Cv] - mean[:Cv]) * invstd[:Cv] * gamma + beta)
+    if pool_k > 1:
+        z, idx = z.view(-1, pool_k, Cv).max(dim=1)
+    o = out.float()
+    assert torch.allclose(o[:, :Cv], z, rtol=2.0 ** -7, atol=1e-6)
+    assert float(o[:, Cv:].abs().max()) == 0.0 if Cv < C else True
+    assert float(wide[:, :8].float().min()) == 7.0 and float(wide[:, 8 + C:].float().min()) == 7.0
+
+
+class _Ref(nn.Module):
+    def __init__(self, widths, seed):
+        super().__init__()
+        torch.manual_seed(seed)
+        self.convs = nn.ModuleList(nn.Conv1d(a, b, 1) for a, b in zip(widths[:-1], widths[1:]))
+        self.bns = nn.ModuleList(nn.BatchNorm1d(b) for b in widths[1:])
+        with torch.no_grad():
+            for bn in self.bns:
+                bn.weight.uniform_(0.5, 1.5)
+                bn.bias.normal_(0, 0.2)
+
+
+@pytest.mark.parametrize("widths,M,pool_k", [([16, 32, 32, 64], 16384, 32), ([104, 64, 96, 128], 8192, 16),
+                                              ([264, 128, 196, 256], 2048, 32), ([128, 128], 4096, 1),
+                                              ([1536, 256, 256], 1024, 1)])
+def test_fused_mlp_matches_pytorch_training_mlp(widths, M, pool_k):
+    """Forward, input gradient and parameter gradients of the fused training MLP against conv1d/batch_norm/relu/max
+    in fp32 on the bf16-rounded weights (bf16 GEMM noise: 3e-2 relative in L2)."""
+    net = _Ref(widths, 5).to(DEV).train()
+    ref = _Ref(widths, 5).to(DEV).train()
+    with torch.no_grad():
+        for m in list(net.convs) + list(ref.convs):
+            m.weight.copy_(m.weight.to(torch.bfloat16).float())
+    g = torch.Generator(device=DEV).manual_seed(11)
+    x = torch.randn(M, widths[0], device=DEV, generator=g).to(torch.bfloat16)
+    x1 = x.clone().requires_grad_(True)
+    x2 = x.float().clone().requires_grad_(True)
+    assert ops.mlp_rows_fused_supported(x1, net.convs, net.bns, pool_k)
+    out = ops.mlp_rows_fused(x1, net.convs, net.bns, pool_k)[:, :widths[-1]]
+    h = x2
+    for conv, bn in zip(ref.convs, ref.bns):
+        h = F.relu(F.batch_norm(F.linear(h, conv.weight.flatten(1), conv.bias), bn.running_mean, bn.running_var, bn.weight,
+                                bn.bias, True, bn.momentum, bn.eps))
+    if pool_k > 1:
+        h = h.view(-1, pool_k, h.shape[-1]).max(dim=1)[0]
+    rel = lambda a, b: float((a.float() - b.float()).norm() / (b.float().norm() + 1e-12))
+    assert rel(out, h) < 2e-2, rel(out, h)
+    gout = torch.randn(h.shape, device=DEV, generator=g)
+    out.backward(gout.to(out.dtype))
+    h.backward(gout.to(torch.bfloat16).float())
+    assert rel(x1.grad, x2.grad) < 6e-2, rel(x1.grad, x2.grad)
+    for (n1, p1), (_, p2) in zip(net.named_parameters(), ref.named_parameters()):
+        if n1.startswith("convs") and n1.endswith("bias"):
+            continue                                   # bias before a training-mode BN: zero gradient up to rounding
+        assert p1.grad is not None, n1
+        assert rel(p1.grad, p2.grad) < 6e-2, (n1, rel(p1.grad, p2.grad))
+    for b1, b2 in zip(net.bns, ref.bns):
+        assert torch.allclose(b1.running_mean, b2.running_mean, rtol=2e-2, atol=2e-3)
+        assert torch.allclose(b1.running_var, b2.running_var, rtol=2e-2, atol=2e-3)
+        assert int(b1.num_batches_tracked) == 1
