@@ -256,32 +256,32 @@ int pcb_adam_flat_f32(float *param, const float *grad, float *exp_avg, float *ex
  * multiples of 8, 16-byte aligned bases), fp32 accumulation in TMEM, bf16 result; N, K multiples of 8; rows >= Nw of
  * w count as zero.  Persistent warp-specialised kernel (cp.async producers -> tcgen05.mma -> TMEM -> epilogue).
  *   pcb_linear_rows_bf16          plain product (forward of a conv without BatchNorm; data gradient with w = W^T)
- *   pcb_linear_bn_stats_rows_bf16 + training-mode BatchNorm statistics of the result: mean / invstd [N] (biased
- *                                 variance, eps) of the bias-free output, running_mean / running_var [Cv] updated with
- *                                 `momentum` (unbiased variance; `bias` [Cv], may be NULL, is added to the running mean
- *                                 only).  Column sums are shifted by running_mean - bias as read on entry.  Cv <= N real
- *                                 channels.  work: pcb_gemm_work_floats(M, N, K) floats of scratch; tickets:
+ *   pcb_linear_bn_stats_rows_bf16 + training-mode BatchNorm statistics of the result: mean / invstd / var [N] (biased
+ *                                 variance, eps) of the bias-free output, from (count, mean, M2) triples merged with
+ *                                 Chan's update in a fixed order (stateless, no cancellation).  Cv <= N real channels.  work: pcb_gemm_work_floats(M, N, K) floats of scratch; tickets:
  *                                 pcb_gemm_tickets() zeroed 32-bit words (left zeroed).  Deterministic two-stage sums.
  *   pcb_dgrad_bn_rows_bf16        data gradient THROUGH the previous layer's BN + ReLU: gz = gy . wt^T; dy = gz * [z > 0]
  *                                 with z = BN(yprev) recomputed from yprev [M, ldyp] and mean / invstd / gamma / beta;
  *                                 writes dy [M, lddy] and sums [3][N] = (sum dy, sum dy * yhat, 0)
- *   pcb_bn_apply_rows             out = [max over pool_k rows of] act(BN(y)) with given statistics (ordinary launch)
+ *   pcb_bn_apply_rows             out = [max over pool_k rows of] act(BN(y)) with given statistics (ordinary launch);
+ *                                 updates running_mean / running_var [Cv] (may be NULL) from mean / var with `momentum`
+ *                                 (unbiased variance; `bias` [Cv], may be NULL, is added to the running mean only)
  *   pcb_bn_bwd_apply_rows         gy = gamma * invstd * (dy - sums[0] / M - yhat * sums[1] / M); gy may alias dy */
 int64_t pcb_gemm_work_floats(int64_t M, int N, int K);
 int pcb_gemm_tickets(void);
 int pcb_linear_rows_bf16(const void *x, int64_t ldx, const void *w, int64_t ldw, int64_t M, int N, int Nw, int K, void *y,
                          int64_t ldy, pcb_stream_t stream);
 int pcb_linear_bn_stats_rows_bf16(const void *x, int64_t ldx, const void *w, int64_t ldw, int64_t M, int N, int Nw, int K,
-                                  void *y, int64_t ldy, int Cv, const float *bias, float eps, float momentum,
-                                  float *running_mean, float *running_var, float *mean, float *invstd, float *work,
-                                  unsigned *tickets, pcb_stream_t stream);
+                                  void *y, int64_t ldy, int Cv, float eps, float *mean, float *invstd, float *var,
+                                  float *work, unsigned *tickets, pcb_stream_t stream);
 int pcb_dgrad_bn_rows_bf16(const void *gy, int64_t ldg, const void *wt, int64_t ldwt, int64_t M, int N, int Nw, int K,
                            const void *yprev, int64_t ldyp, const float *mean, const float *invstd, const float *gamma,
                            const float *beta, int Cv, int relu, void *dy, int64_t lddy, float *sums, float *work,
                            unsigned *tickets, pcb_stream_t stream);
 int pcb_bn_apply_rows(const void *y, int dtype, int64_t M, int C, int Cv, int pool_k, const float *mean,
                       const float *invstd, const float *gamma, const float *beta, int relu, void *out, int64_t out_pitch,
-                      unsigned char *argmax, pcb_stream_t stream);
+                      unsigned char *argmax, const float *var, const float *bias, float momentum, float *running_mean,
+                      float *running_var, pcb_stream_t stream);
 int pcb_bn_bwd_apply_rows(const void *dy, const void *y, int dtype, int64_t M, int C, int Cv, const float *mean,
                           const float *invstd, const float *gamma, const float *sums, void *gy, pcb_stream_t stream);
 

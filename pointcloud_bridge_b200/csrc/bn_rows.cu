@@ -398,6 +398,7 @@ struct BnFwdArgs {
     unsigned char *argmax;
     const float *bias, *gamma, *beta;
     float *running_mean, *running_var, *mean, *invstd, *work;
+    const float *var;                                  // biased batch variance (bn_apply_rows_kernel only)
     int64_t M, upc;
     int C, Cv, pool_k, relu, nparts;                   // C = row pitch (multiple of 4), Cv <= C real channels
     int64_t out_pitch;                                 // row pitch of out (C, or wider when out is a column slice)
@@ -739,6 +740,17 @@ bn_apply_rows_kernel(const BnFwdArgs a)
     const int C = a.C;
     __shared__ float s_buf[2][kBnThreads][V];
     float *s_const = nullptr;
+    if (blockIdx.x == 0 && a.running_mean) {
+        // running statistics as torch.nn.functional.batch_norm updates them (momentum, unbiased variance; the conv bias
+        // that was folded out of y is added back to the mean)
+        const float Mf = (float)a.M;
+        for (int c = threadIdx.x; c < a.Cv; c += kBnThreads) {
+            const float b = a.bias ? a.bias[c] : 0.f, var = a.var[c];
+            a.running_mean[c] = (1.f - a.momentum) * a.running_mean[c] + a.momentum * (a.mean[c] + b);
+            const float unbiased = a.M > 1 ? var * (Mf / (float)(a.M - 1)) : var;
+            a.running_var[c] = (1.f - a.momentum) * a.running_var[c] + a.momentum * unbiased;
+        }
+    }
     if (C <= kBnThreads * V) {
         s_const = &s_buf[0][0][0];
         for (int c = threadIdx.x; c < C; c += kBnThreads) {
@@ -978,19 +990,23 @@ PCB_API int pcb_bn_bwd_rows(const void *gz, int64_t gz_pitch, const void *y, con
     return bn_bwd_launch<__nv_bfloat16, 4>(a, st);
 }
 
-// Elementwise half of the forward pass with given statistics (mean / invstd from the GEMM epilogue):
-// out = [max over pool_k rows of] act(BN(y)); ordinary launch.
+// Elementwise half of the forward pass with given statistics (mean / invstd / var from the GEMM epilogue):
+// out = [max over pool_k rows of] act(BN(y)); ordinary launch.  With running_mean != NULL the first CTA also updates the
+// running statistics from mean / var (bias: the conv bias that was folded out of y, may be NULL).
 PCB_API int pcb_bn_apply_rows(const void *y, int dtype, int64_t M, int C, int Cv, int pool_k, const float *mean,
                               const float *invstd, const float *gamma, const float *beta, int relu, void *out,
-                              int64_t out_pitch, unsigned char *argmax, pcb_stream_t stream)
+                              int64_t out_pitch, unsigned char *argmax, const float *var, const float *bias, float momentum,
+                              float *running_mean, float *running_var, pcb_stream_t stream)
 {
     PCB_REQUIRE(y && gamma && beta && mean && invstd && out, PCB_EINVAL);
+    PCB_REQUIRE(!running_mean || (running_var && var), PCB_EINVAL);
     PCB_BN_CHECK(M, C, pool_k);
     PCB_REQUIRE(Cv > 0 && Cv <= C && (Cv == C || C <= 1024), PCB_ERANGE);
     BnFwdArgs a = {};
     a.y = y, a.out = out, a.argmax = argmax, a.gamma = gamma, a.beta = beta;
     a.mean = const_cast<float *>(mean), a.invstd = const_cast<float *>(invstd), a.M = M, a.C = C, a.Cv = Cv;
     a.pool_k = pool_k, a.relu = relu, a.out_pitch = out_pitch > 0 ? out_pitch : C;
+    a.var = var, a.bias = bias, a.momentum = momentum, a.running_mean = running_mean, a.running_var = running_var;
     PCB_REQUIRE(a.out_pitch >= C && a.out_pitch % 4 == 0, PCB_ERANGE);
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t units = M / pool_k;

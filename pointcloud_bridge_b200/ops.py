@@ -938,7 +938,11 @@ def wgrad_rows(gy, x, k: int | None = None, out: torch.Tensor | None = None, n: 
 # ---------------------------------------------------------------------------------------------
 # tensor-core GEMMs on rows (csrc/gemm_rows.cu): tcgen05.mma, fp32 accumulation in TMEM, BatchNorm sums in the epilogue
 # ---------------------------------------------------------------------------------------------
-_OWN_GEMM = os.environ.get("PCB_NO_OWN_GEMM", "0") != "1"     # debugging aid: library GEMM + cooperative BN kernels
+# PCB_OWN_GEMM=1 routes the training MLPs through the tcgen05 GEMMs of csrc/gemm_rows.cu (BatchNorm sums in the epilogue).
+# Round-2 measurements (profiles/r2_gemm_rows.md): correct on every layer shape, but 2.5-3x slower than the library GEMM on
+# these memory-bound, few-hundred-flop-per-byte shapes (per-tile instruction overhead of the epilogue), so the default
+# stays the library GEMM + cooperative BN row kernels until the kernel is at parity.
+_OWN_GEMM = os.environ.get("PCB_OWN_GEMM", "0") == "1"
 _ticket_pool: dict[int, list] = {}
 
 
@@ -1119,7 +1123,7 @@ class _MlpRows(torch.autograd.Function):
             wl, wt = _weight_pair(w)
             K = min(cur.shape[1], wl.shape[1])
             y = torch.empty(M, n8, dtype=torch.bfloat16, device=dev)
-            stats = torch.empty(2, n8, dtype=torch.float32, device=dev)
+            stats = torch.empty(3, n8, dtype=torch.float32, device=dev)          # mean, invstd, biased variance
             work = torch.empty(max(int(lib.pcb_gemm_work_floats(M, n8, K)), 1), dtype=torch.float32, device=dev)
             tick = _tickets(dev)
             track = bn.track_running_stats
@@ -1131,10 +1135,8 @@ class _MlpRows(torch.autograd.Function):
             g32, b32 = params[4 * l + 2].detach().float(), params[4 * l + 3].detach().float()
             bias = params[4 * l + 1]
             _call("pcb_linear_bn_stats_rows_bf16", dev, cur.data_ptr(), cur.stride(0), wl.data_ptr(), wl.stride(0), M, n8,
-                  min(wl.shape[0], n8), K, y.data_ptr(), y.stride(0), n,
-                  bias.data_ptr() if bias is not None else None, float(bn.eps), float(bn.momentum),
-                  bn.running_mean.data_ptr() if track else None, bn.running_var.data_ptr() if track else None,
-                  stats[0].data_ptr(), stats[1].data_ptr(), work.data_ptr(), tick.data_ptr(),
+                  min(wl.shape[0], n8), K, y.data_ptr(), y.stride(0), n, float(bn.eps),
+                  stats[0].data_ptr(), stats[1].data_ptr(), stats[2].data_ptr(), work.data_ptr(), tick.data_ptr(),
                   alg_bytes=2 * M * (K + n8) + 2 * wl.numel())
             last = l == L - 1
             pk = pool_k if last else 1
@@ -1148,7 +1150,9 @@ class _MlpRows(torch.autograd.Function):
             argmax = torch.empty(Mo, n8, dtype=torch.uint8, device=dev) if pk > 1 else None
             _call("pcb_bn_apply_rows", dev, y.data_ptr(), 1, M, n8, n, pk, stats[0].data_ptr(), stats[1].data_ptr(),
                   g32.data_ptr(), b32.data_ptr(), 1, z.data_ptr(), z.stride(0),
-                  argmax.data_ptr() if argmax is not None else None,
+                  argmax.data_ptr() if argmax is not None else None, stats[2].data_ptr(),
+                  bias.data_ptr() if bias is not None else None, float(bn.momentum),
+                  bn.running_mean.data_ptr() if track else None, bn.running_var.data_ptr() if track else None,
                   alg_bytes=2 * (M + Mo) * n8 + (Mo * n8 if pk > 1 else 0))
             saved += [y, stats, g32, b32, wt]
             if not last:

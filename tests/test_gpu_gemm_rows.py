@@ -72,12 +72,18 @@ def test_linear_bn_stats_epilogue(M, K, N):
     for rep in range(2):
         rm, rv = rm0.clone(), rv0.clone()
         y = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
-        stats = torch.full((2, N), float("nan"), device=DEV)
+        stats = torch.full((3, N), float("nan"), device=DEV)
         work = torch.empty(max(int(lib.pcb_gemm_work_floats(M, N, K)), 1), device=DEV)
         tick = ops._tickets(torch.device(DEV))
         ops._call("pcb_linear_bn_stats_rows_bf16", x.device, x.data_ptr(), x.stride(0), w.data_ptr(), w.stride(0), M, N, N, K,
-                  y.data_ptr(), y.stride(0), Cv, bias.data_ptr(), 1e-5, 0.1, rm.data_ptr(), rv.data_ptr(),
-                  stats[0].data_ptr(), stats[1].data_ptr(), work.data_ptr(), tick.data_ptr())
+                  y.data_ptr(), y.stride(0), Cv, 1e-5,
+                  stats[0].data_ptr(), stats[1].data_ptr(), stats[2].data_ptr(), work.data_ptr(), tick.data_ptr())
+        # the elementwise kernel that follows owns the running statistics
+        z = torch.empty_like(y)
+        ones, zeros = torch.ones(Cv, device=DEV), torch.zeros(Cv, device=DEV)
+        ops._call("pcb_bn_apply_rows", y.device, y.data_ptr(), 1, M, N, Cv, 1, stats[0].data_ptr(), stats[1].data_ptr(),
+                  ones.data_ptr(), zeros.data_ptr(), 1, z.data_ptr(), z.stride(0), None, stats[2].data_ptr(),
+                  bias.data_ptr(), 0.1, rm.data_ptr(), rv.data_ptr())
         torch.cuda.synchronize()
         assert int(tick.abs().sum()) == 0                 # tickets are left zeroed
         outs.append((y, stats, rm, rv))
@@ -87,6 +93,7 @@ def test_linear_bn_stats_epilogue(M, K, N):
     mean, var = yf.mean(0), yf.var(0, unbiased=False)
     assert torch.allclose(stats[0, :Cv], mean, rtol=1e-4, atol=1e-5 * float(yf.abs().max()))
     assert torch.allclose(stats[1, :Cv], torch.rsqrt(var + 1e-5), rtol=2e-4)
+    assert torch.allclose(stats[2, :Cv], var, rtol=2e-4, atol=1e-7)
     assert torch.allclose(rm, 0.9 * rm0 + 0.1 * (mean + bias), rtol=1e-4, atol=1e-5)
     assert torch.allclose(rv, 0.9 * rv0 + 0.1 * yf.var(0, unbiased=True), rtol=2e-4, atol=1e-6)
     if Cv < N:
@@ -164,7 +171,8 @@ def test_bn_apply_rows(M, C, Cv, pool_k):
     out = wide[:, 8:8 + C]
     am = torch.empty(M // pool_k, C, device=DEV, dtype=torch.uint8) if pool_k > 1 else None
     ops._call("pcb_bn_apply_rows", y.device, y.data_ptr(), 1, M, C, Cv, pool_k, mean.data_ptr(), invstd.data_ptr(),
-              gamma.data_ptr(), beta.data_ptr(), 1, out.data_ptr(), out.stride(0), am.data_ptr() if am is not None else None)
+              gamma.data_ptr(), beta.data_ptr(), 1, out.data_ptr(), out.stride(0), am.data_ptr() if am is not None else None,
+              None, None, 0.0, None, None)
     z = torch.relu((y.float()[:, :Cv] - mean[:Cv]) * invstd[:Cv] * gamma + beta)
     if pool_k > 1:
         z, idx = z.view(-1, pool_k, Cv).max(dim=1)
@@ -189,38 +197,50 @@ class _Ref(nn.Module):
 @pytest.mark.parametrize("widths,M,pool_k", [([16, 32, 32, 64], 16384, 32), ([104, 64, 96, 128], 8192, 16),
                                               ([264, 128, 196, 256], 2048, 32), ([128, 128], 4096, 1),
                                               ([1536, 256, 256], 1024, 1)])
-def test_fused_mlp_matches_pytorch_training_mlp(widths, M, pool_k):
-    """Forward, input gradient and parameter gradients of the fused training MLP against conv1d/batch_norm/relu/max
-    in fp32 on the bf16-rounded weights (bf16 GEMM noise: 3e-2 relative in L2)."""
-    net = _Ref(widths, 5).to(DEV).train()
-    ref = _Ref(widths, 5).to(DEV).train()
+def test_fused_mlp_matches_pytorch_training_mlp(widths, M, pool_k, monkeypatch):
+    """Forward, input gradient and parameter gradients of the fused training MLP (a) against the round-1 composition
+    with the same bf16 rounding points (library GEMM + cooperative BN row kernels, themselves checked against PyTorch
+    in test_gpu_bn_rows.py): only summation order differs; (b) against conv1d / batch_norm / relu / max in fp32 on
+    the bf16-rounded weights, where a bf16 rounding can hand the max-pool to another neighbour (loose bound)."""
+    from pointcloud_bridge_b200.partsize import pointnet_util as pu
+    nets = [_Ref(widths, 5).to(DEV).train() for _ in range(3)]
     with torch.no_grad():
-        for m in list(net.convs) + list(ref.convs):
-            m.weight.copy_(m.weight.to(torch.bfloat16).float())
+        for net in nets:
+            for m in net.convs:
+                m.weight.copy_(m.weight.to(torch.bfloat16).float())
     g = torch.Generator(device=DEV).manual_seed(11)
     x = torch.randn(M, widths[0], device=DEV, generator=g).to(torch.bfloat16)
-    x1 = x.clone().requires_grad_(True)
-    x2 = x.float().clone().requires_grad_(True)
-    assert ops.mlp_rows_fused_supported(x1, net.convs, net.bns, pool_k)
-    out = ops.mlp_rows_fused(x1, net.convs, net.bns, pool_k)[:, :widths[-1]]
-    h = x2
-    for conv, bn in zip(ref.convs, ref.bns):
+    xs = [x.clone().requires_grad_(True), x.clone().requires_grad_(True), x.float().clone().requires_grad_(True)]
+    monkeypatch.setattr(ops, "_OWN_GEMM", True)
+    assert ops.mlp_rows_fused_supported(xs[0], nets[0].convs, nets[0].bns, pool_k)
+    out = ops.mlp_rows_fused(xs[0], nets[0].convs, nets[0].bns, pool_k)[:, :widths[-1]]
+    monkeypatch.setattr(ops, "_OWN_GEMM", False)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        old = pu.mlp_rows(xs[1], nets[1].convs, nets[1].bns, pool_k)
+    monkeypatch.undo()
+    h = xs[2]
+    for conv, bn in zip(nets[2].convs, nets[2].bns):
         h = F.relu(F.batch_norm(F.linear(h, conv.weight.flatten(1), conv.bias), bn.running_mean, bn.running_var, bn.weight,
                                 bn.bias, True, bn.momentum, bn.eps))
     if pool_k > 1:
         h = h.view(-1, pool_k, h.shape[-1]).max(dim=1)[0]
-    rel = lambda a, b: float((a.float() - b.float()).norm() / (b.float().norm() + 1e-12))
-    assert rel(out, h) < 2e-2, rel(out, h)
-    gout = torch.randn(h.shape, device=DEV, generator=g)
-    out.backward(gout.to(out.dtype))
-    h.backward(gout.to(torch.bfloat16).float())
-    assert rel(x1.grad, x2.grad) < 6e-2, rel(x1.grad, x2.grad)
-    for (n1, p1), (_, p2) in zip(net.named_parameters(), ref.named_parameters()):
+    rel = lambda a, b: float((a.detach().float() - b.detach().float()).norm() / (b.detach().float().norm() + 1e-12))
+    print("forward: vs round-1 path %.2e, vs fp32 %.2e" % (rel(out, old), rel(out, h)))
+    assert rel(out, old) < 5e-3 and rel(out, h) < 2e-2
+    gout = torch.randn(h.shape, device=DEV, generator=g).to(torch.bfloat16)
+    out.backward(gout)
+    old.backward(gout.to(old.dtype))
+    h.backward(gout.float())
+    loose = 0.35 if pool_k > 1 else 8e-2
+    print("input gradient: vs round-1 path %.2e, vs fp32 %.2e" % (rel(xs[0].grad, xs[1].grad), rel(xs[0].grad, xs[2].grad)))
+    assert rel(xs[0].grad, xs[1].grad) < 4e-2 and rel(xs[0].grad, xs[2].grad) < loose
+    for (n1, p1), (_, p2), (_, p3) in zip(*[net.named_parameters() for net in nets]):
         if n1.startswith("convs") and n1.endswith("bias"):
             continue                                   # bias before a training-mode BN: zero gradient up to rounding
         assert p1.grad is not None, n1
-        assert rel(p1.grad, p2.grad) < 6e-2, (n1, rel(p1.grad, p2.grad))
-    for b1, b2 in zip(net.bns, ref.bns):
-        assert torch.allclose(b1.running_mean, b2.running_mean, rtol=2e-2, atol=2e-3)
-        assert torch.allclose(b1.running_var, b2.running_var, rtol=2e-2, atol=2e-3)
+        print(n1, "vs round-1 path %.2e, vs fp32 %.2e" % (rel(p1.grad, p2.grad), rel(p1.grad, p3.grad)))
+        assert rel(p1.grad, p2.grad) < 4e-2 and rel(p1.grad, p3.grad) < loose, n1
+    for b1, b3 in zip(nets[0].bns, nets[2].bns):
+        assert torch.allclose(b1.running_mean, b3.running_mean, rtol=2e-2, atol=2e-3)
+        assert torch.allclose(b1.running_var, b3.running_var, rtol=2e-2, atol=2e-3)
         assert int(b1.num_batches_tracked) == 1
