@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of one CUDA graph per step")
     ap.add_argument("--cpu-sample-blocks", type=int, default=4)
+    ap.add_argument("--repeats", type=int, default=5, help="timed K-step regions; the median one is reported")
     return ap.parse_args()
 
 
@@ -56,8 +57,12 @@ def workload_config(a, world):
             "e2e": "public API (engine.Trainer): batch i+1 copied H2D from pinned memory on a side stream while step i runs "
                    "(Trainer.prefetch), loss of step i copied D2H after the step and read by the host one step later; "
                    "wall clock over K steps incl. the L2 flush writes",
-            "launch": "eager" if a.no_graph else "one CUDA graph per step (zero+fwd+loss+bwd+Adam; FPS start indices "
-                      "drawn on the CPU generator as the reference does and copied in before each replay)"}
+            "launch": "eager" if a.no_graph else "one CUDA graph per step (zero+fwd+loss+bwd+Adam); the sampling / grouping "
+                      "indices of batch i+1 (FPS with start indices drawn on the CPU generator as the reference does, ball "
+                      "query, three-NN) are computed on a side stream while batch i trains and copied into the graph's "
+                      "static buffers before its replay",
+            "timed_region": "K steps bracketed by barrier+synchronize, per-step CUDA events summed; repeated --repeats "
+                            "times, median region reported"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -173,7 +178,10 @@ KERNEL_OF = {                                         # C-ABI entry point -> dev
     "pcb_group_points_bwd_bf16": "group_points_bwd_vec_kernel", "pcb_bn_fwd_rows": "bn_fwd_fused_kernel",
     "pcb_bn_bwd_rows": "bn_bwd_fused_kernel", "pcb_fp_concat_bf16": "fp_concat_chunk_kernel",
     "pcb_fp_concat_bwd_bf16": "fp_concat_bwd_vec_kernel", "pcb_wgrad_rows_bf16": "wgrad_rows_kernel",
-    "pcb_adam_flat_f32": "adam_flat_kernel", "pcb_sa_fused_bf16": "sa_fused_kernel"}
+    "pcb_adam_flat_f32": "adam_flat_kernel", "pcb_sa_fused_bf16": "sa_fused_kernel",
+    "pcb_linear_rows_bf16": "gemm_rows_kernel<EPI_STORE>", "pcb_linear_bn_stats_rows_bf16": "gemm_rows_kernel<EPI_STATS>",
+    "pcb_dgrad_bn_rows_bf16": "gemm_rows_kernel<EPI_BNBWD>", "pcb_bn_apply_rows": "bn_apply_rows_kernel",
+    "pcb_bn_bwd_apply_rows": "bn_bwd_apply_rows_kernel"}
 
 
 def run_ours(a):
@@ -214,29 +222,44 @@ def run_ours(a):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # The step of batch i runs while the sampling / grouping indices of batch i + 1 are computed on a side stream
+    # (Trainer.prefetch: farthest point sampling, ball query, three-NN depend on the coordinates only).  Every
+    # iteration below issues exactly one step and one index chain, so K timed iterations are K complete steps.
     def step_resident(i, ev=None):
         flush.fill_(0.0)                                    # L2 flush BETWEEN timed steps: outside the event bracket
-        x, y = resident[i % len(resident)]
         if ev is not None:
             ev[0].record()
-        loss = trainer.step(x, labels=y)
+        loss = trainer.step_prefetched()
         if ev is not None:
             ev[1].record()
+        x, y = resident[(i + 1) % len(resident)]
+        trainer.prefetch(x, labels=y)
         return loss
 
+    x, y = resident[0]
+    trainer.prefetch(x, labels=y)
     for i in range(max(a.warmup, 3) + (4 if trainer.graph else 0)):      # graph mode: 3 eager + capture first
         step_resident(i)
 
-    # ---- value: K steps, inputs resident, device-timed, max over ranks ----
-    barrier()
-    launches0 = _lib.launches()
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
+    # ---- value: K steps, inputs resident, device-timed, max over ranks; the K-step region is repeated a.repeats times
+    # (each bracketed by barrier + synchronize on both sides) and the MEDIAN region is reported: one stalled replay in a
+    # 20-step window otherwise moves the number by several per cent ----
+    regions = []
+    gpu_launches = 0
     with ClockSampler(local) as clocks:
-        for i in range(a.steps):
-            step_resident(i, evs[i])
-        barrier()
-    ms = pdist.max_over_ranks(sum(e0.elapsed_time(e1) for e0, e1 in evs), dev)    # K steps, flushes excluded
-    gpu_launches = _lib.launches() - launches0
+        for rep in range(max(a.repeats, 1)):
+            barrier()
+            launches0 = _lib.launches()
+            evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
+            for i in range(a.steps):
+                step_resident(i, evs[i])
+            barrier()
+            per_step = [e0.elapsed_time(e1) for e0, e1 in evs]
+            regions.append((pdist.max_over_ranks(sum(per_step), dev), per_step))     # K steps, flushes excluded
+            gpu_launches = _lib.launches() - launches0
+    regions.sort(key=lambda r: r[0])
+    ms, per_step = regions[len(regions) // 2]
+    per_step_sorted = sorted(per_step)
     value = world * B * NPTS * a.steps / (ms * 1e-3)
 
     # ---- e2e: batch from pinned host memory every step, loss read back every step ----
@@ -249,6 +272,7 @@ def run_ours(a):
         y = hy.to(dev, non_blocking=True)
         return float(trainer.step(x, labels=y).item())              # D2H of the step's result
 
+    trainer.step_prefetched()                           # drain the batch the value loop left in the prefetch stage
     for i in range(2):
         step_e2e(i)
     barrier()
@@ -303,11 +327,21 @@ def run_ours(a):
     torch.cuda.synchronize()
     ops.set_kernel_timer(None)
     inst_ms = ei0.elapsed_time(ei1)   # (eager, instrumented: only used as a sanity figure)
+    # an event pair around NOTHING still reads a few microseconds: measure that and take it off every bracket, so that
+    # the per-kernel shares of the step are not inflated by the instrumentation
+    cal = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(200)]
+    torch.cuda._sleep(int(2e7))
+    for c0, c1 in cal:
+        c0.record()
+        c1.record()
+    torch.cuda.synchronize()
+    gaps = sorted(c0.elapsed_time(c1) for c0, c1 in cal)
+    evt_overhead_ms = gaps[len(gaps) // 2]
     # aggregate per C-ABI entry point (one kernel family), all shapes of the step together
     agg = {}
     for name, nbytes, s, e in sink:
         t = agg.setdefault(name, [0.0, 0, 0])
-        t[0] += s.elapsed_time(e)
+        t[0] += max(s.elapsed_time(e) - evt_overhead_ms, 1e-4)
         t[1] += 1
         t[2] += nbytes
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -333,11 +367,16 @@ def run_ours(a):
                 "avg_launch_ms": top["avg_launch_ms"], "launches_per_step": top["launches_per_step"],
                 "alg_bytes_per_launch": top["alg_bytes_per_launch"], "share_of_step": top["share_of_step"],
                 "note": "kernel family of ours with the largest share of the step (all layer shapes together); per-launch "
-                        "durations from CUDA events around every launch of an eager, spin-ahead instrumented pass",
+                        "durations from CUDA events around every launch of an eager, spin-ahead instrumented pass, minus "
+                        "the measured duration of an empty event bracket",
+                "event_bracket_overhead_ms": round(evt_overhead_ms, 5),
                 "all_our_kernels_share_of_step": round(ours_share, 4), "kernels": kernels[:10]}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
             "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "timing": {"regions_ms_per_step": [round(r[0] / a.steps, 4) for r in regions], "reported": "median region",
+                       "per_step_ms_median": round(per_step_sorted[len(per_step_sorted) // 2], 4),
+                       "per_step_ms_p90": round(per_step_sorted[min(len(per_step_sorted) - 1, int(0.9 * len(per_step_sorted)))], 4)},
             "dtype": "f32" if a.fp32 else "bf16", "data": "synthetic", "config": workload_config(a, world),
             "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": gpu_launches, "roofline": roofline}
 
@@ -351,11 +390,9 @@ def run_ours(a):
     if world > 1:
         dist.barrier()
         torch.cuda.synchronize()
-        # The step graph holds a captured NCCL all-reduce; tearing the communicator down underneath it can
-        # block in destroy_process_group.  Everything is printed and synchronised: leave without the teardown.
-        sys.stdout.flush()
-        sys.stderr.flush()
-        os._exit(0)
+        trainer.close()                                   # the step graph holds a captured all-reduce: drop it first
+        del trainer
+        dist.destroy_process_group()
 
 
 def main():

@@ -46,18 +46,37 @@ class FpsStartBuffers:
             self.shapes.append((B, N, device))
         return ops._draw_start(B, N, device)
 
+    RING = 4                       # pinned staging sets; a set is rewritten only after its copies have run
+
     def allocate(self):
-        self.calls = [(N, torch.zeros(B, dtype=torch.long, device=dev), torch.zeros(B, dtype=torch.long).pin_memory())
+        self.calls = [(N, torch.zeros(B, dtype=torch.long, device=dev),
+                       [torch.zeros(B, dtype=torch.long).pin_memory() for _ in range(self.RING)])
                       for (B, N, dev) in self.shapes]
+        self._events = [None] * self.RING
+        self._refills = 0
         self._next = 0
 
     def refill(self, n=None):
         """n: number of live clouds of a short batch -- draws exactly what the eager code would draw for n
-        clouds (the remaining entries keep their previous values; their clouds are padding)."""
-        for N, buf, stage in self.calls:
+        clouds (the remaining entries keep their previous values; their clouds are padding).
+        The host may be several replays ahead of the GPU: each staging set is guarded by the event of its last
+        host->device copies and rewritten only after they have completed."""
+        if not self.calls:
+            return
+        slot = self._refills % self.RING
+        self._refills += 1
+        if self._events[slot] is not None:
+            self._events[slot].synchronize()
+        for N, buf, stages in self.calls:
+            stage = stages[slot]
             m = stage.shape[0] if n is None else n
+            if n is not None:                                # padding clouds keep the previous replay's values
+                stage.copy_(stages[(slot - 1) % self.RING])
             stage[:m].copy_(torch.randint(0, N, (m,), dtype=torch.long))
             buf.copy_(stage, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self._events[slot] = ev
 
 
 def _nll_mean(logp, labels):
@@ -157,6 +176,13 @@ class Trainer:
         self._opt_in_graph = False
         self._last_logits = None
         self._pf_stream = self._pf_bufs = self._pf_ready = self._pf_consumed = None
+        self._pf_pre = None
+        self._mark_consumed = False
+        # Networks whose sampling / grouping indices depend on the coordinates only expose `index_chain`: the
+        # indices of a batch are then computed before its step -- by `prefetch` on a side stream, while the previous
+        # batch trains -- and the captured step contains no farthest point sampling, ball query or three-NN at all.
+        self._use_chain = hasattr(net, "index_chain") and os.environ.get("PCB_NO_INDEX_PREFETCH", "0") != "1"
+        self._static_pre = None
 
     @torch.no_grad()
     def last_pred(self, class_dim: int = 1) -> torch.Tensor:
@@ -174,18 +200,32 @@ class Trainer:
         """Call after changing parameters from outside (net.load_state_dict, manual edits): re-derives the
         bf16 weight shadows that the optimizer kernel otherwise keeps current."""
         self._ctx.refresh_shadows()
+        ops.bump_param_generation()
+
+    def close(self) -> None:
+        """Drop the captured graphs (a graph that holds a captured NCCL all-reduce must go before the process group is
+        destroyed, otherwise `destroy_process_group` can block) and the prefetch state.  The trainer can still step
+        eagerly afterwards; a later graph step re-captures."""
+        torch.cuda.synchronize()
+        self._g = None
+        if hasattr(self, "_g_opt"):
+            self._g_opt = None
+        self._static = self._static_pre = None
+        self._pf_bufs = self._pf_pre = self._pf_ready = self._pf_consumed = None
+        self._warm = 0
 
     # -- eager pieces ---------------------------------------------------------------------
-    def _fwd_bwd(self, inputs, labels, loss_inputs):
+    def _fwd_bwd(self, inputs, labels, loss_inputs, pre=None):
         self.bucket.zero()
+        kw = {} if pre is None else {"pre": pre}
         with self._ctx:
             self._ctx.counters.append(self.opt.step_t)      # advanced with the BN counters in one multi-tensor add
             if self.loss_fn is None:       # plain mean NLL: the heads hand their logits rows to the loss kernel
                 with ops.head_logits_mode(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=self.amp):
-                    out = self.net(*inputs)
+                    out = self.net(*inputs, **kw)
             else:
                 with torch.autocast("cuda", dtype=torch.bfloat16, enabled=self.amp):
-                    out = self.net(*inputs)
+                    out = self.net(*inputs, **kw)
             logits = out[0] if isinstance(out, tuple) else out
             self._last_logits = logits if isinstance(logits, ops.LogitRows) else logits.detach()
             if isinstance(logits, ops.LogitRows):
@@ -200,19 +240,25 @@ class Trainer:
     def _multi(self):
         return pdist.is_dist() and torch.distributed.get_world_size() > 1
 
-    def _step_eager(self, inputs, labels, loss_inputs):
-        loss = self._fwd_bwd(inputs, labels, loss_inputs)
+    def _step_eager(self, inputs, labels, loss_inputs, pre=None):
+        loss = self._fwd_bwd(inputs, labels, loss_inputs, pre)
         self.bucket.pack()
         if self._multi():
             self.bucket.allreduce_mean()
         self.opt.step(increment=False)
+        ops.bump_param_generation()
         return loss
 
     # -- CUDA-graph path --------------------------------------------------------------------
-    def _capture(self, inputs, labels, loss_inputs):
+    def _capture(self, inputs, labels, loss_inputs, pre=None):
         """Capture one step with static input buffers.  With several ranks the NCCL all-reduce and
         the optimizer stay outside the graph (zero + forward + loss + backward are captured)."""
+        from torch.utils import _pytree as pytree
         self._static = ([t.clone() for t in inputs], labels.clone(), [t.clone() for t in loss_inputs])
+        if pre is not None:                                  # static copies of the precomputed indices, same structure
+            flat, spec = pytree.tree_flatten(pre)
+            self._static_pre_flat = [t.clone() for t in flat]
+            self._static_pre = pytree.tree_unflatten(self._static_pre_flat, spec)
         # several ranks: the NCCL all-reduce is captured into the same graph (one launch per step) unless
         # PCB_GRAPH_ALLREDUCE=0, in which case it runs eagerly between two graphs
         self._opt_in_graph = (not self._multi()) or os.environ.get("PCB_GRAPH_ALLREDUCE", "1") != "0"
@@ -224,7 +270,7 @@ class Trainer:
         n0 = _lib.launches()
         try:
             with torch.cuda.graph(self._g):
-                loss = self._fwd_bwd(self._static[0], self._static[1], self._static[2])
+                loss = self._fwd_bwd(self._static[0], self._static[1], self._static[2], self._static_pre)
                 self.bucket.pack()
                 if self._opt_in_graph:
                     if self._multi():
@@ -256,24 +302,42 @@ class Trainer:
         with torch.cuda.stream(self._pf_stream):
             for b, t in zip(self._pf_bufs, srcs):
                 b.copy_(t, non_blocking=True)
+            # sampling / grouping indices of that batch, on the same side stream: they overlap the running step
+            self._pf_pre = self.net.index_chain(self._pf_bufs[0]) if self._use_chain else None
             self._pf_ready = torch.cuda.Event()
             self._pf_ready.record(self._pf_stream)
         self._pf_counts = (len(inputs), len(loss_inputs))
 
     def step_prefetched(self):
         """`step` on the batch handed to `prefetch`."""
-        torch.cuda.current_stream().wait_event(self._pf_ready)
+        main = torch.cuda.current_stream()
+        main.wait_event(self._pf_ready)
         ni, nl = self._pf_counts
         bufs = self._pf_bufs
-        loss = self.step(*bufs[:ni], labels=bufs[ni], loss_inputs=tuple(bufs[ni + 1:ni + 1 + nl]))
-        self._pf_consumed = torch.cuda.Event()
-        self._pf_consumed.record()          # (graph mode copies the staging buffers into the static inputs first)
+        pre = self._pf_pre
+        if pre is not None:                  # allocated on the side stream, consumed on this one
+            from torch.utils import _pytree as pytree
+            for t in pytree.tree_flatten(pre)[0]:
+                t.record_stream(main)
+        self._mark_consumed = True
+        loss = self.step(*bufs[:ni], labels=bufs[ni], loss_inputs=tuple(bufs[ni + 1:ni + 1 + nl]), pre=pre)
+        if self._mark_consumed:             # eager step: the staging buffers were read throughout
+            self._note_consumed()
         return loss
 
-    def step(self, *inputs, labels, loss_inputs=()):
-        """One optimisation step on this rank's batch; returns the (device) loss tensor."""
+    def _note_consumed(self):
+        self._pf_consumed = torch.cuda.Event()
+        self._pf_consumed.record()
+        self._mark_consumed = False
+
+    def step(self, *inputs, labels, loss_inputs=(), pre=None):
+        """One optimisation step on this rank's batch; returns the (device) loss tensor.
+        pre: the batch's precomputed indices (`net.index_chain`), normally handed over by `step_prefetched`; computed
+        here, on the step's own stream, when the network has an index chain and none was given."""
+        if self._use_chain and pre is None:
+            pre = self.net.index_chain(inputs[0])
         if not self.graph:
-            return self._step_eager(inputs, labels, loss_inputs)
+            return self._step_eager(inputs, labels, loss_inputs, pre)
         if self._warm < 3:                                  # eager warm-up steps on a side stream
             self._warm += 1
             discover = self._warm == 3                      # the last one also records the FPS call list
@@ -285,7 +349,7 @@ class Trainer:
             s.wait_stream(torch.cuda.current_stream())
             try:
                 with torch.cuda.stream(s):
-                    loss = self._step_eager(inputs, labels, loss_inputs)
+                    loss = self._step_eager(inputs, labels, loss_inputs, pre)
             finally:
                 if discover:
                     self._starts.mode = "off"
@@ -293,14 +357,20 @@ class Trainer:
             torch.cuda.current_stream().wait_stream(s)
             return loss
         if self._g is None:
-            self._capture(inputs, labels, loss_inputs)
+            self._capture(inputs, labels, loss_inputs, pre)
         for dst, src in zip(self._static[0], inputs):
             dst.copy_(src, non_blocking=True)
         self._static[1].copy_(labels, non_blocking=True)
         for dst, src in zip(self._static[2], loss_inputs):
             dst.copy_(src, non_blocking=True)
+        if self._static_pre is not None:
+            from torch.utils import _pytree as pytree
+            torch._foreach_copy_(self._static_pre_flat, pytree.tree_flatten(pre)[0])
+        if self._mark_consumed:             # the prefetch staging buffers are free again: the next copy may start
+            self._note_consumed()
         self._starts.refill()
         self._g.replay()
+        ops.bump_param_generation()
         from . import _lib
         _lib.count_launches(self.kernel_launches_per_replay)
         if not self._opt_in_graph:                          # eager NCCL all-reduce between the two graphs

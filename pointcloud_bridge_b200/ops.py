@@ -84,8 +84,11 @@ def set_fps_start_provider(fn) -> None:
 
 # Ring of pinned staging buffers for the FPS start indices: a host->device copy from pageable
 # memory makes the host wait for all earlier work of the stream; from pinned memory it is
-# asynchronous.  64 slots per batch size: a slot is reused only after 63 later FPS calls.
-_start_ring: dict[int, tuple[list, list]] = {}
+# asynchronous.  Every slot carries the CUDA event of its last copy: the host rewrites a slot only
+# after that copy has run, however far it is ahead of the GPU (a step runner never drains the
+# stream between steps).
+_START_RING_SLOTS = 64
+_start_ring: dict[int, list] = {}
 
 
 def _draw_start(B: int, N: int, device) -> torch.Tensor:
@@ -93,13 +96,22 @@ def _draw_start(B: int, N: int, device) -> torch.Tensor:
     host = torch.randint(0, N, (B,), dtype=torch.long)
     ring = _start_ring.get(B)
     if ring is None:
-        ring = ([torch.empty(B, dtype=torch.long).pin_memory() for _ in range(64)], [0])
+        ring = [[torch.empty(B, dtype=torch.long).pin_memory() for _ in range(_START_RING_SLOTS)],
+                [None] * _START_RING_SLOTS, 0]
         _start_ring[B] = ring
-    bufs, pos = ring
-    buf = bufs[pos[0] % len(bufs)]
-    pos[0] += 1
+    bufs, events, pos = ring
+    slot = pos % _START_RING_SLOTS
+    ring[2] = pos + 1
+    if events[slot] is not None:
+        events[slot].synchronize()                 # the copy that last read this slot has completed
+    buf = bufs[slot]
     buf.copy_(host)
-    return buf.to(device, non_blocking=True)
+    out = buf.to(device, non_blocking=True)
+    if not torch.cuda.is_current_stream_capturing():
+        ev = torch.cuda.Event()
+        ev.record()
+        events[slot] = ev
+    return out
 
 
 def _err_counter(dev: torch.device) -> torch.Tensor:
@@ -763,9 +775,21 @@ class PackedMLP:
         self.ok = self.smem <= 200 * 1024 and maxw <= 256 and self.nlayers <= 3
 
 
+# Bumped by everything that rewrites parameters or BatchNorm buffers behind autograd's back (the step runner's fused
+# Adam and BN kernels write through raw pointers, CUDA-graph replays run no Python at all): tensor `_version`
+# counters do not see those updates, so the folded-weight cache below also keys on this generation.
+_param_generation = 0
+
+
+def bump_param_generation() -> None:
+    global _param_generation
+    _param_generation += 1
+
+
 def packed_mlp(owner, key, convs, bns, c_in):
     """Cache of PackedMLP per module, invalidated when a parameter / running statistic changes."""
-    ver = tuple(t._version for m in list(convs) + list(bns) for t in list(m.parameters()) + list(m.buffers()))
+    ver = (_param_generation,) + tuple(t._version for m in list(convs) + list(bns)
+                                       for t in list(m.parameters()) + list(m.buffers()))
     cache = owner.__dict__.setdefault("_pcb_packed", {})
     hit = cache.get(key)
     if hit is None or hit[0] != ver:

@@ -2,11 +2,13 @@
 Partsize-identical/models/pointnet2_sem_seg.py (same `get_model(num_classes)` / `get_loss()`,
 same parameter names, same [B,9,N] -> ([B,N,num_classes] log-probabilities, l4_points) contract).
 """
+import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
 from .. import ops
-from .pointnet_util import PointNetFeaturePropagation, PointNetSetAbstraction, _rows, conv_bn_relu_rows
+from .pointnet_util import (PointNetFeaturePropagation, PointNetSetAbstraction, _rows, conv_bn_relu_rows,
+                            farthest_point_sample, index_points, query_ball_point)
 
 
 class get_model(nn.Module):
@@ -26,17 +28,46 @@ class get_model(nn.Module):
         self.bn1 = nn.BatchNorm1d(128)
         self.drop1 = nn.Dropout(0.5)
 
-    def forward(self, xyz):
+    def forward(self, xyz, pre=None):
+        # pre: the dictionary of `index_chain(xyz)` (indices computed ahead of the step) or None
+        sa = pre["sa"] if pre is not None else (None,) * 4
+        fp = pre["fp"] if pre is not None else (None,) * 4
         l0_points, l0_xyz = xyz, xyz[:, :3, :]
-        l1_xyz, l1_points = self.sa1(l0_xyz, l0_points)
-        l2_xyz, l2_points = self.sa2(l1_xyz, l1_points)
-        l3_xyz, l3_points = self.sa3(l2_xyz, l2_points)
-        l4_xyz, l4_points = self.sa4(l3_xyz, l3_points)
-        l3_points = self.fp4(l3_xyz, l4_xyz, l3_points, l4_points)
-        l2_points = self.fp3(l2_xyz, l3_xyz, l2_points, l3_points)
-        l1_points = self.fp2(l1_xyz, l2_xyz, l1_points, l2_points)
-        l0_points = self.fp1(l0_xyz, l1_xyz, None, l1_points)
+        l1_xyz, l1_points = self.sa1(l0_xyz, l0_points, sa[0])
+        l2_xyz, l2_points = self.sa2(l1_xyz, l1_points, sa[1])
+        l3_xyz, l3_points = self.sa3(l2_xyz, l2_points, sa[2])
+        l4_xyz, l4_points = self.sa4(l3_xyz, l3_points, sa[3])
+        l3_points = self.fp4(l3_xyz, l4_xyz, l3_points, l4_points, fp[0])
+        l2_points = self.fp3(l2_xyz, l3_xyz, l2_points, l3_points, fp[1])
+        l1_points = self.fp2(l1_xyz, l2_xyz, l1_points, l2_points, fp[2])
+        l0_points = self.fp1(l0_xyz, l1_xyz, None, l1_points, fp[3])
         return _seg_head(self, l0_points), l4_points
+
+    @staticmethod
+    def _ball_indices(m, xyz_r, new_xyz):
+        return [query_ball_point(m.radius, m.nsample, xyz_r, new_xyz)]
+
+    @torch.no_grad()
+    def index_chain(self, xyz):
+        """Every sampling / grouping / interpolation index of one forward pass.  They are functions of the input
+        coordinates only (each level's centroids are exact gathers of the level below), so a step runner can compute
+        them for the NEXT batch on a side stream while the current batch trains (engine.Trainer.prefetch) -- farthest
+        point sampling is a serial chain that keeps 16 of 148 SMs busy for a tenth of the step.  Same calls, same order,
+        same CPU-generator draws for the FPS start indices as the forward pass itself (pointnet_util.py:66-112,
+        316-328).  xyz: the network input [B, 9, N].  Returns {"sa": [(new_xyz, [idx...])] * 4, "fp": [(idx, weight)] * 4}
+        (fp in the order fp4, fp3, fp2, fp1) for `forward(xyz, pre=...)`."""
+        cur = _rows(xyz[:, :3, :])
+        levels, sa, fp = [cur], [], []
+        for i in (1, 2, 3, 4):
+            m = getattr(self, f"sa{i}")
+            new_xyz = index_points(cur, farthest_point_sample(cur, m.npoint))
+            sa.append((new_xyz, self._ball_indices(m, cur, new_xyz)))
+            levels.append(new_xyz)
+            cur = new_xyz
+        for lvl in (3, 2, 1, 0):
+            _, idx, weight = ops.three_nn(levels[lvl], levels[lvl + 1], 3)
+            fp.append((idx, weight))
+        return {"sa": sa, "fp": fp}
 
 
 def _seg_head(net, feats_bcn):

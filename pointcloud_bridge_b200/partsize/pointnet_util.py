@@ -186,10 +186,17 @@ class PointNetSetAbstraction(nn.Module):
             self.mlp_bns.append(nn.BatchNorm2d(out))
             last = out
 
-    def forward(self, xyz, points):
+    def forward(self, xyz, points, pre=None):
+        # pre: (new_xyz [B,S,3], [idx [B,S,K]]) computed ahead of the step (get_model.index_chain) or None
         xyz_r = _rows(xyz)
         pts_r = _rows(points) if points is not None else None
         B = xyz_r.shape[0]
+        if pre is not None and not self.group_all:
+            new_xyz, (idx,) = pre
+            grouped = ops.group_points(xyz_r, pts_r, new_xyz, idx, xyz_first=True, pad_to=8)
+            S, K, C = grouped.shape[1:]
+            y = mlp_rows(grouped.reshape(B * S * K, C), self.mlp_convs, self.mlp_bns, pool_k=K)
+            return new_xyz.permute(0, 2, 1), _cf_view(y, B, S)
         if not self.group_all and ops.fused_inference_enabled() and not self.mlp_bns[0].training:
             pk = ops.packed_mlp(self, 0, self.mlp_convs, self.mlp_bns, 3 + (pts_r.shape[2] if pts_r is not None else 0))
             if pk.ok and self.nsample <= 128:
@@ -225,15 +232,19 @@ class PointNetSetAbstractionMsg(nn.Module):
             self.conv_blocks.append(convs)
             self.bn_blocks.append(bns)
 
-    def forward(self, xyz, points):
+    def forward(self, xyz, points, pre=None):
+        # pre: (new_xyz [B,S,3], [idx per radius]) computed ahead of the step (get_model.index_chain) or None
         xyz_r = _rows(xyz)
         pts_r = _rows(points) if points is not None else None
         B = xyz_r.shape[0]
         S = self.npoint
-        new_xyz = index_points(xyz_r, farthest_point_sample(xyz_r, S))
         outs, joined = [], None
-        # every radius in one scan of the cloud (the reference calls query_ball_point once per radius, :250)
-        idxs = ops.ball_query_multi(self.radius_list, self.nsample_list, xyz_r, new_xyz)
+        if pre is not None:
+            new_xyz, idxs = pre
+        else:
+            new_xyz = index_points(xyz_r, farthest_point_sample(xyz_r, S))
+            # every radius in one scan of the cloud (the reference calls query_ball_point once per radius, :250)
+            idxs = ops.ball_query_multi(self.radius_list, self.nsample_list, xyz_r, new_xyz)
         groupeds = None
         if self.training and xyz_r.is_cuda and pts_r is not None and pts_r.requires_grad:
             # all scales grouped by one autograd node: their scatter-add backward shares one gradient buffer
@@ -278,14 +289,18 @@ class PointNetFeaturePropagation(nn.Module):
             self.mlp_bns.append(nn.BatchNorm1d(out))
             last = out
 
-    def forward(self, xyz1, xyz2, points1, points2):
+    def forward(self, xyz1, xyz2, points1, points2, pre=None):
+        # pre: (idx [B,N,3], weight [B,N,3]) of the three nearest xyz2 points, computed ahead of the step, or None
         x1, x2, p2 = _rows(xyz1), _rows(xyz2), _rows(points2)
         B, N, _ = x1.shape
         S = x2.shape[1]
         if S == 1:
             interp = p2.repeat(1, N, 1)
         else:
-            _, idx, weight = ops.three_nn(x1, x2, 3)
+            if pre is not None:
+                idx, weight = pre
+            else:
+                _, idx, weight = ops.three_nn(x1, x2, 3)
             p1 = _rows(points1) if points1 is not None else None
             if self.mlp_bns[0].training and ops.fp_concat_supported(p1, p2):
                 # bf16 training: interpolate + concat + cast in one pass, rows padded for the GEMM

@@ -279,3 +279,168 @@ def test_bristrunet_training_forward_fused_rows_vs_plain(g, monkeypatch):
         assert torch.isfinite(flat).all() and flat.abs().max().item() > 0
     print("BriStruNet train loss plain / fused:", losses)
     assert abs(losses["plain"] - losses["fused"]) <= 2e-2 * max(1.0, abs(losses["plain"]))
+
+
+def test_index_chain_precomputed_equals_inline(g):
+    """get_model.index_chain + forward(pre=...) == the plain forward: same CPU-generator draws, same indices, so the
+    training-mode loss is bit-identical (SSG and MSG)."""
+    x9, _, _, lab = inputs(g)
+    for mod, classes, seed in ((ssg, 13, 1), (msg, 5, 2)):
+        losses = []
+        for use_pre in (False, True):
+            torch.manual_seed(3)
+            net = parity.seeded_fill_(mod.get_model(classes), seed).to(DEV).train()
+            net.drop1.eval()
+            torch.manual_seed(SEED_FPS)
+            pre = net.index_chain(x9) if use_pre else None
+            y, _ = net(x9, pre=pre)
+            losses.append(float(F.nll_loss(y.reshape(-1, classes), lab.reshape(-1) % classes).item()))
+        assert losses[0] == losses[1], (mod.__name__, losses)
+
+
+def test_graph_steps_without_host_sync_follow_the_eager_sequence(g):
+    """The host runs several replays ahead of the GPU (no .item() between steps): the FPS start indices of every
+    step must still be the ones the eager sequence draws -- the pinned staging buffers are rewritten only after their
+    copies have run.  lr = 0, so the loss depends on the start indices only.  Both the prefetch pipeline (indices
+    computed ahead on a side stream) and the in-graph sampling path (PCB_NO_INDEX_PREFETCH) are checked."""
+    from pointcloud_bridge_b200.engine import Trainer
+    x9, _, _, lab = inputs(g)
+    x = x9.repeat(4, 1, 1)                                  # 8 blocks: a step long enough for the host to run ahead
+    labs = lab.repeat(4, 1)
+    nsteps = 10
+
+    def run(graph, prefetch, chain=True):
+        torch.manual_seed(7)
+        net = parity.seeded_fill_(msg.get_model(5), 2).to(DEV).train()
+        net.drop1.eval()
+        for m in net.modules():
+            if isinstance(m, torch.nn.modules.batchnorm._BatchNorm):
+                m.momentum = 0.0
+        tr = Trainer(net, amp=False, graph=graph, lr=0.0, weight_decay=0.0)
+        tr._use_chain = chain
+        out = torch.zeros(nsteps, device=DEV)
+        torch.manual_seed(11)
+        if prefetch:
+            tr.prefetch(x, labels=labs)
+            for i in range(nsteps):
+                out[i].copy_(tr.step_prefetched())
+                tr.prefetch(x, labels=labs)
+        else:
+            for i in range(nsteps):
+                out[i].copy_(tr.step(x, labels=labs))
+        torch.cuda.synchronize()
+        return out.cpu().numpy()
+
+    ref = run(False, False)
+    assert len(set(np.round(ref, 4))) > 4                   # the starts really vary per step
+    for graph, prefetch, chain in ((True, False, True), (True, True, True), (False, True, True), (True, False, False)):
+        got = run(graph, prefetch, chain)
+        assert np.allclose(got, ref, rtol=2e-5, atol=0), (graph, prefetch, chain, got, ref)
+
+
+def test_eval_after_training_steps_uses_current_weights(g, monkeypatch):
+    """The fused tcgen05 inference block caches folded conv+BN weights.  The step runner updates parameters and running
+    statistics through raw pointers (and CUDA-graph replays run no Python), so the cache is keyed on a parameter
+    generation that every step bumps: eval logits after N replayed steps must equal the unfused evaluation."""
+    from pointcloud_bridge_b200 import ops
+    from pointcloud_bridge_b200.engine import Trainer
+    x9, _, _, lab = inputs(g)
+    torch.manual_seed(7)
+    net = parity.seeded_fill_(ssg.get_model(5), 1).to(DEV).train()
+    tr = Trainer(net, amp=True, graph=True, lr=1e-2, weight_decay=0.0)
+
+    def evaluate():
+        net.eval()
+        torch.manual_seed(SEED_FPS)
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+            y, _ = net(x9)
+        net.train()
+        return y.float()
+
+    torch.manual_seed(11)
+    tr.step(x9, labels=lab)
+    first = evaluate()                                        # fills the cache
+    for _ in range(6):
+        tr.step(x9, labels=lab)
+    fused = evaluate()
+    monkeypatch.setenv("PCB_NO_FUSED", "1")
+    plain = evaluate()
+    monkeypatch.delenv("PCB_NO_FUSED")
+    scale = float(plain.abs().max())
+    assert float((first - plain).abs().max()) > 5e-2 * scale, "the weights did not move: the test would prove nothing"
+    assert float((fused - plain).abs().mean()) < 1e-2 * scale
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_msg_b16_benchmarked_configuration_pinned_to_reference(seed):
+    """The configuration bench.py times -- PointNet++ MSG train step, 16 x 4096 points, Trainer(amp=True, graph=True),
+    196 -> 200 channel padding ON -- against one training step of the unmodified reference at that size
+    (tests/golden/msg_train_b16.npz, CPU fp32, two seeds).
+      * level-1 FPS indices: bit-exact;
+      * fp32 eager step: loss and log-probabilities at the fp32 bar;
+      * bf16 graph step: loss and log-probabilities within north_star's 1e-2 (relative to max|logp|), asserted on the MAX;
+      * gradients: this randomly initialised network amplifies a forward perturbation into its gradients by ~5e4 (the
+        reference's own CPU gradients move by 5e-3 between 1 and 8 threads, i.e. under 1e-7 summation noise), so bf16
+        gradients are compared by their distance to the fp32 golden with and without the channel padding: padding must
+        not be further away than the unpadded path (it is a mathematical no-op; what differs is rounding)."""
+    from pointcloud_bridge_b200 import ops
+    from pointcloud_bridge_b200.engine import Trainer
+    gold = parity.load("msg_train_b16.npz")
+    p = f"s{seed}_"
+    xyz, rgb, lab = synthetic.bridge_batch(100 + seed, 16)
+    x9 = torch.from_numpy(synthetic.sem_seg_input(xyz, rgb)).to(DEV)
+    tlab = torch.from_numpy(lab).to(DEV)
+    ref_loss = float(gold[p + "loss"])
+    ref_logp = gold[p + "logp_sample"]
+    scale = float(np.abs(ref_logp).max())
+    names = [k[len(p) + 2:] for k in gold.files if k.startswith(p + "g_")]
+
+    # indices
+    torch.manual_seed(SEED_FPS + seed)
+    fps1 = ops.furthest_point_sample(x9[:, :3, :].permute(0, 2, 1).contiguous(), 1024)
+    assert np.array_equal(fps1.cpu().numpy().astype(np.int16), gold[p + "fps1"])
+
+    # fp32 eager
+    net = parity.seeded_fill_(msg.get_model(5), 2).to(DEV).train()
+    net.drop1.eval()
+    torch.manual_seed(SEED_FPS + seed)
+    y, _ = net(x9)
+    loss = F.nll_loss(y.reshape(-1, 5), tlab.reshape(-1))
+    loss.backward()
+    e_logp = float(np.abs(y.detach().cpu().numpy()[:, ::16, :] - ref_logp).max()) / scale
+    print(f"fp32: loss {float(loss):.7f} vs {ref_loss:.7f}, logp max rel err {e_logp:.2e}")
+    assert abs(float(loss) - ref_loss) <= 1e-5 * abs(ref_loss)
+    assert e_logp < 5e-5          # measured 1e-5..3e-5: GEMM / BN summation order (cuBLAS vs MKL), 34 BN layers deep
+    params = dict(net.named_parameters())
+    rel = lambda a, b: float(np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-20))
+    fp32_g = {n: rel(params[n].grad.cpu().numpy(), gold[p + "g_" + n]) for n in names}
+    print("fp32 gradient distance to the reference:", {n: round(v, 4) for n, v in fp32_g.items()})
+
+    # bf16 graph step, padded (benchmarked) and unpadded
+    dist = {}
+    for pad in (True, False):
+        old = ops._PAD_N
+        ops._PAD_N = pad
+        try:
+            net = parity.seeded_fill_(msg.get_model(5), 2).to(DEV).train()
+            net.drop1.eval()
+            tr = Trainer(net, amp=True, graph=True, lr=0.0, weight_decay=0.0)
+            for _ in range(4):                                # 3 eager warm-up steps + capture
+                tr.step(x9, labels=tlab)
+            torch.manual_seed(SEED_FPS + seed)
+            loss = tr.step(x9, labels=tlab)                   # a pure replay with the reference's draws
+            torch.cuda.synchronize()
+            logp = tr._last_logits.log_probs().float().cpu().numpy()[:, ::16, :]
+            e = float(np.abs(logp - ref_logp).max()) / scale
+            print(f"bf16 graph pad={pad}: loss {float(loss):.5f} vs {ref_loss:.5f}, logp max rel err {e:.2e}")
+            assert abs(float(loss) - ref_loss) <= 1e-2 * abs(ref_loss)
+            assert e < 1e-2, e
+            views = {n: v for (n, _), v in zip(net.named_parameters(), tr.bucket.views)}
+            dist[pad] = {n: rel(views[n].cpu().numpy(), gold[p + "g_" + n]) for n in names}
+        finally:
+            ops._PAD_N = old
+    print("bf16 gradient distance to the fp32 reference, padded:  ", {n: round(v, 3) for n, v in dist[True].items()})
+    print("bf16 gradient distance to the fp32 reference, unpadded:", {n: round(v, 3) for n, v in dist[False].items()})
+    med = lambda d: float(np.median(list(d.values())))
+    assert med(dist[True]) <= 1.5 * med(dist[False]) + 0.02, (med(dist[True]), med(dist[False]))
+    assert dist[True]["conv2.weight"] < 0.05 and dist[True]["conv2.bias"] < 0.05      # no BN stack below: plain bf16 noise
