@@ -172,6 +172,9 @@ int pcb_graph_feature_bwd_f32(const float *grad_out, const int64_t *idx, int B, 
  * out_pitch / gz_pitch (elements, 0 = C): `out` resp. `gz` may be a column slice of a wider row-major buffer -- the
  * scales of a multi-scale module write straight into their concatenated output and read their slice of its gradient. */
 int64_t pcb_bn_work_floats(int C);
+/* SMs the cooperative BN grids are sized for from now on (0 = all): lets a step runner keep a few SMs free for a
+ * long-running kernel of another stream (FPS of the next batch) that would otherwise stall every cooperative launch. */
+int pcb_bn_set_coop_sms(int sms);
 int pcb_bn_fwd_rows(const void *y, int dtype, int64_t M, int C, int Cv, int pool_k, const float *bias, const float *gamma,
                     const float *beta, float eps, float momentum, float *running_mean, float *running_var, int relu,
                     float *mean, float *invstd, void *out, int64_t out_pitch, unsigned char *argmax, float *work,

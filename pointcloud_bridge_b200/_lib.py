@@ -64,7 +64,7 @@ _SIGNATURES = {
 }
 
 EXPORTS = ["pcb_version", "pcb_error_string", "pcb_bn_work_floats", "pcb_nll_rows_blocks", "pcb_gemm_work_floats",
-           "pcb_gemm_tickets", *_SIGNATURES]
+           "pcb_gemm_tickets", "pcb_bn_set_coop_sms", *_SIGNATURES]
 
 
 class PcbError(RuntimeError):
@@ -92,6 +92,8 @@ def lib():
         l.pcb_gemm_work_floats.argtypes = [_i64, _i, _i]
         l.pcb_gemm_tickets.restype = _i
         l.pcb_gemm_tickets.argtypes = []
+        l.pcb_bn_set_coop_sms.restype = _i
+        l.pcb_bn_set_coop_sms.argtypes = [_i]
         for name, args in _SIGNATURES.items():
             fn = getattr(l, name)
             fn.restype = _i

@@ -239,13 +239,8 @@ PCB_API int pcb_ball_query_multi_f32(const float *xyz, const float *new_xyz, int
     const int chunk = N < kBqMultiChunk ? ((N + 3) & ~3) : kBqMultiChunk;
     const int use_bulk = ((reinterpret_cast<uintptr_t>(xyz) & 15) == 0) && (N % 4 == 0);
     const size_t smem = (size_t)chunk * 28;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(ball_query_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             kBqMultiChunk * 28);
-        if (e != cudaSuccess) return (int)e;
-        attr_set = true;
-    }
+    static bool attr_set[kMaxDevices] = {};
+    if (cudaError_t e = smem_optin_once(ball_query_multi_kernel, kBqMultiChunk * 28, attr_set)) return (int)e;
     dim3 grid((unsigned)ceil_div(S, kBqWarps), (unsigned)B);
     ball_query_multi_kernel<<<grid, kBqWarps * 32, smem, (cudaStream_t)stream>>>(xyz, new_xyz, N, S, p, chunk, use_bulk);
     PCB_RETURN_LAUNCH_STATUS();
@@ -263,13 +258,8 @@ PCB_API int pcb_ball_query_f32(const float *xyz, const float *new_xyz, int B, in
     // chunk length*12 must be multiples of 16
     int use_bulk = ((reinterpret_cast<uintptr_t>(xyz) & 15) == 0) && (N % 4 == 0);
     size_t smem = (size_t)chunk * 16;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(ball_query_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             kBqChunk * 16);
-        if (e != cudaSuccess) return (int)e;
-        attr_set = true;
-    }
+    static bool attr_set[kMaxDevices] = {};
+    if (cudaError_t e = smem_optin_once(ball_query_kernel, kBqChunk * 16, attr_set)) return (int)e;
     dim3 grid((unsigned)ceil_div(S, kBqWarps), (unsigned)B);
     ball_query_kernel<<<grid, kBqWarps * 32, smem, (cudaStream_t)stream>>>(xyz, new_xyz, N, S, radius2, nsample,
                                                                           out_idx, chunk, use_bulk);

@@ -861,18 +861,32 @@ static int stream_grid(int64_t units, int C, int V)
 // ---------------------------------------------------------------------------------------------
 // launch
 // ---------------------------------------------------------------------------------------------
+// SMs the cooperative grids are sized for (0 = all).  A step runner that overlaps a long-running kernel of another
+// stream with the step (the FPS chain of the next batch: one persistent CTA per cloud for ~0.3 ms) leaves that many
+// SMs out: a cooperative grid needs ALL of its CTAs resident at once, so a grid sized for every SM would stall each of
+// the ~70 cooperative launches of a step until the other stream's kernel has finished.
+static int g_coop_sms = 0;
+
 // co-resident CTAs of `kernel` on the current device (cooperative launch limit), capped at
-// PCB_BN_CTAS_PER_SM per SM (default 2) and kBnMaxParts in total
+// PCB_BN_CTAS_PER_SM per SM (default 2) and kBnMaxParts in total; the occupancy query is cached per device
 template <typename K>
-static int coop_capacity(K kernel)
+static int coop_capacity(K kernel, int (&occ_cache)[kMaxDevices])
 {
-    int dev = 0, sms = 0, occ = 0;
+    int dev = 0, sms = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kBnThreads, 0);
-    const char *e = getenv("PCB_BN_CTAS_PER_SM");
-    const int cap = e ? atoi(e) : 2;
-    if (cap >= 1 && occ > cap) occ = cap;
+    int occ = (dev >= 0 && dev < kMaxDevices) ? occ_cache[dev] : 0;
+    if (occ == 0) {
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kBnThreads, 0);
+        const char *e = getenv("PCB_BN_CTAS_PER_SM");
+        const int cap = e ? atoi(e) : 2;
+        if (cap >= 1 && occ > cap) occ = cap;
+        if (occ < 1) occ = 1;
+        if (dev >= 0 && dev < kMaxDevices) occ_cache[dev] = occ;
+    }
+    const char *es = getenv("PCB_BN_SMS");
+    int limit = g_coop_sms > 0 ? g_coop_sms : (es ? atoi(es) : 0);
+    if (limit >= 1 && limit < sms) sms = limit;
     int g = occ * sms;
     if (g > kBnMaxParts) g = kBnMaxParts;
     return g < 1 ? 1 : g;
@@ -910,7 +924,8 @@ static int coop_launch(K kernel, int grid, const A &args, cudaStream_t st)
 template <typename T, int V>
 static int bn_fwd_launch(BnFwdArgs a, cudaStream_t st)
 {
-    static const int cap = coop_capacity(bn_fwd_fused_kernel<T, V>);
+    static int occ_cache[kMaxDevices] = {};
+    const int cap = coop_capacity(bn_fwd_fused_kernel<T, V>, occ_cache);
     const Plan p = make_plan(a.M, a.C, V, cap);           // statistics are over rows, pooled or not
     a.upc = p.upc, a.nparts = p.nparts;
     int grid = p.grid;
@@ -924,7 +939,8 @@ static int bn_fwd_launch(BnFwdArgs a, cudaStream_t st)
 template <typename T, int V>
 static int bn_bwd_launch(BnBwdArgs a, cudaStream_t st)
 {
-    static const int cap = coop_capacity(bn_bwd_fused_kernel<T, V>);
+    static int occ_cache[kMaxDevices] = {};
+    const int cap = coop_capacity(bn_bwd_fused_kernel<T, V>, occ_cache);
     const Plan p = make_plan(a.M / a.pool_k, a.C, V, cap);
     a.upc = p.upc, a.nparts = p.nparts;
     return coop_launch(bn_bwd_fused_kernel<T, V>, p.grid, a, st);
@@ -949,6 +965,12 @@ PCB_API int pcb_bn_debug_trace(unsigned long long *host_out)
 #endif
 
 PCB_API int64_t pcb_bn_work_floats(int C) { return 3 * (int64_t)C * (1 + kBnMaxParts); }
+
+PCB_API int pcb_bn_set_coop_sms(int sms)
+{
+    g_coop_sms = sms > 0 ? sms : 0;
+    return 0;
+}
 
 PCB_API int pcb_bn_fwd_rows(const void *y, int dtype, int64_t M, int C, int Cv, int pool_k, const float *bias,
                             const float *gamma, const float *beta, float eps, float momentum, float *running_mean,

@@ -1045,13 +1045,8 @@ PCB_API int pcb_graph_feature_f32(const float *x, const int64_t *idx, int B, int
         const unsigned quantum = kGfsThreads * 4;
         unsigned eps = (unsigned)ceil_div(ceil_div(NK, splits), quantum) * quantum;
         splits = (unsigned)ceil_div(NK, eps);
-        static bool attr_set = false;
-        if (!attr_set) {
-            cudaError_t e = cudaFuncSetAttribute(graph_feature_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                 96 * 1024);
-            if (e != cudaSuccess) return (int)e;
-            attr_set = true;
-        }
+        static bool attr_set[kMaxDevices] = {};
+        if (cudaError_t e = smem_optin_once(graph_feature_smem_kernel, 96 * 1024, attr_set)) return (int)e;
         dim3 grid(splits, groups, (unsigned)B);
         graph_feature_smem_kernel<<<grid, kGfsThreads, smem, (cudaStream_t)stream>>>(x, idx, D, N, make_fastdiv(k), NK, eps, out);
         PCB_RETURN_LAUNCH_STATUS();

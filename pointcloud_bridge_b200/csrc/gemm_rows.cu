@@ -561,14 +561,8 @@ static int gemm_launch(GemmParams &p, cudaStream_t st)
     GemmPlan g;
     if (!gemm_plan(p.M, p.N, p.K, EPI, g)) return PCB_ERANGE;
     p.BN = g.BN, p.BK = g.BK, p.stages = g.stages, p.mtiles = g.mtiles, p.ntiles = g.ntiles;
-    static int attr_dev[16] = {0};                                           // per device: opt-in to > 48 KB of shared memory
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev < 0 || dev >= 16 || !attr_dev[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_rows_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
-        if (e != cudaSuccess) return (int)e;
-        if (dev >= 0 && dev < 16) attr_dev[dev] = 1;
-    }
+    static bool attr_set[kMaxDevices] = {};
+    if (cudaError_t e = smem_optin_once(gemm_rows_kernel<EPI>, 224 * 1024, attr_set)) return (int)e;
     gemm_rows_kernel<EPI><<<dim3((unsigned)g.grid_x, (unsigned)g.ntiles), kGemmThreads, g.smem, st>>>(p);
     PCB_RETURN_LAUNCH_STATUS();
 }

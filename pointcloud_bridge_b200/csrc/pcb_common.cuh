@@ -19,6 +19,21 @@
 
 namespace pcb {
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel call site, device): function attributes are per
+// device, so a process that drives several GPUs must opt in on each of them.  `flags` is the call site's own
+// zero-initialised static array.
+constexpr int kMaxDevices = 64;
+template <typename K>
+static inline cudaError_t smem_optin_once(K kernel, int bytes, bool (&flags)[kMaxDevices])
+{
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < kMaxDevices && flags[dev]) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess && dev >= 0 && dev < kMaxDevices) flags[dev] = true;
+    return e;
+}
+
 __host__ __device__ __forceinline__ int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // |p|^2 exactly as ATen's CPU sum(v**2, -1) evaluates it for three components:

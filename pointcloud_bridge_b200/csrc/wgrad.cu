@@ -202,12 +202,8 @@ PCB_API int pcb_wgrad_rows_bf16(const void *gy, const void *x, int64_t M, int N,
     const int64_t rows_per_split = ceil_div(chunks, splits) * kWgTile;
     splits = ceil_div(M, rows_per_split);
     const size_t smem = (size_t)kWgStages * 2 * kWgTileBytes;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(wgrad_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-        attr_set = true;
-    }
+    static bool attr_set[kMaxDevices] = {};
+    if (cudaError_t e = smem_optin_once(wgrad_rows_kernel, (int)smem, attr_set)) return (int)e;
     dim3 grid((unsigned)tiles, (unsigned)splits);
     wgrad_rows_kernel<<<grid, kWgThreads, smem, (cudaStream_t)stream>>>(
         (const __nv_bfloat16 *)gy, (const __nv_bfloat16 *)x, M, N, K, ldgy, ldx, tiles_k, rows_per_split, gw, ldw);

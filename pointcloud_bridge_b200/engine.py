@@ -293,7 +293,16 @@ class Trainer:
         step: the H2D transfer runs while that step computes."""
         dev = self.bucket.flat.device
         if self._pf_stream is None:
-            self._pf_stream = torch.cuda.Stream(device=dev)
+            # high priority: the index chain's few persistent CTAs (FPS: one per cloud) take an SM as soon as one frees up
+            self._pf_stream = torch.cuda.Stream(device=dev, priority=-1)
+            if self._use_chain and self._g is None:
+                # ... and the cooperative BN grids of the step leave those SMs out (csrc/bn_rows.cu: g_coop_sms), otherwise
+                # every cooperative launch waits for the whole FPS kernel.  Grid sizes are frozen at capture: set it first.
+                from . import _lib
+                sms = torch.cuda.get_device_properties(dev).multi_processor_count
+                clouds = int(inputs[0].shape[0]) if inputs else 0
+                reserve = int(os.environ.get("PCB_PREFETCH_SMS", str(min(clouds, sms // 4))))
+                _lib.lib().pcb_bn_set_coop_sms(sms - reserve if reserve > 0 else 0)
         srcs = list(inputs) + [labels] + list(loss_inputs)
         if self._pf_bufs is None or [tuple(b.shape) for b in self._pf_bufs] != [tuple(t.shape) for t in srcs]:
             self._pf_bufs = [torch.empty(t.shape, dtype=t.dtype, device=dev) for t in srcs]
@@ -334,8 +343,13 @@ class Trainer:
         """One optimisation step on this rank's batch; returns the (device) loss tensor.
         pre: the batch's precomputed indices (`net.index_chain`), normally handed over by `step_prefetched`; computed
         here, on the step's own stream, when the network has an index chain and none was given."""
-        if self._use_chain and pre is None:
-            pre = self.net.index_chain(inputs[0])
+        replay = self.graph and self._warm >= 3 and self._g is not None
+        if not replay:                                       # eager, warm-up and capture steps want device tensors
+            dev = self.bucket.flat.device
+            put = lambda t: t if t.is_cuda else t.to(dev, non_blocking=True)
+            inputs, labels, loss_inputs = tuple(put(t) for t in inputs), put(labels), tuple(put(t) for t in loss_inputs)
+            if self._use_chain and pre is None:
+                pre = self.net.index_chain(inputs[0])
         if not self.graph:
             return self._step_eager(inputs, labels, loss_inputs, pre)
         if self._warm < 3:                                  # eager warm-up steps on a side stream
@@ -365,6 +379,8 @@ class Trainer:
             dst.copy_(src, non_blocking=True)
         if self._static_pre is not None:
             from torch.utils import _pytree as pytree
+            if pre is None:                                  # no prefetch: the index chain runs here, on the step's stream
+                pre = self.net.index_chain(self._static[0][0])
             torch._foreach_copy_(self._static_pre_flat, pytree.tree_flatten(pre)[0])
         if self._mark_consumed:             # the prefetch staging buffers are free again: the next copy may start
             self._note_consumed()
