@@ -3,8 +3,7 @@
 blocks per GPU, bf16 autocast (BASELINE.json configs[1]) -> points/sec.
 
     python bench.py --gpus N --steps K --warmup W            # our arm (B200 kernels)
-    python bench.py --impl reference --gpus N --steps K ...  # CPU arm: the oracle's restatement
-                                                             # of the reference path on host cores
+    python bench.py --impl reference --gpus N --steps K ...  # CPU arm: the reference itself on host cores
     torchrun ... bench.py --gpus N ...                       # N > 1: one rank per GPU, NCCL
 
 One JSON line on stdout (rank 0).  A step = forward + NLL loss + backward + one flat NCCL
@@ -12,8 +11,9 @@ gradient all-reduce (N > 1) + fused Adam on one synthetic batch already resident
 (`value`); `e2e` repeats the measurement through the public API with the batch coming from
 pinned host memory each step and the loss read back.  `roofline` describes the kernel of ours
 with the largest share of the step, timed live with CUDA events in an instrumented pass;
-`cpu_baseline` is the oracle port of the reference path timed on this host's cores on a
-bounded sample (rank 0, N = 1).
+`cpu_baseline` / `--impl reference` time the UNMODIFIED reference (oracle/_ref, copied there by
+oracle/make_ref.py; the oracle's port if absent) on this host's cores on a bounded sample
+(rank 0, N = 1).
 """
 from __future__ import annotations
 
@@ -119,27 +119,53 @@ class ClockSampler:
 # CPU arm: oracle port of the reference path (the only place bench.py executes oracle/)
 # ------------------------------------------------------------------------------------------------
 def cpu_msg_train_points_per_sec(blocks, steps, warmup, threads=None):
-    import numpy as np
+    """MSG train step (forward + NLL + backward + Adam) on the host cores.  With oracle/_ref present (the unmodified
+    reference files, oracle/make_ref.py) this IS the reference: its get_model, its pointnet_util functions, torch CPU
+    fp32 -> kind "reference"; otherwise the oracle's port (C primitives + torch CPU ops) -> kind "port"."""
+    import contextlib
+    import io
     import torch
-    from oracle import oracle as orc
-    from oracle import ref_models
+    from oracle import make_ref
     from pointcloud_bridge_b200 import synthetic
     threads = threads or os.cpu_count() or 1
     torch.set_num_threads(threads)
-    orc.set_num_threads(threads)
     xyz, rgb, lab = synthetic.bridge_batch(123, blocks, NPTS)
     x = torch.from_numpy(synthetic.sem_seg_input(xyz, rgb))
     y = torch.from_numpy(lab)
     torch.manual_seed(0)
-    net = ref_models.PointNet2MSG(NUM_CLASSES).train()
-    opt = torch.optim.Adam(net.parameters(), lr=1e-3, weight_decay=1e-4)
+    if make_ref.available():
+        kind = "reference"
+        net = make_ref.load_msg().get_model(NUM_CLASSES).train()
+        opt = torch.optim.Adam(net.parameters(), lr=1e-3, weight_decay=1e-4)
+
+        def step():
+            opt.zero_grad(set_to_none=True)
+            with contextlib.redirect_stdout(io.StringIO()):       # the reference prints tensor shapes
+                logp, _ = net(x)
+            loss = torch.nn.functional.nll_loss(logp.reshape(-1, NUM_CLASSES), y.reshape(-1))
+            loss.backward()
+            opt.step()
+    else:
+        kind = "port"
+        from oracle import oracle as orc
+        from oracle import ref_models
+        orc.set_num_threads(threads)
+        net = ref_models.PointNet2MSG(NUM_CLASSES).train()
+        opt = torch.optim.Adam(net.parameters(), lr=1e-3, weight_decay=1e-4)
+        step = lambda: ref_models.msg_train_step(net, opt, x, y)
     for _ in range(warmup):
-        ref_models.msg_train_step(net, opt, x, y)
+        step()
     t0 = time.perf_counter()
     for _ in range(steps):
-        ref_models.msg_train_step(net, opt, x, y)
+        step()
     dt = time.perf_counter() - t0
-    return blocks * NPTS * steps / dt, dt / steps, threads
+    return blocks * NPTS * steps / dt, dt / steps, threads, kind
+
+
+def cpu_workload_config(a):
+    return {"workload": "pointnet2_sem_seg_msg train step (fwd+NLL+bwd+Adam), BASELINE configs[1], on the host CPU",
+            "blocks_per_step": a.cpu_sample_blocks, "of_blocks_per_gpu": a.batch, "points_per_block": NPTS, "channels": 9,
+            "num_classes": NUM_CLASSES, "precision": "fp32 (torch CPU)", "launch": "eager PyTorch, all host threads"}
 
 
 def run_reference(a):
@@ -151,13 +177,15 @@ def run_reference(a):
     # bounded: every step is a `blocks`-block sample of the 16-block batch
     steps = max(1, min(a.steps, 20))
     warmup = max(1, min(a.warmup, 2))
-    pps, sec, threads = cpu_msg_train_points_per_sec(blocks, steps, warmup)
-    sample = f"{blocks} of {a.batch} blocks per step, {steps} timed + {warmup} warm-up steps, oracle port (C prims + torch CPU fp32)"
+    pps, sec, threads, kind = cpu_msg_train_points_per_sec(blocks, steps, warmup)
+    what = "unmodified reference from oracle/_ref (torch CPU fp32)" if kind == "reference" else \
+        "oracle port (C prims + torch CPU fp32)"
+    sample = f"{blocks} of {a.batch} blocks per step, {steps} timed + {warmup} warm-up steps, {what}"
     line = {"impl": "reference", "metric": METRIC, "value": pps, "unit": UNIT, "n_gpus": a.gpus, "steps": steps,
             "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(a, max(world, 1)),
-            "cpu_baseline": {"value": pps, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "config": cpu_workload_config(a),
+            "cpu_baseline": {"value": pps, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
             "e2e": {"value": pps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -381,10 +409,11 @@ def run_ours(a):
             "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": gpu_launches, "roofline": roofline}
 
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
-        pps, sec, threads = cpu_msg_train_points_per_sec(a.cpu_sample_blocks, 2, 1)
-        line["cpu_baseline"] = {"value": pps, "unit": UNIT, "cores": threads, "kind": "port",
-                                "sample": f"{a.cpu_sample_blocks} of {B} blocks per step, 2 timed + 1 warm-up steps, "
-                                          "oracle port (C prims + torch CPU fp32), scaled per point"}
+        pps, sec, threads, kind = cpu_msg_train_points_per_sec(a.cpu_sample_blocks, 3, 1)
+        what = "unmodified reference from oracle/_ref" if kind == "reference" else "oracle port (C prims + torch CPU ops)"
+        line["cpu_baseline"] = {"value": pps, "unit": UNIT, "cores": threads, "kind": kind,
+                                "sample": f"{a.cpu_sample_blocks} of {B} blocks per step, 3 timed + 1 warm-up steps, "
+                                          f"{what}, torch CPU fp32, scaled per point"}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
