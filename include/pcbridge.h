@@ -200,23 +200,28 @@ int pcb_wgrad_rows_bf16(const void *gy, const void *x, int64_t M, int N, int K, 
  * the host in float64 as the reference does); x0, y0, stride locate the candidate windows of a point and
  * `reach` = ceil(block_size / stride) + 1 bounds how far below floor((x - x0) / stride) they can start.
  *   count : counts[iy*grid_x + ix] += 1 per member point (counts zeroed by the caller)
- *   fill  : members[offsets[w] + k] = point index, k handed out through cursor[w] (zeroed); offsets = exclusive
- *           prefix sum of counts
- *   blocks: block b takes entries (blk_first[b] + j) mod blk_cnt[b], j < block_points, of the member segment at
- *           blk_off[b] (cyclic padding) -> data [nblocks, block_points, 9] = (x - cx, y - cy, z, r, g, b,
- *           x/ext_x, y/ext_y, z/ext_z) computed in double and rounded to fp32, point_idx [nblocks, block_points]
+ *   fill  : keys[offsets[w] + k] = (w << 47) | (hash16(seed, point, w) << 31) | point index, k handed out through
+ *           cursor[w] (zeroed); offsets = exclusive prefix sum of counts.  The caller sorts `keys` (ascending): every
+ *           window's members are then in a pseudo-random order that does not depend on the order of the atomics;
+ *           members = keys & 0x7fffffff.  grid_x * grid_y < 65536.
+ *   blocks: the padded window has tot = ceil(n / block_points) * block_points entries (n = blk_cnt[b]); entry
+ *           q = blk_first[b] + j of it takes slot s = (1000003 q + seed % 999983) mod tot of the member segment at
+ *           blk_off[b], slots >= n wrapping to (s - n) mod n (the reference's np.random.choice padding + shuffle,
+ *           BridgeDataLoader.py:239-242, from a counter-based hash) -> data [nblocks, block_points, 9] = (x - cx,
+ *           y - cy, z, r, g, b, x/ext_x, y/ext_y, z/ext_z) computed in double and rounded to fp32,
+ *           point_idx [nblocks, block_points]
  *   vote  : pool[point_idx[t] * num_classes + pred[t]] += 1;  vote_argmax: first maximum per point */
 int pcb_scene_window_count_f32(const float *points, int64_t P, int point_stride, int grid_x, int grid_y,
                                const double *lo_x, const double *hi_x, const double *lo_y, const double *hi_y, double x0,
                                double y0, double stride, int reach, int *counts, pcb_stream_t stream);
 int pcb_scene_window_fill_f32(const float *points, int64_t P, int point_stride, int grid_x, int grid_y,
                               const double *lo_x, const double *hi_x, const double *lo_y, const double *hi_y, double x0,
-                              double y0, double stride, int reach, const int64_t *offsets, int *cursor, int *members,
-                              pcb_stream_t stream);
+                              double y0, double stride, int reach, const int64_t *offsets, int *cursor, unsigned seed,
+                              int64_t *keys, pcb_stream_t stream);
 int pcb_scene_blocks_f32(const float *points, int point_stride, const int *members, const int64_t *blk_off,
                          const int *blk_cnt, const int64_t *blk_first, const double *blk_center, int64_t nblocks,
-                         int block_points, double ext_x, double ext_y, double ext_z, float *data, int64_t *point_idx,
-                         pcb_stream_t stream);
+                         int block_points, double ext_x, double ext_y, double ext_z, unsigned seed, float *data,
+                         int64_t *point_idx, pcb_stream_t stream);
 int pcb_scene_vote(const int64_t *point_idx, const unsigned char *pred, int64_t total, int64_t P, int num_classes,
                    int *pool, pcb_stream_t stream);
 int pcb_scene_vote_argmax(const int *pool, int64_t P, int num_classes, unsigned char *labels, pcb_stream_t stream);

@@ -7,10 +7,28 @@ only tests/, __graft_entry__.smoke() and bench.py's CPU legs may import this; th
 
 The reference draws the padding of a window with np.random.choice and shuffles the window (:240-242): those
 two steps are random, so the oracle exposes the deterministic part (window order, exact membership, block
-count, per-entry features) and builds blocks with cyclic padding like the CUDA path.  Pinned against outputs
-of the unmodified reference class in tests/golden/scene.npz (tests/golden/make_golden_scene.py).
+count, per-entry features) and builds the blocks with the product's counter-based rule (include/pcbridge.h:
+members ordered by (hash16(seed, point, window), point), padding = the first members of that order again,
+members and padding interleaved by the affine permutation s = (1000003 q + seed % 999983) mod tot).  Pinned
+against outputs of the unmodified reference class in tests/golden/scene.npz (tests/golden/make_golden_scene.py).
 """
 import numpy as np
+
+
+def scene_hash(seed, i, w):
+    """lowbias32 mix of (seed, point index, window id), uint32 arithmetic (csrc/scene.cu:scene_hash)."""
+    m = np.uint64(0xFFFFFFFF)
+    h = (np.uint64(seed) ^ ((np.asarray(i, np.uint64) * np.uint64(0x9E3779B1)) & m) ^ ((np.uint64(w) * np.uint64(0x85EBCA77)) & m)) & m
+    h ^= h >> np.uint64(16)
+    h = (h * np.uint64(0x7FEB352D)) & m
+    h ^= h >> np.uint64(15)
+    h = (h * np.uint64(0x846CA68B)) & m
+    h ^= h >> np.uint64(16)
+    return h
+
+
+def vote_seed(seed, vote):
+    return (int(seed) * 0x9E3779B1 + int(vote) * 0x632BE5AB + 0x7F4A7C15) & 0xFFFFFFFF
 
 
 def tile_windows(points, block_size=1.0, stride=0.5, padding=0.001):
@@ -51,14 +69,20 @@ def entry_features(points, idx, s_x, s_y, coord_min, coord_max, block_size=1.0):
     return np.concatenate((d, norm), axis=1).astype(np.float32)
 
 
-def tile_scene(points, block_points=4096, block_size=1.0, stride=0.5, padding=0.001):
-    """Blocks with cyclic padding and ascending member order: data [nb, block_points, 9] fp32,
+def tile_scene(points, block_points=4096, block_size=1.0, stride=0.5, padding=0.001, seed=0, vote=0):
+    """Blocks in the product's pseudo-random composition: data [nb, block_points, 9] fp32,
     point_idx [nb, block_points] int64, window id per block."""
     wins, grid, cmin, cmax = tile_windows(points, block_size, stride, padding)
+    sd = vote_seed(seed, vote)
     data, pidx, wid = [], [], []
     for w, s_x, s_y, idx in wins:
         nb = int(np.ceil(idx.size / block_points))
-        rep = idx[np.arange(nb * block_points) % idx.size]
+        n, tot = idx.size, nb * block_points
+        key = ((scene_hash(sd, idx, w) >> np.uint64(16)) << np.uint64(31)) | idx.astype(np.uint64)
+        order = idx[np.argsort(key, kind="stable")]              # members by (hash16, point index)
+        q = np.arange(tot, dtype=np.uint64)
+        s = ((q * np.uint64(1000003) + np.uint64(sd % 999983)) % np.uint64(tot)).astype(np.int64)
+        rep = order[np.where(s < n, s, (s - n) % n)]
         data.append(entry_features(points, rep, s_x, s_y, cmin, cmax, block_size).reshape(nb, block_points, 9))
         pidx.append(rep.reshape(nb, block_points))
         wid += [w] * nb

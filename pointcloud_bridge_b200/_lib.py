@@ -47,8 +47,8 @@ _SIGNATURES = {
     "pcb_bn_apply_rows": [_vp, _i, _i64, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _i64, _vp, _vp, _vp, _f, _vp, _vp, _vp],
     "pcb_bn_bwd_apply_rows": [_vp, _vp, _i, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp],
     "pcb_scene_window_count_f32": [_vp, _i64, _i, _i, _i, _vp, _vp, _vp, _vp, _d, _d, _d, _i, _vp, _vp],
-    "pcb_scene_window_fill_f32": [_vp, _i64, _i, _i, _i, _vp, _vp, _vp, _vp, _d, _d, _d, _i, _vp, _vp, _vp, _vp],
-    "pcb_scene_blocks_f32": [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i64, _i, _d, _d, _d, _vp, _vp, _vp],
+    "pcb_scene_window_fill_f32": [_vp, _i64, _i, _i, _i, _vp, _vp, _vp, _vp, _d, _d, _d, _i, _vp, _vp, ctypes.c_uint, _vp, _vp],
+    "pcb_scene_blocks_f32": [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i64, _i, _d, _d, _d, ctypes.c_uint, _vp, _vp, _vp],
     "pcb_scene_vote": [_vp, _vp, _i64, _i64, _i, _vp, _vp],
     "pcb_scene_vote_argmax": [_vp, _i64, _i, _vp, _vp],
     "pcb_nll_rows_fwd": [_vp, _i, _vp, _vp, _i64, _i, _i, _vp, _vp],

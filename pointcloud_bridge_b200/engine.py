@@ -510,23 +510,25 @@ def run_sharded_scene(net, blocks_x_host, rank, world, device, batch_blocks=128,
 
 @torch.no_grad()
 def segment_scene(net, points, num_classes, rank=0, world=1, block_points=4096, stride=0.5, block_size=1.0,
-                  padding=0.001, batch_blocks=128, amp=True, num_votes=1, infer=None):
+                  padding=0.001, batch_blocks=128, amp=True, num_votes=1, infer=None, seed=0):
     """Whole-scene evaluation on the GPU -- the loop of Partsize-identical/test_sem_seg.py:120-162 (tile the scene
     into overlapping blocks, predict every block `num_votes` times, scatter the predictions back as votes, take
     the per-point argmax).  points [P, >=6] fp32 CUDA tensor (x, y, z, r, g, b); returns uint8 labels [P].
     With several ranks every rank tiles the scene, evaluates its contiguous shard of the block list
     (distributed.shard_range) and the int32 vote counts are summed with ONE all-reduce -- the only exchange."""
     from . import scene
-    tiles = scene.SceneTiler(block_points, stride, block_size, padding).tile(points)
-    nb = tiles.data.shape[0]
-    rng = pdist.shard_range(nb, rank, world)
+    tiler = scene.SceneTiler(block_points, stride, block_size, padding, seed=seed)
     infer = infer or BlockInference(net, batch_blocks=batch_blocks, amp=amp)
     pool = scene.new_vote_pool(points.shape[0], num_classes, points.device)
-    if len(rng):
-        x = tiles.model_input()[rng.start:rng.stop]           # [n_local, 9, N] view of point-major rows
-        pidx = tiles.point_idx[rng.start:rng.stop]
-        for _ in range(num_votes):
-            scene.add_vote(pool, pidx, infer.run(x))
+    for vote in range(num_votes):
+        # every vote sees another pseudo-random subsample of each window (the reference re-draws padding and shuffle
+        # on every pass, BridgeDataLoader.py:239-242); the block list -- and with it the shards -- has the same length
+        tiles = tiler.tile(points, vote=vote)
+        rng = pdist.shard_range(tiles.data.shape[0], rank, world)
+        if len(rng):
+            x = tiles.model_input()[rng.start:rng.stop]       # [n_local, 9, N] view of point-major rows
+            scene.add_vote(pool, tiles.point_idx[rng.start:rng.stop], infer.run(x))
+        del tiles
     if world > 1 and pdist.is_dist():
         torch.distributed.all_reduce(pool)
     return scene.vote_argmax(pool)

@@ -971,17 +971,17 @@ _ticket_pool: dict[int, list] = {}
 
 
 def _tickets(dev: torch.device) -> torch.Tensor:
-    """Zeroed counter words for one statistics GEMM (the kernel leaves them zeroed).  4096 slots handed out round
+    """Zeroed counter words for one statistics GEMM (the kernel leaves them zeroed).  1024 slots handed out round
     robin: launches that could overlap never share a slot.  Created on first use -- before any graph capture, because
     the warm-up steps of a runner are eager."""
     key = dev.index if dev.index is not None else torch.cuda.current_device()
     st = _ticket_pool.get(key)
     if st is None:
         n = _lib.lib().pcb_gemm_tickets()
-        st = [torch.zeros(4096 * n, dtype=torch.int32, device=dev), 0, n]
+        st = [torch.zeros(1024 * n, dtype=torch.int32, device=dev), 0, n]
         _ticket_pool[key] = st
     buf, pos, n = st
-    st[1] = (pos + 1) % 4096
+    st[1] = (pos + 1) % 1024
     return buf[pos * n:(pos + 1) * n]
 
 

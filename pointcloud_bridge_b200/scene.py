@@ -13,8 +13,11 @@ Partsize-identical/test_sem_seg.py:58-65, 132-162:
 
 Window membership is bit-identical to the reference (bounds computed in float64 like numpy does, compared
 in double on the device).  The reference pads every window to a multiple of `block_points` with random
-re-draws of its own points and shuffles it (np.random); here the padding repeats the window's points
-cyclically and the order is the fill order -- the same multiset structure without a host RNG.
+re-draws of its own points and shuffles members + padding (np.random), so each block is a uniform random
+subsample of its window.  Here the same structure comes from a counter-based hash of (seed, vote, point,
+window): members are sorted by hash, the padding re-uses the first members of that order, and an affine
+permutation interleaves members and padding over the blocks -- deterministic for a given seed, different for
+every vote, independent of the order in which the atomics filled the windows.
 """
 from __future__ import annotations
 
@@ -60,12 +63,19 @@ class SceneTiles:
 
 
 class SceneTiler:
-    def __init__(self, block_points: int = 4096, stride: float = 0.5, block_size: float = 1.0, padding: float = 0.001):
+    def __init__(self, block_points: int = 4096, stride: float = 0.5, block_size: float = 1.0, padding: float = 0.001,
+                 seed: int = 0):
         self.block_points, self.stride, self.block_size, self.padding = int(block_points), float(stride), float(block_size), float(padding)
+        self.seed = int(seed)
+
+    def vote_seed(self, vote: int) -> int:
+        """32-bit seed of the block composition of one vote (a new pseudo-random subsample per vote, as the
+        reference's np.random draws give on every pass over the scene)."""
+        return (self.seed * 0x9E3779B1 + int(vote) * 0x632BE5AB + 0x7F4A7C15) & 0xFFFFFFFF
 
     @torch.no_grad()
-    def tile(self, points: torch.Tensor) -> SceneTiles:
-        """points [P, >=6] fp32 CUDA tensor (x, y, z, r, g, b, ...)."""
+    def tile(self, points: torch.Tensor, vote: int = 0) -> SceneTiles:
+        """points [P, >=6] fp32 CUDA tensor (x, y, z, r, g, b, ...); `vote`: which pass over the scene."""
         if not points.is_cuda or points.dtype != torch.float32 or points.dim() != 2 or points.shape[1] < 6:
             raise ValueError("SceneTiler.tile expects a [P, >=6] fp32 CUDA tensor")
         points = points.contiguous()
@@ -89,10 +99,14 @@ class SceneTiler:
         ops._call("pcb_scene_window_count_f32", dev, *common, counts.data_ptr(), alg_bytes=P * 8)
         offsets = torch.cumsum(counts.long(), 0) - counts.long()
         total = int(counts.sum().item())                      # host sync: sizes of the outputs depend on it
-        members = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
+        seed = self.vote_seed(vote)
+        keys = torch.empty(max(total, 1), dtype=torch.int64, device=dev)
         cursor = torch.zeros(nwin, dtype=torch.int32, device=dev)
-        ops._call("pcb_scene_window_fill_f32", dev, *common, offsets.data_ptr(), cursor.data_ptr(), members.data_ptr(),
-                  alg_bytes=P * 8 + total * 4)
+        ops._call("pcb_scene_window_fill_f32", dev, *common, offsets.data_ptr(), cursor.data_ptr(), seed, keys.data_ptr(),
+                  alg_bytes=P * 8 + total * 8)
+        # one radix sort over all windows: (window, hash, point) ascending = every window in its pseudo-random order
+        members = (torch.sort(keys)[0] & 0x7FFFFFFF).to(torch.int32)
+        del keys
         # per-block metadata (small, nwin-sized tensors): blocks of a window are consecutive, windows in (iy, ix) order
         nblk_w = (counts.long() + self.block_points - 1) // self.block_points
         nb = int(nblk_w.sum().item())
@@ -112,7 +126,7 @@ class SceneTiler:
         pidx = torch.empty(nb, self.block_points, dtype=torch.long, device=dev)
         ops._call("pcb_scene_blocks_f32", dev, points.data_ptr(), pstride, members.data_ptr(), blk_off.data_ptr(),
                   blk_cnt.data_ptr(), blk_first.data_ptr(), blk_center.data_ptr(), nb, self.block_points, float(ext[0]),
-                  float(ext[1]), float(ext[2]), data.data_ptr(), pidx.data_ptr(),
+                  float(ext[1]), float(ext[2]), seed, data.data_ptr(), pidx.data_ptr(),
                   alg_bytes=nb * self.block_points * (24 + 36 + 8 + 4))
         return SceneTiles(data, pidx, win, counts, (gx, gy))
 

@@ -30,10 +30,50 @@ def test_tiler_matches_oracle_and_reference_golden():
         e = pidx[sel].reshape(-1)
         assert np.array_equal(np.unique(e), members), f"window {w}: member set"
         _, cnt = np.unique(e, return_counts=True)
-        assert cnt.max() - cnt.min() <= 1, "cyclic padding"
+        assert cnt.max() - cnt.min() <= 1, "padding draws without replacement while it is shorter than the window"
         feats = so.entry_features(pts.astype(np.float64), e, s_x, s_y, cmin, cmax)
         assert np.array_equal(feats.view(np.uint32), data[sel].reshape(-1, 9).view(np.uint32)), f"window {w}: features"
     assert tiles.model_input().shape == (pidx.shape[0], 9, bp)
+    # the block composition itself (hashed member order, padding, affine interleave) is the oracle's, bit for bit
+    assert np.array_equal(pidx, o_idx)
+    assert np.array_equal(data.view(np.uint32), o_data.view(np.uint32))
+
+
+def test_tiler_is_deterministic_mixes_blocks_and_redraws_per_vote():
+    """Advisor finding of round 1: blocks were contiguous chunks of the atomics' fill order.  Now (a) two runs give
+    identical blocks, (b) every block of a multi-block window is spread over the whole window (the reference
+    shuffles: each block is a uniform subsample), (c) duplicates are spread over the blocks, (d) another vote gives
+    another composition of the same member sets."""
+    rng = np.random.default_rng(5)
+    n = 200_000
+    xyz = np.stack([rng.uniform(0, 3.0, n), rng.uniform(0, 2.0, n), rng.uniform(0, 1.0, n)], 1).astype(np.float32)
+    xyz = xyz[np.argsort(xyz[:, 0], kind="stable")]                  # scan order = x order: the worst case for chunking
+    pts = torch.from_numpy(np.concatenate([xyz, rng.uniform(0, 1, (n, 3)).astype(np.float32)], 1)).to(DEV)
+    tiler = scene.SceneTiler(block_points=4096, seed=3)
+    a, b = tiler.tile(pts), tiler.tile(pts)
+    assert torch.equal(a.point_idx, b.point_idx) and torch.equal(a.data, b.data)
+    o_data, o_idx, o_wid, _ = so.tile_scene(pts.cpu().numpy(), block_points=4096, seed=3)
+    assert np.array_equal(a.point_idx.cpu().numpy(), o_idx)
+    pidx = a.point_idx.cpu().numpy()
+    wid = a.window_of_block.cpu().numpy()
+    w = np.bincount(wid).argmax()                                     # the window with most blocks
+    blocks = pidx[wid == w]
+    assert blocks.shape[0] >= 8
+    x_all = xyz[np.unique(blocks), 0]
+    spread = [np.ptp(xyz[blk, 0]) / np.ptp(x_all) for blk in blocks]
+    assert min(spread) > 0.95, spread                                # no block is a spatial slice of the window
+    means = [xyz[blk, 0].mean() for blk in blocks]
+    assert np.ptp(means) < 0.05 * np.ptp(x_all)
+    members, counts = np.unique(blocks, return_counts=True)
+    dup = members[counts > 1]
+    if dup.size >= blocks.shape[0] * 8:                              # duplicates (padding) land in every block
+        per_block = [np.isin(blk, dup).sum() for blk in blocks]
+        assert min(per_block) > 0.3 * np.mean(per_block), per_block
+    c = tiler.tile(pts, vote=1)
+    assert not torch.equal(a.point_idx, c.point_idx)
+    pc = c.point_idx.cpu().numpy()
+    for ww in np.unique(wid)[::3]:
+        assert np.array_equal(np.unique(pidx[wid == ww]), np.unique(pc[wid == ww]))
 
 
 def test_vote_matches_reference_golden():
