@@ -327,8 +327,6 @@ PCB_API int pcb_fps_f32(const float *xyz, int B, int N, const int64_t *start, in
         }
     }
     if (N <= 8192) return launch_fps_pair<1024, 8>(xyz, B, N, start, npoint, out_idx, st);
-    if (false) {
-    }
     size_t smem = (size_t)N * sizeof(float);
     cudaError_t e = cudaFuncSetAttribute(fps_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)smem);

@@ -523,11 +523,9 @@ def segment_scene(net, points, num_classes, rank=0, world=1, block_points=4096, 
     for vote in range(num_votes):
         # every vote sees another pseudo-random subsample of each window (the reference re-draws padding and shuffle
         # on every pass, BridgeDataLoader.py:239-242); the block list -- and with it the shards -- has the same length
-        tiles = tiler.tile(points, vote=vote)
-        rng = pdist.shard_range(tiles.data.shape[0], rank, world)
-        if len(rng):
-            x = tiles.model_input()[rng.start:rng.stop]       # [n_local, 9, N] view of point-major rows
-            scene.add_vote(pool, tiles.point_idx[rng.start:rng.stop], infer.run(x))
+        tiles = tiler.tile(points, vote=vote, block_range=lambda nb: pdist.shard_range(nb, rank, world))
+        if tiles.data.shape[0]:                               # this rank's shard of the block list only
+            scene.add_vote(pool, tiles.point_idx, infer.run(tiles.model_input()))
         del tiles
     if world > 1 and pdist.is_dist():
         torch.distributed.all_reduce(pool)

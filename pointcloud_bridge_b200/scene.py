@@ -56,6 +56,8 @@ class SceneTiles:
     window_of_block: torch.Tensor  # [nb] int64 window id (iy * grid_x + ix) -- blocks follow the reference's window order
     window_counts: torch.Tensor   # [grid_y * grid_x] int32 points per window (before padding)
     grid: tuple                   # (grid_x, grid_y)
+    num_blocks: int = 0           # blocks of the whole scene
+    block_offset: int = 0         # first block held in `data` / `point_idx` (tile(..., block_range=...))
 
     def model_input(self) -> torch.Tensor:
         """[nb, 9, block_points] view, the layout the PointNet++ networks take."""
@@ -74,8 +76,10 @@ class SceneTiler:
         return (self.seed * 0x9E3779B1 + int(vote) * 0x632BE5AB + 0x7F4A7C15) & 0xFFFFFFFF
 
     @torch.no_grad()
-    def tile(self, points: torch.Tensor, vote: int = 0) -> SceneTiles:
-        """points [P, >=6] fp32 CUDA tensor (x, y, z, r, g, b, ...); `vote`: which pass over the scene."""
+    def tile(self, points: torch.Tensor, vote: int = 0, block_range=None) -> SceneTiles:
+        """points [P, >=6] fp32 CUDA tensor (x, y, z, r, g, b, ...); `vote`: which pass over the scene.
+        block_range: callable (num_blocks) -> range of the blocks to materialise (a rank's shard of the block list:
+        windows are counted and ordered for the whole scene, only the shard's [.., block_points, 9] rows are built)."""
         if not points.is_cuda or points.dtype != torch.float32 or points.dim() != 2 or points.shape[1] < 6:
             raise ValueError("SceneTiler.tile expects a [P, >=6] fp32 CUDA tensor")
         points = points.contiguous()
@@ -122,13 +126,16 @@ class SceneTiler:
         cy = d(sy + self.block_size / 2.0)[win // gx]
         blk_center = torch.stack([cx, cy], dim=1).contiguous()
         ext = cmax - cmin
-        data = torch.empty(nb, self.block_points, 9, dtype=torch.float32, device=dev)
-        pidx = torch.empty(nb, self.block_points, dtype=torch.long, device=dev)
-        ops._call("pcb_scene_blocks_f32", dev, points.data_ptr(), pstride, members.data_ptr(), blk_off.data_ptr(),
-                  blk_cnt.data_ptr(), blk_first.data_ptr(), blk_center.data_ptr(), nb, self.block_points, float(ext[0]),
-                  float(ext[1]), float(ext[2]), seed, data.data_ptr(), pidx.data_ptr(),
-                  alg_bytes=nb * self.block_points * (24 + 36 + 8 + 4))
-        return SceneTiles(data, pidx, win, counts, (gx, gy))
+        rng = range(nb) if block_range is None else block_range(nb)
+        lo, n_loc = rng.start, len(rng)
+        data = torch.empty(n_loc, self.block_points, 9, dtype=torch.float32, device=dev)
+        pidx = torch.empty(n_loc, self.block_points, dtype=torch.long, device=dev)
+        if n_loc:
+            ops._call("pcb_scene_blocks_f32", dev, points.data_ptr(), pstride, members.data_ptr(),
+                      blk_off[lo:].data_ptr(), blk_cnt[lo:].data_ptr(), blk_first[lo:].data_ptr(),
+                      blk_center[lo:].data_ptr(), n_loc, self.block_points, float(ext[0]), float(ext[1]), float(ext[2]), seed,
+                      data.data_ptr(), pidx.data_ptr(), alg_bytes=n_loc * self.block_points * (24 + 36 + 8 + 4))
+        return SceneTiles(data, pidx, win[lo:lo + n_loc], counts, (gx, gy), nb, lo)
 
 
 def new_vote_pool(num_points: int, num_classes: int, device) -> torch.Tensor:
