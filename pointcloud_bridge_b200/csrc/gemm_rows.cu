@@ -7,28 +7,32 @@
 //   353-356 and Highway_bridge/models/DGCNN.py:134-148 (EdgeConv)
 // in the forward pass (A = activations, B = weight [out, in]) and in the data-gradient pass (A = gradient rows,
 // B = weight transposed [in, out]).  Two epilogues fold the BatchNorm passes that used to follow into the GEMM:
-//   EPI_STATS  forward: per-channel (count, mean, M2) of the bf16 result -- exact two-pass blocks of 16 rows merged with
-//              Chan's update per thread, per CTA, per group of 16 CTAs and finally over the groups, always in a fixed
-//              order -- folded to mean / invstd / variance (training-mode BatchNorm statistics);
+//   EPI_STATS  forward: per-channel (count, mean, M2) of the bf16 result -- shifted sums per thread (shift = the first
+//              value the thread sees, so no cancellation), merged with Chan's update per CTA, per group of 16 CTAs and
+//              finally over the groups, always in a fixed order -- folded to mean / invstd / variance;
 //   EPI_BNBWD  backward: the accumulator is d loss / d z of the PREVIOUS layer's BN+ReLU output; the epilogue reads that
 //              layer's pre-activation tile y, applies the ReLU mask and emits dy together with the per-channel sums of
 //              dy and dy * yhat that the BatchNorm backward needs (yhat = (y - mean) * invstd).
 //
-// Design (second version; the first was a persistent warp-specialised kernel of 13 warps whose single-warp roles made
-// every phase instruction-latency bound: 2.5-3x slower than the library on these shapes, profiles/r2_gemm_rows.md).
-// The layers are memory-bound (K, N of a few dozen to a few hundred) and consist of thousands of tiny 128-row tiles, so
-// the kernel is built like a classic occupancy-driven CUDA kernel around ONE tcgen05.mma chain per tile:
+// Design (third version; profiles/r2_gemm_rows.md has the measurements that led here).  The layers are memory-bound
+// (K, N of a few dozen to a few hundred) and consist of thousands of 128-row tiles, so the kernel keeps every per-tile
+// cost that is not a byte of HBM traffic off the instruction stream:
+//   * operand tiles arrive by TMA tensor copies (cp.async.bulk.tensor.2d, ONE instruction per 128 x BK slab) straight
+//     into the swizzled K-major UMMA layout -- 128-byte swizzle for K > 32, 64-byte for K <= 32, 32-byte for K <= 16, so
+//     that narrow layers do not pay shared memory for zero fill; K / M / N tails are zero-filled by the TMA unit;
 //   * a CTA is 128 threads = the 128 rows of a tile = the 128 TMEM lanes; 2-6 CTAs are resident per SM (shared memory
-//     and <= 512 TMEM columns permitting) and hide each other's load / MMA / epilogue latencies;
-//   * every thread copies operand chunks with cp.async (16 B) straight into the canonical K-major no-swizzle UMMA
-//     layout (zero fill for the K / M / N tails), two stages: the slab of the NEXT step is in flight while thread 0
-//     issues the MMAs of the current one; the weight slab stays resident when K fits one slab;
-//   * epilogue, thread = row: tcgen05.ld -> bf16 -> 16-byte global stores straight from registers (+ the row of a
-//     shared-memory tile for the statistics); then one thread per column PAIR sums its rows with plain LDS.32;
+//     and <= 512 TMEM columns permitting) and hide each other's load / MMA / epilogue latencies; inside a CTA warp 0
+//     runs the copy ring (2-4 stages) and lane 0 issues the tcgen05.mma chain of a slab;
+//   * epilogue, thread = row: tcgen05.ld -> bf16 -> swizzled shared-memory tile (conflict-free 16-byte stores) -> ONE TMA
+//     tensor store per 64-column sub-tile (clips the M / N tails); the statistics pass re-reads the same tile with
+//     thread = (16-byte column unit, row group): LDS.128, 8 columns per thread;
+//   * EPI_BNBWD double-buffers the y tiles (TMA loads, same swizzled geometry as the output tile);
 //   * CTAs loop over row tiles with stride gridDim.x, keeping their statistics in registers; the per-CTA partials are
 //     folded in two deterministic levels by "last arriver" CTAs (group of 16, then all groups).
 // Algorithmic bytes: 2 * M * (K + N) [+ 2 * M * N for the y tile of EPI_BNBWD]; the tensor pipe idles by construction.
+#include <cuda.h>
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "pcb_common.cuh"
 #include "umma.cuh"
@@ -36,29 +40,24 @@
 namespace pcb {
 
 constexpr int kGemmThreads = 128;
-constexpr int kGemmLboPad = 16;            // bytes added to the K-chunk plane stride: spreads the 16-byte units of one
-                                           // row (consecutive K chunks) over different banks for the cp.async stores
-constexpr int kFoldGroup = 16;             // CTAs per first-level fold group
+constexpr int kFoldGroup = 32;             // CTAs per first-level fold group
+constexpr int kCombFloats = 3 * 1024;      // row-group combine: rgroups * BN <= 1024 columns x (n, mean, M2)
 enum { EPI_STORE = 0, EPI_STATS = 1, EPI_BNBWD = 2 };
 
 struct GemmParams {
-    const __nv_bfloat16 *A;      // [M, lda]
-    const __nv_bfloat16 *B;      // [Nb, ldb]: row n = output column n
-    __nv_bfloat16 *C;            // [M, ldc]
-    int64_t lda, ldb, ldc, M;
+    int64_t M;
     int N;                       // output columns written (multiple of 8)
-    int Nb;                      // rows of B that exist (others are zero)
     int K;                       // contraction length (multiple of 8)
-    int BN, BK, mtiles, ntiles, stages;
     int Cv;                      // real channels among the N columns (statistics epilogues)
+    int BN, BK, swzA;            // column tile; operand slab = BK columns = swzA bytes per row (swizzle span 32 / 64 / 128)
+    int wsub, nsub, wshift;      // output sub-tiles: nsub x [128 rows x wsub columns] (wsub = 16 / 32 / 64 = 1 << wshift)
+    int mtiles, ntiles, stages, sshift, nslabs;   // stages = 1 << sshift (2 or 4)
     float *parts;                // [ntiles][gridDim.x + groups][3][BN] partial column statistics (CTAs, then groups)
     unsigned *tickets;           // [ntiles][1 + groups], zero on entry, zero on exit
     // EPI_STATS
     float eps;
     float *mean, *invstd, *var;  // [N] results (var: biased batch variance)
     // EPI_BNBWD
-    const __nv_bfloat16 *Y;      // [M, ldy] pre-activation of the layer whose output gradient this GEMM produces
-    int64_t ldy;
     const float *bn_mean, *bn_invstd, *gamma, *beta;   // [Cv]
     int relu;
     float *sums;                 // [3][N]: sum dy, sum dy*yhat, 0 (gradient of the folded conv bias)
@@ -86,54 +85,206 @@ __device__ __forceinline__ void chan_merge(float &n, float &mean, float &m2, flo
     }
 }
 
+// ---- TMA tensor copies (2-D tiled tensor maps) and swizzled UMMA descriptors ----------------------------------------
+__device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap *tm, int c0, int c1, uint64_t *bar)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+            smem_dst),
+        "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *tm, int c0, int c1, uint32_t smem_src)
+{
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];" ::"l"(
+                     reinterpret_cast<uint64_t>(tm)),
+                 "r"(c0), "r"(c1), "r"(smem_src)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *tm)
+{
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
+}
+// K-major operand tile whose rows are one swizzle span wide (span = 32 / 64 / 128 bytes): 8-row core groups are
+// 8 * span bytes apart (SBO), the leading-dimension offset is unused, layout code 6 / 4 / 2 (sm_100 encoding).
+__device__ __forceinline__ uint64_t umma_desc_swz(uint32_t smem_addr, uint32_t span)
+{
+    const uint32_t layout = span == 128 ? 2u : (span == 64 ? 4u : 6u);
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(((8 * span) >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;                                // descriptor version 1 (sm_100)
+    d |= (uint64_t)layout << 61;
+    return d;
+}
+// byte offset inside a swizzled tile (base aligned to 1024): 16-byte unit index XOR (row-of-128-bytes index & mask)
+__device__ __forceinline__ uint32_t swz(uint32_t off, uint32_t mask) { return off ^ (((off >> 7) & mask) << 4); }
+
+__device__ __forceinline__ uint4 lds128(uint32_t addr)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4 &v)
+{
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+// mbarrier wait with a watchdog: a protocol error traps (launch failure) instead of hanging the device
+__device__ __forceinline__ void mbar_wait_wd(uint64_t *bar, uint32_t parity)
+{
+    const uint32_t a = smem_u32(bar);
+    for (uint32_t spin = 0;; ++spin) {
+        uint32_t ok;
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(ok)
+            : "r"(a), "r"(parity)
+            : "memory");
+        if (ok) return;
+        if (spin > (1u << 26)) __trap();
+    }
+}
+
 struct GemmSmem {
-    int lboA, lboB, a_bytes, stage_bytes, pitchC;
-    int off_tile0, off_tile1, off_const, off_comb, total;
+    int a_bytes, b_bytes, nb, off_b, off_out, sub_bytes, out_bytes, off_y, off_const, total;
 };
 
-__host__ __device__ __forceinline__ GemmSmem gemm_smem_layout(int BN, int BK, int epi, int stages)
+__host__ __device__ __forceinline__ GemmSmem gemm_smem_layout(int BN, int swzA, int nslabs, int stages, int epi, int wsub)
 {
     GemmSmem s;
-    s.lboA = 128 * 16 + kGemmLboPad;
-    s.lboB = BN * 16 + kGemmLboPad;
-    const int nch = BK / 8;
-    s.a_bytes = nch * s.lboA;
-    s.stage_bytes = (nch * (s.lboA + s.lboB) + 127) & ~127;
-    s.pitchC = (BN + 8) * 2;
-    const int tile = (128 * s.pitchC + 127) & ~127;
-    s.off_tile0 = stages * s.stage_bytes;                                   // operand stages
-    s.off_tile1 = s.off_tile0 + (epi == EPI_STORE ? 0 : tile);              // tile0: bf16 result (y tile for EPI_BNBWD)
-    s.off_const = s.off_tile1 + (epi == EPI_BNBWD ? tile : 0);              // tile1: dy (EPI_BNBWD)
-    s.off_comb = s.off_const + (epi == EPI_BNBWD ? 4 * BN * 4 : 0);
-    s.total = s.off_comb + (epi == EPI_STORE ? 0 : 8 * BN * 3 * 4);          // row-group combine: [<= 8][BN][3]
+    s.a_bytes = 128 * swzA;                                                  // 4 / 8 / 16 KB
+    s.b_bytes = (BN * swzA + 1023) & ~1023;
+    s.nb = nslabs == 1 ? 1 : stages;                                         // resident weights when K fits one slab
+    s.off_b = stages * s.a_bytes;
+    int opnd = s.off_b + s.nb * s.b_bytes;
+    if (epi != EPI_STORE && opnd < kCombFloats * 4) opnd = kCombFloats * 4;  // the combine scratch aliases the operand ring
+    s.sub_bytes = 128 * wsub * 2;
+    s.out_bytes = ((BN + wsub - 1) / wsub) * s.sub_bytes;
+    s.off_out = (opnd + 1023) & ~1023;
+    s.off_y = s.off_out + s.out_bytes;
+    s.off_const = s.off_y + (epi == EPI_BNBWD ? 2 * s.out_bytes : 0);        // y tiles: double buffered
+    s.total = s.off_const + (epi == EPI_BNBWD ? 4 * BN * 4 : 0) + 1024;      // + slack for the 1024-byte alignment
     return s;
+}
+
+// packed fp32 pairs (FADD2 / FFMA2): two columns per instruction in the statistics passes
+__device__ __forceinline__ uint64_t pk2(float lo, float hi)
+{
+    return (uint64_t)__float_as_uint(lo) | ((uint64_t)__float_as_uint(hi) << 32);
+}
+__device__ __forceinline__ float pk_lo(uint64_t v) { return __uint_as_float((uint32_t)v); }
+__device__ __forceinline__ float pk_hi(uint64_t v) { return __uint_as_float((uint32_t)(v >> 32)); }
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b)
+{
+    uint64_t r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t sub2(uint64_t a, uint64_t b)
+{
+    uint64_t r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c)
+{
+    uint64_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+// the two bf16 of a 32-bit word as a packed fp32 pair (low half = even column)
+__device__ __forceinline__ uint64_t bf2_to_f2(unsigned w) { return (uint64_t)(w << 16) | ((uint64_t)(w & 0xffff0000u) << 32); }
+
+// `cnt` partial triples (n, mean | sum, M2 | sum) of column c, `stride` floats apart, merged in index order; the loads
+// of eight partials are in flight together (the fold is a chain of L2 round trips otherwise)
+template <int EPI>
+__device__ __forceinline__ void fold_range(const float *base, int cnt, size_t stride, int BN, float &n, float &m, float &q)
+{
+    for (int j0 = 0; j0 < cnt; j0 += 8) {
+        float en[8], em[8], eq[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const bool ok = j0 + u < cnt;
+            const float *e = base + (size_t)(ok ? j0 + u : 0) * stride;
+            en[u] = (EPI == EPI_STATS && ok) ? __ldcg(e) : 0.f;
+            em[u] = ok ? __ldcg(e + BN) : 0.f;
+            eq[u] = ok ? __ldcg(e + 2 * BN) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            if (EPI == EPI_STATS) chan_merge(n, m, q, en[u], em[u], eq[u]);
+            else m += em[u], q += eq[u];
+        }
+    }
+}
+
+// all threads: fold `cnt` partials per column; 128 / BN threads share a column (contiguous slices of the partials,
+// merged in slice order through `scratch`); the totals of column tid land in (n, m, q) of the threads tid < BN
+template <int EPI>
+__device__ __forceinline__ void fold_cols(const float *base, int cnt, int BN, float *scratch, float &n, float &m, float &q)
+{
+    const int tid = threadIdx.x;
+    int slices = kGemmThreads / BN;
+    if (slices < 1) slices = 1;
+    const int per = (cnt + slices - 1) / slices;
+    const int s = tid / BN, c = tid - s * BN;
+    n = m = q = 0.f;
+    if (s < slices) {
+        const int lo = s * per, hi = lo + per < cnt ? lo + per : cnt;
+        if (hi > lo) fold_range<EPI>(base + (size_t)lo * 3 * BN + c, hi - lo, (size_t)3 * BN, BN, n, m, q);
+        float *e = scratch + ((size_t)s * BN + c) * 3;
+        e[0] = n, e[1] = m, e[2] = q;
+    }
+    __syncthreads();
+    if (tid < BN) {
+        n = m = q = 0.f;
+        for (int g = 0; g < slices; ++g) {
+            const float *e = scratch + ((size_t)g * BN + tid) * 3;
+            if (EPI == EPI_STATS) chan_merge(n, m, q, e[0], e[1], e[2]);
+            else m += e[1], q += e[2];
+        }
+    }
+    __syncthreads();
 }
 
 template <int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 4)
-gemm_rows_kernel(const GemmParams p)
+gemm_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmY, const GemmParams p)
 {
-    extern __shared__ __align__(128) unsigned char smem[];
-    __shared__ __align__(8) uint64_t s_mma[4];                               // MMAs of a stage complete
+    extern __shared__ unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t s_full[4];                              // operand slab of a stage has landed
+    __shared__ __align__(8) uint64_t s_mma[4];                               // MMAs reading a stage have completed
+    __shared__ __align__(8) uint64_t s_yfull[2];                             // y tile buffer has landed (EPI_BNBWD)
     __shared__ uint32_t s_tmem;
     __shared__ int s_flag;
 
-    const int tid = threadIdx.x, warp = tid >> 5;
-    const int BN = p.BN, BK = p.BK;
-    const int S = p.stages;                                                  // 2..4 operand stages
-    const GemmSmem L = gemm_smem_layout(BN, BK, EPI, S);
-    const int nt = blockIdx.y, n0 = nt * BN;
-    const int nslabs = (p.K + BK - 1) / BK;
-    unsigned char *tile0 = smem + L.off_tile0, *tile1 = smem + L.off_tile1;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int BN = p.BN, BK = p.BK, S = p.stages, sshift = p.sshift, nslabs = p.nslabs;
+    const GemmSmem L = gemm_smem_layout(BN, p.swzA, nslabs, S, EPI, p.wsub);
+    const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    unsigned char *smem = smem_raw + (sbase - smem_u32(smem_raw));
+    const uint32_t sA = sbase, sB = sbase + L.off_b, sOut = sbase + L.off_out, sY = sbase + L.off_y;
     float *s_const = reinterpret_cast<float *>(smem + L.off_const);         // EPI_BNBWD: [nm | is | sc | sh] x BN
-    float *s_comb = reinterpret_cast<float *>(smem + L.off_comb);
+    float *s_comb = reinterpret_cast<float *>(smem);                        // after the tile loop
+    const int nt = blockIdx.y, n0 = nt * BN;
+    const bool b_resident = nslabs == 1;
 
     int tmem_cols = 32;
     while (tmem_cols < BN) tmem_cols <<= 1;
 
     if (tid == 0) {
-        for (int i = 0; i < 4; ++i) mbar_init(&s_mma[i], 1);
+        for (int i = 0; i < 4; ++i) mbar_init(&s_full[i], 1), mbar_init(&s_mma[i], 1);
+        mbar_init(&s_yfull[0], 1), mbar_init(&s_yfull[1], 1);
         fence_mbar_init();
+        tma_prefetch_desc(&tmA), tma_prefetch_desc(&tmB), tma_prefetch_desc(&tmC);
+        if (EPI == EPI_BNBWD) tma_prefetch_desc(&tmY);
     }
     if (warp == 0) tmem_alloc(smem_u32(&s_tmem), (uint32_t)tmem_cols);
     if (EPI == EPI_BNBWD) {
@@ -154,250 +305,206 @@ gemm_rows_kernel(const GemmParams p)
     const uint32_t tmem_base = s_tmem;
     const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
     const uint32_t idesc = umma_idesc_bf16_m128(BN);
-    const uint32_t smem_base = smem_u32(smem);
 
-    // ---- operand copies: K chunk kc = tid & 7 of rows (tid >> 3) + 16 j; eight consecutive threads copy the 128
-    //      contiguous bytes of one row's slab, the copies of one slab are independent instructions
-    const int kc = tid & 7, r0 = tid >> 3;
-    const uint32_t sa_off = (uint32_t)(kc * L.lboA + r0 * 16), sb_off = (uint32_t)(L.a_bytes + kc * L.lboB + r0 * 16);
-    const int64_t a_step = 16 * p.lda * 2, b_step = 16 * p.ldb * 2;          // bytes between the rows of consecutive j
-    const char *b_row = reinterpret_cast<const char *>(p.B) + ((int64_t)(n0 + r0) * p.ldb + kc * 8) * 2;
-    const int b_valid = p.Nb - n0 - r0;                                      // rows n0 + r0 + 16 j exist while 16 j < b_valid
-    const int b_iters = BN >> 4;
-    const bool b_resident = nslabs == 1;                                     // the whole weight slab is loaded once
+    const int my_tiles = ((int)blockIdx.x < p.mtiles) ? (p.mtiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    const int nsteps = my_tiles * nslabs;
+    const uint32_t a_tx = (uint32_t)L.a_bytes, b_tx = (uint32_t)(BN * p.swzA);
 
-    auto load_slab = [&](int mt, int ks, int stage, bool with_b) {
-        const int64_t m0 = (int64_t)mt * 128;
-        const int k0 = ks * BK;
-        const int kw = p.K - k0 < BK ? p.K - k0 : BK;                        // real columns of this slab (multiple of 8)
-        const int nch = ((kw + 15) >> 4) << 1;                               // 16-byte K chunks incl. zero fill to K % 16 == 0
-        if (kc < nch) {
-            const bool kreal = kc < (kw >> 3);                               // else: zero fill of the K tail
-            const uint32_t sdst = smem_base + (uint32_t)stage * (uint32_t)L.stage_bytes;
-            const char *asrc = reinterpret_cast<const char *>(p.A) + ((m0 + r0) * p.lda + k0 + kc * 8) * 2;
-            const int64_t a_left = p.M - m0 - r0;
-            const int a_valid = a_left > 128 ? 128 : (int)a_left;            // row m0 + r0 + 16 j exists while 16 j < a_valid
+    // operand copies of a step (row tile mt, K slab ks) into `stage`: one thread
+    auto issue_loads = [&](int mt, int ks, int stage, bool with_b) {
+        mbar_expect_tx(&s_full[stage], a_tx + (with_b ? b_tx : 0u));
+        tma_load_2d(sA + (uint32_t)(stage * L.a_bytes), &tmA, ks * BK, mt * 128, &s_full[stage]);
+        if (with_b) tma_load_2d(sB + (uint32_t)((b_resident ? 0 : stage) * L.b_bytes), &tmB, ks * BK, n0, &s_full[stage]);
+    };
+    // y tile of row tile `mt` into buffer `buf` (EPI_BNBWD): nsub boxes of [128 x wsub]
+    auto issue_y = [&](int mt, int buf) {
+        int boxes = 0;
+        for (int j = 0; j < p.nsub; ++j) boxes += (n0 + j * p.wsub < p.N) ? 1 : 0;
+        mbar_expect_tx(&s_yfull[buf], (uint32_t)(boxes * L.sub_bytes));
+        for (int j = 0; j < p.nsub; ++j)
+            if (n0 + j * p.wsub < p.N)
+                tma_load_2d(sY + (uint32_t)(buf * L.out_bytes + j * L.sub_bytes), &tmY, n0 + j * p.wsub, mt * 128, &s_yfull[buf]);
+    };
+
+    // ---- epilogue bookkeeping: output tile geometry, statistics roles
+    const int wsub = p.wsub, wshift = p.wshift, pitchO = wsub * 2;
+    const uint32_t omask = (uint32_t)(pitchO >> 4) - 1u;                     // swizzle mask of the output / y tiles
+    const int U = BN >> 3;                                                   // 16-byte column units of the tile
+    const int rgroups = kGemmThreads / U;                                    // >= 4 (BN <= 256)
+    const bool st_active = EPI != EPI_STORE && tid < U * rgroups;
+    const int st_rg = tid / U, st_u = tid - st_rg * U;
+    const int st_j = (st_u << 3) >> wshift, st_uu = st_u - ((st_j << wshift) >> 3);
+    const uint32_t st_base = (uint32_t)(st_j * L.sub_bytes);
+    const uint32_t st_col = (uint32_t)(st_uu * 16);
+    // EPI_STATS: count, shift, sum (x - shift), sum (x - shift)^2;  EPI_BNBWD: a = sum dy, b = sum dy * yhat
+    float rn = 0.f;
+    uint64_t sh2[4], ra2[4], rb2[4], is2[4], nm2[4];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const bool ok = kreal && 16 * j < a_valid;
-                cp_async16_s(sdst + sa_off + j * 256, ok ? asrc + j * a_step : reinterpret_cast<const char *>(p.A), ok ? 16 : 0);
-            }
-            if (with_b) {
-                const char *bsrc = b_row + (int64_t)k0 * 2;
-#pragma unroll 4
-                for (int j = 0; j < b_iters; ++j) {
-                    const bool ok = kreal && 16 * j < b_valid;
-                    cp_async16_s(sdst + sb_off + j * 256, ok ? bsrc + j * b_step : reinterpret_cast<const char *>(p.B),
-                                 ok ? 16 : 0);
-                }
-            }
-        }
-    };
-
-    // ---- epilogue bookkeeping
-    const int cols_out = p.N - n0 < BN ? p.N - n0 : BN;                      // columns of this tile that exist (multiple of 8)
-    unsigned char *out_tile = EPI == EPI_BNBWD ? tile1 : tile0;
-    unsigned char *myrow = out_tile + (size_t)tid * L.pitchC;
-    // y tile prefetch (EPI_BNBWD): 16-byte chunk cc = tid % cp2 of rows tid / cp2 + rpp j
-    int cp2 = 1, cp2_log = 0;
-    while (cp2 < (BN >> 3)) cp2 <<= 1, ++cp2_log;
-    const int cp_cc = tid & (cp2 - 1), cp_r0 = tid >> cp2_log, rpp = 128 >> cp2_log;
-    auto prefetch_y = [&](int mt) {
-        const int64_t m0 = (int64_t)mt * 128;
-        const int rows = p.M - m0 < 128 ? (int)(p.M - m0) : 128;
-        if (cp_cc < (BN >> 3)) {                                             // all BN columns: the tail is zero-filled
-            const char *src = reinterpret_cast<const char *>(p.Y) + ((m0 + cp_r0) * p.ldy + n0 + cp_cc * 8) * 2;
-            const int64_t step = (int64_t)rpp * p.ldy * 2;
-            const uint32_t dst = smem_u32(tile0) + (uint32_t)(cp_r0 * L.pitchC + cp_cc * 16);
-#pragma unroll 4
-            for (int j = 0; j < cp2; ++j) {
-                const bool ok = cp_cc * 8 < cols_out && cp_r0 + j * rpp < rows;
-                cp_async16_s(dst + (uint32_t)(j * rpp * L.pitchC), ok ? src + j * step : reinterpret_cast<const char *>(p.Y),
-                             ok ? 16 : 0);
-            }
-        }
-    };
-    // column statistics: thread = (row group rg, column pair cp)
-    const int ncp = BN >> 1;
-    int rgroups = 1;
-    while (rgroups * 2 * ncp <= 128 && rgroups < 8) rgroups <<= 1;
-    const int rpg = 128 / rgroups;                                           // 16 .. 128 rows per thread, blocks of 16
-    const bool st_active = EPI != EPI_STORE && tid < ncp * rgroups;
-    const int st_rg = tid / ncp, st_cp = tid - st_rg * ncp;
-    float rn = 0.f, rm0 = 0.f, rq0 = 0.f, rm1 = 0.f, rq1 = 0.f;              // EPI_STATS: count, mean / M2 of the two columns
-    float c_nm0 = 0.f, c_is0 = 0.f, c_nm1 = 0.f, c_is1 = 0.f;                // EPI_BNBWD: rq = sum dy, rm = sum dy*yhat
+    for (int i = 0; i < 4; ++i) sh2[i] = ra2[i] = rb2[i] = is2[i] = nm2[i] = 0ull;
     if (EPI == EPI_BNBWD && st_active) {
-        c_nm0 = s_const[2 * st_cp], c_is0 = s_const[BN + 2 * st_cp];
-        c_nm1 = s_const[2 * st_cp + 1], c_is1 = s_const[BN + 2 * st_cp + 1];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            nm2[i] = pk2(s_const[8 * st_u + 2 * i], s_const[8 * st_u + 2 * i + 1]);
+            is2[i] = pk2(s_const[BN + 8 * st_u + 2 * i], s_const[BN + 8 * st_u + 2 * i + 1]);
+        }
     }
 
     // ---- pipeline over the steps (tile, K slab) of this CTA: the copies of the next S - 1 steps are in flight while the
-    //      MMAs of a step run; stage = step % S; s_mma[stage] completes when the MMAs that read the stage have finished.
-    //      One cp.async group per step (possibly empty), committed in step order.
-    const int my_tiles = ((int)blockIdx.x < p.mtiles) ? (p.mtiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-    const int nsteps = my_tiles * nslabs;
-    auto issue_step = [&](int st) {                                          // copies of step `st` into its stage
-        if (st < nsteps) {
-            const int t = st / nslabs, ks = st - t * nslabs;
-            load_slab(blockIdx.x + t * gridDim.x, ks, st % S, st == 0 || !b_resident);
-            if (EPI == EPI_BNBWD && st == 0) prefetch_y(blockIdx.x);
-        }
-        cp_async_commit();
+    //      MMAs of a step run; stage = step & (S - 1)
+    int ld_t = 0, ld_ks = 0, ld_step = 0;                                    // next step to load (warp 0)
+    auto load_next = [&]() {                                                 // warp 0, all lanes keep the counters
+        if (lane == 0) issue_loads(blockIdx.x + ld_t * gridDim.x, ld_ks, ld_step & (S - 1), !b_resident || ld_step == 0);
+        ++ld_step;
+        if (++ld_ks == nslabs) ld_ks = 0, ++ld_t;
     };
-    for (int st = 0; st < S - 1; ++st) issue_step(st);
+    if (warp == 0) {
+        for (int st = 0; st < S - 1 && st < nsteps; ++st) load_next();
+        if (EPI == EPI_BNBWD && lane == 0 && my_tiles > 0) issue_y(blockIdx.x, 0);
+    }
     int step = 0;
     for (int ti = 0; ti < my_tiles; ++ti) {
         const int mt = blockIdx.x + ti * gridDim.x;
         const int64_t m0 = (int64_t)mt * 128;
         const int rows = p.M - m0 < 128 ? (int)(p.M - m0) : 128;
-        for (int ks = 0; ks < nslabs; ++ks, ++step) {
-            const int stage = step % S;
-            // copies of step + S - 1 into the stage that step - 1 used, once its MMAs are done
-            {
-                const int nxt = step + S - 1;
-                if (nxt < nsteps && step >= 1) mbar_wait(&s_mma[nxt % S], ((uint32_t)((step - 1) / S)) & 1u);
-                issue_step(nxt);
-            }
-            switch (S) {                                                     // this step's copies (and y tile) have landed
-            case 2: cp_async_wait<1>(); break;
-            case 3: cp_async_wait<2>(); break;
-            default: cp_async_wait<3>(); break;
-            }
-            proxy_fence();                                                   // generic-proxy writes -> tensor-core reads
-            tc_fence_before();
-            __syncthreads();
-            if (tid == 0) {
-                tc_fence_after();
-                const int kw = p.K - ks * BK < BK ? p.K - ks * BK : BK;
-                const int ksteps = (kw + 15) >> 4;
-                const uint32_t a_base = smem_base + (uint32_t)stage * (uint32_t)L.stage_bytes;
-                // resident weights live in stage 0 (loaded with the first step)
-                const uint32_t b_base = smem_base + (uint32_t)(b_resident ? 0 : stage) * (uint32_t)L.stage_bytes + L.a_bytes;
-                for (int kk = 0; kk < ksteps; ++kk) {
-                    const uint64_t da = umma_desc(a_base + (uint32_t)(kk * 2 * L.lboA), (uint32_t)L.lboA, 128);
-                    const uint64_t db = umma_desc(b_base + (uint32_t)(kk * 2 * L.lboB), (uint32_t)L.lboB, 128);
-                    umma_bf16(tmem_base, da, db, idesc, (ks | kk) ? 1u : 0u);
+        if (warp == 0) {
+            for (int ks = 0; ks < nslabs; ++ks, ++step) {
+                const int stage = step & (S - 1);
+                if (ld_step < nsteps) {                                      // refill the stage that step - 1 used
+                    if (step >= 1) mbar_wait_wd(&s_mma[(step - 1) & (S - 1)], ((uint32_t)((step - 1) >> sshift)) & 1u);
+                    load_next();
                 }
-                umma_commit(&s_mma[stage]);
+                mbar_wait_wd(&s_full[stage], ((uint32_t)(step >> sshift)) & 1u);
+                tc_fence_after();
+                if (lane == 0) {
+                    const int kw = p.K - ks * BK < BK ? p.K - ks * BK : BK;
+                    const int ksteps = (kw + 15) >> 4;
+                    const uint64_t da = umma_desc_swz(sA + (uint32_t)(stage * L.a_bytes), (uint32_t)p.swzA);
+                    const uint64_t db = umma_desc_swz(sB + (uint32_t)((b_resident ? 0 : stage) * L.b_bytes), (uint32_t)p.swzA);
+                    for (int kk = 0; kk < ksteps; ++kk)                      // + 32 bytes along K = + 2 in the address field
+                        umma_bf16(tmem_base, da + (uint64_t)(2 * kk), db + (uint64_t)(2 * kk), idesc, (ks | kk) ? 1u : 0u);
+                    umma_commit(&s_mma[stage]);
+                }
+                __syncwarp();
             }
+        } else {
+            step += nslabs;
         }
-        // ---- epilogue of the tile: wait for the MMAs of its last slab
-        {
-            const int last = step - 1;
-            mbar_wait(&s_mma[last % S], ((uint32_t)(last / S)) & 1u);
-            tc_fence_after();
+        // ---- epilogue of the tile: its last slab's MMAs have completed; the previous tile's store has read the out tile
+        mbar_wait_wd(&s_mma[(step - 1) & (S - 1)], ((uint32_t)((step - 1) >> sshift)) & 1u);
+        tc_fence_after();
+        if (tid == 0) bulk_wait_read0();
+        __syncthreads();                                                     // (A) out tile + the other y buffer are free
+        const uint32_t ybuf = sY + (uint32_t)((ti & 1) * L.out_bytes);
+        if (EPI == EPI_BNBWD) {
+            if (tid == 0 && ti + 1 < my_tiles) issue_y(mt + gridDim.x, (ti + 1) & 1);
+            mbar_wait_wd(&s_yfull[ti & 1], ((uint32_t)(ti >> 1)) & 1u);
         }
-        __nv_bfloat16 *grow = p.C + (m0 + tid) * p.ldc + n0;
-        const bool row_ok = tid < rows;
         for (int c0 = 0; c0 < BN; c0 += 16) {
             float v[16];
             tmem_ld16(trow + (uint32_t)c0, v);
+            const int j = c0 >> wshift, cs = c0 - (j << wshift);
+            const uint32_t off0 = (uint32_t)(j * L.sub_bytes) + swz((uint32_t)(tid * pitchO + cs * 2), omask);
+            const uint32_t off1 = (uint32_t)(j * L.sub_bytes) + swz((uint32_t)(tid * pitchO + cs * 2 + 16), omask);
             if (EPI == EPI_BNBWD && p.relu) {
-                const uint4 *ysrc = reinterpret_cast<const uint4 *>(tile0 + (size_t)tid * L.pitchC + c0 * 2);
+                float y[8];
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
-                    float y[8];
-                    unpack8(ysrc[h], y);
+                    unpack8(lds128(ybuf + (h ? off1 : off0)), y);
+                    const float4 *sc4 = reinterpret_cast<const float4 *>(s_const + 2 * BN + c0 + 8 * h);
+                    const float4 *sh4 = reinterpret_cast<const float4 *>(s_const + 3 * BN + c0 + 8 * h);
+                    const float4 s0 = sc4[0], s1 = sc4[1], t0 = sh4[0], t1 = sh4[1];
+                    const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+                    const float sf[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const int c = c0 + 8 * h + j;
-                        const float z = fmaf(y[j], s_const[2 * BN + c], s_const[3 * BN + c]);
-                        v[8 * h + j] = z > 0.f ? v[8 * h + j] : 0.f;
+                    for (int q = 0; q < 8; ++q) {
+                        const float z = fmaf(y[q], sc[q], sf[q]);
+                        v[8 * h + q] = z > 0.f ? v[8 * h + q] : 0.f;
                     }
                 }
             }
-            const uint4 u0 = pack8(v), u1 = pack8(v + 8);
-            if (row_ok && c0 < cols_out) *reinterpret_cast<uint4 *>(grow + c0) = u0;
-            if (row_ok && c0 + 8 < cols_out) *reinterpret_cast<uint4 *>(grow + c0 + 8) = u1;
-            if (EPI != EPI_STORE) {
-                uint4 *dst = reinterpret_cast<uint4 *>(myrow + c0 * 2);
-                dst[0] = u0;
-                dst[1] = u1;
-            }
+            sts128(sOut + off0, pack8(v));
+            sts128(sOut + off1, pack8(v + 8));
         }
         tc_fence_before();                                                   // TMEM reads done before the next tile's MMAs
-        if (EPI != EPI_STORE) {
-            __syncthreads();                                                 // tile complete
-            if (st_active) {
-                const unsigned char *col = out_tile + st_cp * 4;
-                const int r_beg = st_rg * rpg;
-                const int r_end = r_beg + rpg < rows ? r_beg + rpg : rows;
-                if (EPI == EPI_STATS) {
-                    for (int rb = r_beg; rb < r_end; rb += 16) {
-                        const int cnt = r_end - rb < 16 ? r_end - rb : 16;
-                        unsigned w[16];
+        proxy_fence();                                                       // generic-proxy writes -> TMA store reads
+        __syncthreads();                                                     // (B) tile complete
+        if (tid == 0) {
+            for (int j = 0; j < p.nsub; ++j)
+                if (n0 + j * wsub < p.N) tma_store_2d(&tmC, n0 + j * wsub, mt * 128, sOut + (uint32_t)(j * L.sub_bytes));
+            bulk_commit();
+        }
+        if (EPI != EPI_STORE && st_active) {
+            if (EPI == EPI_STATS) {
+                if (ti == 0 && st_rg < rows) {
+                    const uint4 w = lds128(sOut + st_base + swz((uint32_t)(st_rg * pitchO) + st_col, omask));
+                    sh2[0] = bf2_to_f2(w.x), sh2[1] = bf2_to_f2(w.y), sh2[2] = bf2_to_f2(w.z), sh2[3] = bf2_to_f2(w.w);
+                }
+                for (int r = st_rg; r < rows; r += 4 * rgroups) {
+                    uint4 w[4];
 #pragma unroll
-                        for (int j = 0; j < 16; ++j)                         // 16 independent loads, then arithmetic
-                            w[j] = j < cnt ? *reinterpret_cast<const unsigned *>(col + (size_t)(rb + j) * L.pitchC) : 0u;
-                        float sa0 = 0.f, sb0 = 0.f, sa1 = 0.f, sb1 = 0.f;
-#pragma unroll
-                        for (int j = 0; j < 16; j += 2) {                    // rows beyond cnt hold 0
-                            sa0 += __uint_as_float(w[j] << 16);
-                            sa1 += __uint_as_float(w[j] & 0xffff0000u);
-                            sb0 += __uint_as_float(w[j + 1] << 16);
-                            sb1 += __uint_as_float(w[j + 1] & 0xffff0000u);
-                        }
-                        const float cn = (float)cnt, inv = 1.f / cn;
-                        const float m0c = (sa0 + sb0) * inv, m1c = (sa1 + sb1) * inv;
-                        float qa0 = 0.f, qb0 = 0.f, qa1 = 0.f, qb1 = 0.f;
-#pragma unroll
-                        for (int j = 0; j < 16; j += 2) {
-                            const float d0 = __uint_as_float(w[j] << 16) - m0c, d1 = __uint_as_float(w[j] & 0xffff0000u) - m1c;
-                            const float e0 = __uint_as_float(w[j + 1] << 16) - m0c;
-                            const float e1 = __uint_as_float(w[j + 1] & 0xffff0000u) - m1c;
-                            qa0 = fmaf(d0, d0, qa0);
-                            qa1 = fmaf(d1, d1, qa1);
-                            qb0 = fmaf(e0, e0, qb0);
-                            qb1 = fmaf(e1, e1, qb1);
-                        }
-                        float q0 = qa0 + qb0, q1 = qa1 + qb1;
-                        if (cnt < 16) {                                      // the 16 - cnt padding zeros each added mean^2
-                            const float pad = (float)(16 - cnt);
-                            q0 -= pad * m0c * m0c;
-                            q1 -= pad * m1c * m1c;
-                        }
-                        float n1 = rn;
-                        chan_merge(rn, rm0, rq0, cn, m0c, q0);
-                        chan_merge(n1, rm1, rq1, cn, m1c, q1);
+                    for (int q = 0; q < 4; ++q) {
+                        const int rr = r + q * rgroups;
+                        if (rr < rows) w[q] = lds128(sOut + st_base + swz((uint32_t)(rr * pitchO) + st_col, omask));
                     }
-                } else if (EPI == EPI_BNBWD) {
-                    const unsigned char *ycol = tile0 + st_cp * 4;
-                    for (int rb = r_beg; rb < r_end; rb += 8) {
-                        const int cnt = r_end - rb < 8 ? r_end - rb : 8;
-                        unsigned w[8], yw[8];
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            w[j] = j < cnt ? *reinterpret_cast<const unsigned *>(col + (size_t)(rb + j) * L.pitchC) : 0u;
-                            yw[j] = j < cnt ? *reinterpret_cast<const unsigned *>(ycol + (size_t)(rb + j) * L.pitchC) : 0u;
+                    for (int q = 0; q < 4; ++q) {
+                        if (r + q * rgroups < rows) {
+                            const unsigned ww[4] = {w[q].x, w[q].y, w[q].z, w[q].w};
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const uint64_t d = sub2(bf2_to_f2(ww[i]), sh2[i]);
+                                ra2[i] = add2(ra2[i], d);
+                                rb2[i] = fma2(d, d, rb2[i]);
+                            }
+                            rn += 1.f;
                         }
+                    }
+                }
+            } else {
+                for (int r = st_rg; r < rows; r += 2 * rgroups) {
+                    uint4 w[2], yw[2];
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const float d0 = __uint_as_float(w[j] << 16), d1 = __uint_as_float(w[j] & 0xffff0000u);
-                            const float h0 = fmaf(__uint_as_float(yw[j] << 16), c_is0, c_nm0);
-                            const float h1 = fmaf(__uint_as_float(yw[j] & 0xffff0000u), c_is1, c_nm1);
-                            rq0 += d0;                                       // rows beyond cnt: dy = 0
-                            rq1 += d1;
-                            rm0 = fmaf(d0, h0, rm0);
-                            rm1 = fmaf(d1, h1, rm1);
+                    for (int q = 0; q < 2; ++q) {
+                        const int rr = r + q * rgroups;
+                        const uint32_t o = st_base + swz((uint32_t)(rr * pitchO) + st_col, omask);
+                        w[q] = rr < rows ? lds128(sOut + o) : make_uint4(0, 0, 0, 0);
+                        yw[q] = rr < rows ? lds128(ybuf + o) : make_uint4(0, 0, 0, 0);
+                    }
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {                            // rows beyond `rows`: dy = 0
+                        const unsigned dw[4] = {w[q].x, w[q].y, w[q].z, w[q].w}, yy[4] = {yw[q].x, yw[q].y, yw[q].z, yw[q].w};
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const uint64_t d = bf2_to_f2(dw[i]);
+                            ra2[i] = add2(ra2[i], d);
+                            rb2[i] = fma2(d, fma2(bf2_to_f2(yy[i]), is2[i], nm2[i]), rb2[i]);
                         }
                     }
                 }
             }
-            __syncthreads();                                                 // tiles free again
-            if (EPI == EPI_BNBWD && ti + 1 < my_tiles) {                     // y tile of the next row tile
-                prefetch_y(mt + gridDim.x);
-                cp_async_commit();
-                cp_async_wait<0>();                                          // (also drains the operand copies in flight;
-            }                                                                //  the wait<S-1> of later steps stays valid)
         }
     }
+    if (tid == 0) bulk_wait_all0();                                          // the last store has left shared memory
 
     if (EPI != EPI_STORE) {
-        // ---- per-CTA partial statistics: the row groups merged in a fixed order through shared memory
+        // ---- per-CTA partial statistics: the row groups merged in a fixed order through shared memory (aliases the
+        //      operand ring: every copy has been consumed and every MMA has completed)
+        __syncthreads();
         if (st_active) {
-            float *c0p = s_comb + ((size_t)st_rg * BN + 2 * st_cp) * 3;
-            c0p[0] = rn, c0p[1] = rm0, c0p[2] = rq0;
-            c0p[3] = rn, c0p[4] = rm1, c0p[5] = rq1;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                float *e = s_comb + ((size_t)st_rg * BN + 8 * st_u + i) * 3;
+                const float a = (i & 1) ? pk_hi(ra2[i >> 1]) : pk_lo(ra2[i >> 1]);
+                const float b = (i & 1) ? pk_hi(rb2[i >> 1]) : pk_lo(rb2[i >> 1]);
+                if (EPI == EPI_STATS) {
+                    const float s0 = (i & 1) ? pk_hi(sh2[i >> 1]) : pk_lo(sh2[i >> 1]);
+                    const float inv = rn > 0.f ? 1.f / rn : 0.f;
+                    const float md = a * inv;
+                    e[0] = rn, e[1] = s0 + md, e[2] = fmaxf(b - a * md, 0.f);
+                } else {
+                    e[0] = 0.f, e[1] = b, e[2] = a;
+                }
+            }
         }
         __syncthreads();
         const int P = gridDim.x, G = (P + kFoldGroup - 1) / kFoldGroup;
@@ -413,8 +520,8 @@ gemm_rows_kernel(const GemmParams p)
             float *my = lvl0 + (size_t)blockIdx.x * 3 * BN;
             my[c] = n, my[BN + c] = m, my[2 * BN + c] = q;
         }
-        // ---- two-level deterministic fold: the last CTA of each group of 16 merges the group (fixed order), the last
-        //      group to finish merges the groups and writes the results
+        // ---- two-level deterministic fold: the last CTA of each group of kFoldGroup merges the group (fixed order),
+        //      the last group to finish merges the groups and writes the results
         __threadfence();
         __syncthreads();
         const int grp = blockIdx.x / kFoldGroup;
@@ -423,76 +530,49 @@ gemm_rows_kernel(const GemmParams p)
         __syncthreads();
         if (s_flag) {
             __threadfence();
-            for (int c = tid; c < BN; c += kGemmThreads) {
-                float n = 0.f, m = 0.f, q = 0.f;
-                for (int j = g_lo; j < g_hi; ++j) {
-                    const float *e = lvl0 + (size_t)j * 3 * BN + c;
-                    const float en = __ldcg(e), em = __ldcg(e + BN), eq = __ldcg(e + 2 * BN);
-                    if (EPI == EPI_STATS) chan_merge(n, m, q, en, em, eq);
-                    else m += em, q += eq;
-                }
-                    if (G == 1) {                                                // a single group: these are the totals
-                    const int gc = n0 + c;
-                    if (gc < p.N) {
-                        if (EPI == EPI_STATS) {
-                            const bool real = gc < p.Cv;
-                            const float var = real ? fmaxf(q / (float)p.M, 0.f) : 0.f;
-                            p.mean[gc] = real ? m : 0.f;
-                            p.invstd[gc] = real ? rsqrtf(var + p.eps) : 0.f;
-                            p.var[gc] = var;
-                        } else {
-                            p.sums[gc] = gc < p.Cv ? q : 0.f;
-                            p.sums[p.N + gc] = gc < p.Cv ? m : 0.f;
-                            p.sums[2 * p.N + gc] = 0.f;
-                        }
-                    }
-                } else {
+            float n, m, q;
+            fold_cols<EPI>(lvl0 + (size_t)g_lo * 3 * BN, g_hi - g_lo, BN, s_comb, n, m, q);
+            bool final_level = G == 1;
+            if (!final_level) {
+                if (tid < BN) {
                     float *o = lvl1 + (size_t)grp * 3 * BN;
-                    o[c] = n, o[BN + c] = m, o[2 * BN + c] = q;
+                    o[tid] = n, o[BN + tid] = m, o[2 * BN + tid] = q;
                 }
-            }
-            if (G == 1) {
-                if (tid == 0) tick[1 + grp] = 0u;
-                goto fold_done;
-            }
-            __threadfence();
-            __syncthreads();
-            if (tid == 0) {
-                tick[1 + grp] = 0u;                                          // ready for the next launch
-                s_flag = atomicAdd(tick, 1u) == (unsigned)(G - 1);
-            }
-            __syncthreads();
-            if (s_flag) {
                 __threadfence();
-                for (int c = tid; c < BN; c += kGemmThreads) {
-                    const int gc = n0 + c;
-                    float n = 0.f, m = 0.f, q = 0.f;
-                    for (int j = 0; j < G; ++j) {
-                        const float *e = lvl1 + (size_t)j * 3 * BN + c;
-                        const float en = __ldcg(e), em = __ldcg(e + BN), eq = __ldcg(e + 2 * BN);
-                        if (EPI == EPI_STATS) chan_merge(n, m, q, en, em, eq);
-                        else m += em, q += eq;
-                    }
-                    if (gc < p.N) {
-                        if (EPI == EPI_STATS) {
-                            const bool real = gc < p.Cv;
-                            const float var = real ? fmaxf(q / (float)p.M, 0.f) : 0.f;
-                            p.mean[gc] = real ? m : 0.f;                     // mean of the bias-free pre-activation
-                            p.invstd[gc] = real ? rsqrtf(var + p.eps) : 0.f;
-                            p.var[gc] = var;                                 // running statistics: pcb_bn_apply_rows
-                        } else {
-                            p.sums[gc] = gc < p.Cv ? q : 0.f;                // sum dy
-                            p.sums[p.N + gc] = gc < p.Cv ? m : 0.f;          // sum dy * yhat
-                            p.sums[2 * p.N + gc] = 0.f;
-                        }
+                __syncthreads();
+                if (tid == 0) {
+                    tick[1 + grp] = 0u;                                      // ready for the next launch
+                    s_flag = atomicAdd(tick, 1u) == (unsigned)(G - 1);
+                }
+                __syncthreads();
+                if (s_flag) {
+                    __threadfence();
+                    fold_cols<EPI>(lvl1, G, BN, s_comb, n, m, q);
+                    final_level = true;
+                    if (tid == 0) tick[0] = 0u;
+                }
+            } else if (tid == 0) {
+                tick[1 + grp] = 0u;
+            }
+            if (final_level && tid < BN) {
+                const int gc = n0 + tid;
+                if (gc < p.N) {
+                    if (EPI == EPI_STATS) {
+                        const bool real = gc < p.Cv;
+                        const float var = real ? fmaxf(q / (float)p.M, 0.f) : 0.f;
+                        p.mean[gc] = real ? m : 0.f;                         // mean of the bias-free pre-activation
+                        p.invstd[gc] = real ? rsqrtf(var + p.eps) : 0.f;
+                        p.var[gc] = var;                                     // running statistics: pcb_bn_apply_rows
+                    } else {
+                        p.sums[gc] = gc < p.Cv ? q : 0.f;                    // sum dy
+                        p.sums[p.N + gc] = gc < p.Cv ? m : 0.f;              // sum dy * yhat
+                        p.sums[2 * p.N + gc] = 0.f;
                     }
                 }
-                if (tid == 0) tick[0] = 0u;
             }
         }
     }
 
-fold_done:
     // ---- teardown: every MMA has completed (each tile's epilogue waited for its last commit)
     tc_fence_before();
     __syncthreads();
@@ -500,44 +580,68 @@ fold_done:
 }
 
 struct GemmPlan {
-    int BN, BK, ntiles, mtiles, grid_x, ctas_per_sm, groups, stages;
+    int BN, BK, swzA, wsub, nsub, nslabs, ntiles, mtiles, grid_x, ctas_per_sm, groups, stages;
     size_t smem;
 };
+
+// CTAs per SM the registers of each epilogue variant allow (cudaFuncGetAttributes once per device; the occupancy API
+// answered 1 in most launches -- measured with ncu, round 2 -- which serialised the whole design on one CTA per SM)
+static int g_reg_limit[3][kMaxDevices];
+
+static int gemm_force_span()                                                 // PCB_GEMM_SPAN=128: one swizzle mode for every K
+{
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("PCB_GEMM_SPAN");
+        v = e ? atoi(e) : 0;
+    }
+    return v;
+}
 
 static bool gemm_plan(int64_t M, int N, int K, int epi, GemmPlan &g)
 {
     g.mtiles = (int)ceil_div(M, 128);
-    g.BK = K > 32 ? 64 : (K > 16 ? 32 : 16);
+    g.swzA = K > 32 ? 128 : (K > 16 ? 64 : 32);
+    if (gemm_force_span() == 128 || gemm_force_span() == 64) g.swzA = g.swzA > gemm_force_span() ? g.swzA : gemm_force_span();
+    g.BK = g.swzA / 2;
+    g.nslabs = (K + g.BK - 1) / g.BK;
     // column tiles of <= 128 columns (several CTAs per SM must fit: shared memory, TMEM), more of them when the row
-    // tiles alone would leave SMs idle
+    // tiles alone would leave SMs idle; several column tiles are multiples of 64 columns (whole output sub-tiles)
     int ntiles = (N + 127) / 128;
     const int want = 2 * PCB_NUM_SMS / (g.mtiles > 0 ? g.mtiles : 1);
-    const int max_split = (N + 31) / 32;
+    const int max_split = (N + 63) / 64;
     if (want > ntiles) ntiles = want < max_split ? want : max_split;
-    if (ntiles < 1) ntiles = 1;
-    int bn = (int)ceil_div(N, ntiles);
-    bn = (bn + 15) & ~15;
-    g.BN = bn;
-    g.ntiles = (int)ceil_div(N, bn);
+    if (ntiles <= 1) {
+        g.BN = (N + 15) & ~15;
+        g.ntiles = 1;
+    } else {
+        int bn = (int)ceil_div(N, ntiles);
+        bn = (bn + 63) & ~63;
+        g.BN = bn;
+        g.ntiles = (int)ceil_div(N, bn);
+    }
+    g.wsub = g.BN >= 64 ? 64 : (g.BN >= 32 ? 32 : 16);
+    g.nsub = (g.BN + g.wsub - 1) / g.wsub;
     int tmem_cols = 32;
-    while (tmem_cols < bn) tmem_cols <<= 1;
-    const int nslabs = (K + g.BK - 1) / g.BK;
+    while (tmem_cols < g.BN) tmem_cols <<= 1;
     // operand stages: two when many CTAs per SM hide the latency for each other; deeper (up to 4, never more than the
     // K slabs + 1) when the tiles are few, so that a CTA has several slabs in flight on its own
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const int reg_limit = (dev >= 0 && dev < kMaxDevices && g_reg_limit[epi][dev] > 0) ? g_reg_limit[epi][dev] : 4;
     auto occupancy = [&](int stages) {
-        const size_t smem = (size_t)gemm_smem_layout(g.BN, g.BK, epi, stages).total;
-        int c = (int)((224 * 1024) / (smem + 1024));
+        const size_t smem = (size_t)gemm_smem_layout(g.BN, g.swzA, g.nslabs, stages, epi, g.wsub).total;
+        int c = (int)((227 * 1024) / (smem + 1024 + 128));                      // + reserved KB + static shared memory
         if (c > 512 / tmem_cols) c = 512 / tmem_cols;
-        return c > 6 ? 6 : c;
+        return c > reg_limit ? reg_limit : c;
     };
     int stages = 2;
     if (occupancy(2) < 1) return false;
     const int64_t tiles = (int64_t)g.mtiles * g.ntiles;
-    while (stages < 4 && stages < nslabs + 1 && occupancy(stages + 1) >= 1 &&
-           (int64_t)PCB_NUM_SMS * occupancy(stages + 1) >= tiles)
-        ++stages;                                                            // deeper only while every tile still gets its own CTA
+    if (g.nslabs >= 3 && occupancy(4) >= 1 && (int64_t)PCB_NUM_SMS * occupancy(4) >= tiles)
+        stages = 4;                                                          // deeper only while every tile still gets its own CTA
     g.stages = stages;
-    g.smem = (size_t)gemm_smem_layout(g.BN, g.BK, epi, stages).total;
+    g.smem = (size_t)gemm_smem_layout(g.BN, g.swzA, g.nslabs, stages, epi, g.wsub).total;
     g.ctas_per_sm = occupancy(stages);
     const int slots = PCB_NUM_SMS * g.ctas_per_sm / g.ntiles;
     g.grid_x = g.mtiles < slots ? g.mtiles : slots;
@@ -546,39 +650,95 @@ static bool gemm_plan(int64_t M, int N, int K, int epi, GemmPlan &g)
     return true;
 }
 
-template <int EPI>
-static int gemm_launch(GemmParams &p, cudaStream_t st)
+// ---- tensor maps: cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn()
 {
-    GemmPlan g;
-    if (!gemm_plan(p.M, p.N, p.K, EPI, g)) return PCB_ERANGE;
-    p.BN = g.BN, p.BK = g.BK, p.mtiles = g.mtiles, p.ntiles = g.ntiles, p.stages = g.stages;
+    static EncodeTiledFn fn = [] {
+        void *f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            f = nullptr;
+        return (EncodeTiledFn)f;
+    }();
+    return fn;
+}
+
+// rows x cols bf16 matrix with leading dimension ld (elements); box = box_rows x box_cols, box_cols * 2 == span bytes
+static int make_map(CUtensorMap *tm, const void *base, int64_t rows, int64_t cols, int64_t ld, int box_rows, int box_cols)
+{
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return PCB_EINVAL;
+    const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    const int span = box_cols * 2;
+    const CUtensorMapSwizzle sw =
+        span == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (span == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+    const CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : PCB_EINVAL;
+}
+
+struct GemmOperands {
+    const void *A, *B, *Y;
+    void *C;
+    int64_t lda, ldb, ldc, ldy;
+    int Nb;                      // rows of B that exist (others are zero)
+};
+
+template <int EPI>
+static int gemm_launch(GemmParams &p, const GemmOperands &o, cudaStream_t st)
+{
     static bool attr_set[kMaxDevices] = {};
     int dev = 0;
     cudaGetDevice(&dev);
-    const bool first = dev >= 0 && dev < kMaxDevices && !attr_set[dev];
-    if (cudaError_t e = smem_optin_once(gemm_rows_kernel<EPI>, 224 * 1024, attr_set)) return (int)e;
-    if (first)      // several CTAs per SM each want tens of KB: ask for the largest shared-memory carve-out
+    if (dev >= 0 && dev < kMaxDevices && !attr_set[dev]) {
+        if (cudaError_t e = smem_optin_once(gemm_rows_kernel<EPI>, 226 * 1024, attr_set)) return (int)e;
+        // several CTAs per SM each want tens of KB: ask for the largest shared-memory carve-out
         cudaFuncSetAttribute(gemm_rows_kernel<EPI>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    // the grid is one wave: never more CTAs than are resident at once (registers may allow fewer than the plan assumed)
-    int occ = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gemm_rows_kernel<EPI>, kGemmThreads, g.smem);
-    if (occ >= 1 && occ < g.ctas_per_sm) {
-        const int slots = PCB_NUM_SMS * occ / g.ntiles;
-        if (slots >= 1 && g.grid_x > slots) g.grid_x = slots;
+        cudaFuncAttributes fa;
+        if (cudaFuncGetAttributes(&fa, gemm_rows_kernel<EPI>) == cudaSuccess && fa.numRegs > 0) {
+            const int regs = (fa.numRegs + 7) & ~7;                          // allocation granularity: 8 registers per thread
+            int c = 65536 / (regs * kGemmThreads);
+            g_reg_limit[EPI][dev] = c < 1 ? 1 : (c > 8 ? 8 : c);
+        }
     }
-    gemm_rows_kernel<EPI><<<dim3((unsigned)g.grid_x, (unsigned)g.ntiles), kGemmThreads, g.smem, st>>>(p);
+    GemmPlan g;
+    if (!gemm_plan(p.M, p.N, p.K, EPI, g)) return PCB_ERANGE;
+    p.BN = g.BN, p.BK = g.BK, p.swzA = g.swzA, p.wsub = g.wsub, p.nsub = g.nsub, p.nslabs = g.nslabs;
+    p.mtiles = g.mtiles, p.ntiles = g.ntiles, p.stages = g.stages;
+    p.sshift = g.stages == 4 ? 2 : 1;
+    p.wshift = g.wsub == 64 ? 6 : (g.wsub == 32 ? 5 : 4);
+    CUtensorMap tmA, tmB, tmC, tmY;
+    if (int rc = make_map(&tmA, o.A, p.M, p.K, o.lda, 128, g.BK)) return rc;
+    if (int rc = make_map(&tmB, o.B, o.Nb, p.K, o.ldb, g.BN, g.BK)) return rc;
+    if (int rc = make_map(&tmC, o.C, p.M, p.N, o.ldc, 128, g.wsub)) return rc;
+    if (EPI == EPI_BNBWD) {
+        if (int rc = make_map(&tmY, o.Y, p.M, p.N, o.ldy, 128, g.wsub)) return rc;
+    } else {
+        tmY = tmC;
+    }
+    gemm_rows_kernel<EPI><<<dim3((unsigned)g.grid_x, (unsigned)g.ntiles), kGemmThreads, g.smem, st>>>(tmA, tmB, tmC, tmY, p);
     PCB_RETURN_LAUNCH_STATUS();
 }
 
 static inline bool al16(const void *q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; }
 
-static int gemm_check(const GemmParams &p)
+static int gemm_check(const GemmParams &p, const GemmOperands &o)
 {
-    PCB_REQUIRE(p.A && p.B && p.C, PCB_EINVAL);
-    PCB_REQUIRE(p.M > 0 && p.N > 0 && p.K > 0 && p.Nb > 0, PCB_EINVAL);
-    PCB_REQUIRE(p.N % 8 == 0 && p.K % 8 == 0 && p.lda % 8 == 0 && p.ldb % 8 == 0 && p.ldc % 8 == 0, PCB_ERANGE);
-    PCB_REQUIRE(p.lda >= p.K && p.ldb >= p.K && p.ldc >= p.N && p.N <= 4096 && p.K <= 8192, PCB_ERANGE);
-    PCB_REQUIRE(al16(p.A) && al16(p.B) && al16(p.C), PCB_EALIGN);
+    PCB_REQUIRE(o.A && o.B && o.C, PCB_EINVAL);
+    PCB_REQUIRE(p.M > 0 && p.N > 0 && p.K > 0 && o.Nb > 0, PCB_EINVAL);
+    PCB_REQUIRE(p.N % 8 == 0 && p.K % 8 == 0 && o.lda % 8 == 0 && o.ldb % 8 == 0 && o.ldc % 8 == 0, PCB_ERANGE);
+    PCB_REQUIRE(o.lda >= p.K && o.ldb >= p.K && o.ldc >= p.N && p.N <= 4096 && p.K <= 8192, PCB_ERANGE);
+    PCB_REQUIRE(p.M < ((int64_t)1 << 31) - 128, PCB_ERANGE);                 // 32-bit TMA row coordinates
+    PCB_REQUIRE(al16(o.A) && al16(o.B) && al16(o.C), PCB_EALIGN);
     return 0;
 }
 
@@ -590,13 +750,10 @@ using namespace pcb;
 PCB_API int64_t pcb_gemm_work_floats(int64_t M, int N, int K)
 {
     GemmPlan g;
-    int64_t need = 0;
-    for (int epi = EPI_STATS; epi <= EPI_BNBWD; ++epi) {
-        if (!gemm_plan(M, N, K, epi, g)) return -1;
-        const int64_t n = (int64_t)g.ntiles * (g.grid_x + g.groups) * 3 * g.BN;
-        if (n > need) need = n;
-    }
-    return need;
+    if (!gemm_plan(M, N, K, EPI_STATS, g)) return -1;                        // BN / ntiles do not depend on the epilogue
+    // upper bound over every occupancy the launch may pick (<= 8 CTAs per SM): the scratch never depends on register counts
+    const int64_t pmax = g.mtiles < PCB_NUM_SMS * 8 ? g.mtiles : PCB_NUM_SMS * 8;
+    return (int64_t)g.ntiles * (pmax + (pmax + kFoldGroup - 1) / kFoldGroup) * 3 * g.BN;
 }
 
 // ticket words a statistics GEMM may use: ntiles * (1 + groups) <= this
@@ -607,11 +764,12 @@ PCB_API int pcb_linear_rows_bf16(const void *x, int64_t ldx, const void *w, int6
                                  void *y, int64_t ldy, pcb_stream_t stream)
 {
     GemmParams p = {};
-    p.A = (const __nv_bfloat16 *)x, p.B = (const __nv_bfloat16 *)w, p.C = (__nv_bfloat16 *)y;
-    p.lda = ldx, p.ldb = ldw, p.ldc = ldy, p.M = M, p.N = N, p.Nb = Nw, p.K = K;
-    const int rc = gemm_check(p);
+    GemmOperands o = {};
+    o.A = x, o.B = w, o.C = y, o.lda = ldx, o.ldb = ldw, o.ldc = ldy, o.Nb = Nw;
+    p.M = M, p.N = N, p.K = K;
+    const int rc = gemm_check(p, o);
     if (rc) return rc;
-    return gemm_launch<EPI_STORE>(p, (cudaStream_t)stream);
+    return gemm_launch<EPI_STORE>(p, o, (cudaStream_t)stream);
 }
 
 // same + training-mode BatchNorm statistics of y: mean / invstd / biased variance of the bias-free output (pcb_bn_apply_rows
@@ -621,14 +779,15 @@ PCB_API int pcb_linear_bn_stats_rows_bf16(const void *x, int64_t ldx, const void
                                           float *var, float *work, unsigned *tickets, pcb_stream_t stream)
 {
     GemmParams p = {};
-    p.A = (const __nv_bfloat16 *)x, p.B = (const __nv_bfloat16 *)w, p.C = (__nv_bfloat16 *)y;
-    p.lda = ldx, p.ldb = ldw, p.ldc = ldy, p.M = M, p.N = N, p.Nb = Nw, p.K = K;
-    const int rc = gemm_check(p);
+    GemmOperands o = {};
+    o.A = x, o.B = w, o.C = y, o.lda = ldx, o.ldb = ldw, o.ldc = ldy, o.Nb = Nw;
+    p.M = M, p.N = N, p.K = K;
+    const int rc = gemm_check(p, o);
     if (rc) return rc;
     PCB_REQUIRE(mean && invstd && var && work && tickets && Cv > 0 && Cv <= N, PCB_EINVAL);
     p.Cv = Cv, p.eps = eps, p.mean = mean, p.invstd = invstd, p.var = var;
     p.parts = work, p.tickets = tickets;
-    return gemm_launch<EPI_STATS>(p, (cudaStream_t)stream);
+    return gemm_launch<EPI_STATS>(p, o, (cudaStream_t)stream);
 }
 
 // data gradient of a layer whose INPUT was z = relu(BN(y)) of the previous layer:
@@ -640,13 +799,14 @@ PCB_API int pcb_dgrad_bn_rows_bf16(const void *gy, int64_t ldg, const void *wt, 
                                    float *sums, float *work, unsigned *tickets, pcb_stream_t stream)
 {
     GemmParams p = {};
-    p.A = (const __nv_bfloat16 *)gy, p.B = (const __nv_bfloat16 *)wt, p.C = (__nv_bfloat16 *)dy;
-    p.lda = ldg, p.ldb = ldwt, p.ldc = lddy, p.M = M, p.N = N, p.Nb = Nw, p.K = K;
-    const int rc = gemm_check(p);
+    GemmOperands o = {};
+    o.A = gy, o.B = wt, o.C = dy, o.Y = yprev, o.lda = ldg, o.ldb = ldwt, o.ldc = lddy, o.ldy = ldyp, o.Nb = Nw;
+    p.M = M, p.N = N, p.K = K;
+    const int rc = gemm_check(p, o);
     if (rc) return rc;
     PCB_REQUIRE(yprev && mean && invstd && gamma && beta && sums && work && tickets, PCB_EINVAL);
     PCB_REQUIRE(Cv > 0 && Cv <= N && ldyp >= N && ldyp % 8 == 0 && al16(yprev), PCB_ERANGE);
-    p.Cv = Cv, p.Y = (const __nv_bfloat16 *)yprev, p.ldy = ldyp, p.bn_mean = mean, p.bn_invstd = invstd, p.gamma = gamma;
+    p.Cv = Cv, p.bn_mean = mean, p.bn_invstd = invstd, p.gamma = gamma;
     p.beta = beta, p.relu = relu, p.sums = sums, p.parts = work, p.tickets = tickets;
-    return gemm_launch<EPI_BNBWD>(p, (cudaStream_t)stream);
+    return gemm_launch<EPI_BNBWD>(p, o, (cudaStream_t)stream);
 }
