@@ -208,8 +208,9 @@ KERNEL_OF = {                                         # C-ABI entry point -> dev
     "pcb_fp_concat_bwd_bf16": "fp_concat_bwd_vec_kernel", "pcb_wgrad_rows_bf16": "wgrad_rows_kernel",
     "pcb_adam_flat_f32": "adam_flat_kernel", "pcb_sa_fused_bf16": "sa_fused_kernel",
     "pcb_linear_rows_bf16": "gemm_rows_kernel<EPI_STORE>", "pcb_linear_bn_stats_rows_bf16": "gemm_rows_kernel<EPI_STATS>",
-    "pcb_dgrad_bn_rows_bf16": "gemm_rows_kernel<EPI_BNBWD>", "pcb_bn_apply_rows": "bn_apply_rows_kernel",
-    "pcb_bn_bwd_apply_rows": "bn_bwd_apply_rows_kernel"}
+    "pcb_dgrad_bn_rows_bf16": "gemm_rows_kernel<EPI_BNBWD>", "pcb_bn_apply_rows": "bn_apply_rows_kernel / bn_apply_pooled_kernel",
+    "pcb_bn_bwd_apply_rows": "bn_bwd_apply_rows_kernel",
+    "pcb_bn_pool_bwd_rows": "bn_pool_sums_kernel + bn_pool_bwd_apply_kernel"}
 
 
 def run_ours(a):

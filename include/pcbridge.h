@@ -266,32 +266,50 @@ int pcb_adam_flat_f32(float *param, const float *grad, float *exp_avg, float *ex
  *   pcb_linear_rows_bf16          plain product (forward of a conv without BatchNorm; data gradient with w = W^T)
  *   pcb_linear_bn_stats_rows_bf16 + training-mode BatchNorm statistics of the result: mean / invstd / var [N] (biased
  *                                 variance, eps) of the bias-free output, from (count, mean, M2) triples merged with
- *                                 Chan's update in a fixed order (stateless, no cancellation).  Cv <= N real channels.  work: pcb_gemm_work_floats(M, N, K) floats of scratch; tickets:
- *                                 pcb_gemm_tickets() zeroed 32-bit words (left zeroed).  Deterministic two-stage sums.
+ *                                 Chan's update in a fixed order (stateless, no cancellation).  Cv <= N real channels.
+ *                                 work: pcb_gemm_work_floats(M, N, K) floats of scratch; tickets: pcb_gemm_tickets()
+ *                                 zeroed 32-bit words (left zeroed).  Deterministic sums.  Deferred final fold
+ *                                 (gparts != NULL): the kernel stops after its first fold level and leaves the group
+ *                                 triples in gparts [*groups_out][3][N] (capacity pcb_gemm_max_groups() rows; *groups_out
+ *                                 is written on the host at launch time); mean / invstd / var may be NULL -- the
+ *                                 pcb_bn_apply_rows call that follows merges the groups and writes them.
  *   pcb_dgrad_bn_rows_bf16        data gradient THROUGH the previous layer's BN + ReLU: gz = gy . wt^T; dy = gz * [z > 0]
  *                                 with z = BN(yprev) recomputed from yprev [M, ldyp] and mean / invstd / gamma / beta;
- *                                 writes dy [M, lddy] and sums [3][N] = (sum dy, sum dy * yhat, 0)
+ *                                 writes dy [M, lddy] and sums [3][N] = (sum dy, sum dy * yhat, 0); deferred as above
+ *                                 (gparts [*groups_out][3][N] = (0, sum dy * yhat, sum dy) per group, sums may be NULL)
  *   pcb_bn_apply_rows             out = [max over pool_k rows of] act(BN(y)) with given statistics (ordinary launch);
  *                                 updates running_mean / running_var [Cv] (may be NULL) from mean / var with `momentum`
- *                                 (unbiased variance; `bias` [Cv], may be NULL, is added to the running mean only)
- *   pcb_bn_bwd_apply_rows         gy = gamma * invstd * (dy - sums[0] / M - yhat * sums[1] / M); gy may alias dy */
+ *                                 (unbiased variance; `bias` [Cv], may be NULL, is added to the running mean only).
+ *                                 gparts != NULL: mean / invstd / var are outputs, merged from `groups` group triples;
+ *                                 ymax != NULL (pooled): also writes y of the winning rows [M / pool_k][C]
+ *   pcb_bn_pool_bwd_rows          backward of a pooled last layer (pool_k > 1) in two ordinary launches: the BatchNorm
+ *                                 sums from gz / ymax / argmax alone (M / pool_k rows), then gy in ONE pass over y
+ *                                 (pcb_bn_bwd_rows: cooperative, two passes); work >= 99 * C floats,
+ *                                 work[0 : 3C] = (sum dy, sum dy * yhat, 0) on return
+ *   pcb_bn_bwd_apply_rows         gy = gamma * invstd * (dy - sums[0] / M - yhat * sums[1] / M); gy may alias dy.
+ *                                 gparts != NULL: sums [3][C] is an output, added up from `groups` group partials */
 int64_t pcb_gemm_work_floats(int64_t M, int N, int K);
 int pcb_gemm_tickets(void);
+int pcb_gemm_max_groups(void);
 int pcb_linear_rows_bf16(const void *x, int64_t ldx, const void *w, int64_t ldw, int64_t M, int N, int Nw, int K, void *y,
                          int64_t ldy, pcb_stream_t stream);
 int pcb_linear_bn_stats_rows_bf16(const void *x, int64_t ldx, const void *w, int64_t ldw, int64_t M, int N, int Nw, int K,
                                   void *y, int64_t ldy, int Cv, float eps, float *mean, float *invstd, float *var,
-                                  float *work, unsigned *tickets, pcb_stream_t stream);
+                                  float *work, unsigned *tickets, float *gparts, int *groups_out, pcb_stream_t stream);
 int pcb_dgrad_bn_rows_bf16(const void *gy, int64_t ldg, const void *wt, int64_t ldwt, int64_t M, int N, int Nw, int K,
                            const void *yprev, int64_t ldyp, const float *mean, const float *invstd, const float *gamma,
                            const float *beta, int Cv, int relu, void *dy, int64_t lddy, float *sums, float *work,
-                           unsigned *tickets, pcb_stream_t stream);
-int pcb_bn_apply_rows(const void *y, int dtype, int64_t M, int C, int Cv, int pool_k, const float *mean,
-                      const float *invstd, const float *gamma, const float *beta, int relu, void *out, int64_t out_pitch,
-                      unsigned char *argmax, const float *var, const float *bias, float momentum, float *running_mean,
-                      float *running_var, pcb_stream_t stream);
+                           unsigned *tickets, float *gparts, int *groups_out, pcb_stream_t stream);
+int pcb_bn_apply_rows(const void *y, int dtype, int64_t M, int C, int Cv, int pool_k, float *mean, float *invstd,
+                      const float *gamma, const float *beta, int relu, void *out, int64_t out_pitch,
+                      unsigned char *argmax, float *var, const float *bias, float momentum, float *running_mean,
+                      float *running_var, const float *gparts, int groups, float eps, void *ymax, pcb_stream_t stream);
+int pcb_bn_pool_bwd_rows(const void *gz, int64_t gz_pitch, const void *ymax, const void *y, const unsigned char *argmax,
+                         int dtype, int64_t M, int C, int Cv, int pool_k, const float *mean, const float *invstd,
+                         const float *gamma, const float *beta, int relu, float *work, void *gy, pcb_stream_t stream);
 int pcb_bn_bwd_apply_rows(const void *dy, const void *y, int dtype, int64_t M, int C, int Cv, const float *mean,
-                          const float *invstd, const float *gamma, const float *sums, void *gy, pcb_stream_t stream);
+                          const float *invstd, const float *gamma, float *sums, void *gy, const float *gparts, int groups,
+                          pcb_stream_t stream);
 
 /* ---- a11 / section 8f rank 1: fused set-abstraction / EdgeConv block for inference
  *          pointnet_util.py:137-147, 203-217, 258-279; pointnet2_utils.py:140-154, 341-356;

@@ -41,11 +41,13 @@ _SIGNATURES = {
     "pcb_adam_flat_f32": [_vp, _vp, _vp, _vp, _i64, _vp, _f, _f, _f, _f, _vp, _vp, _vp, _vp, _vp],
     "pcb_linear_rows_bf16": [_vp, _i64, _vp, _i64, _i64, _i, _i, _i, _vp, _i64, _vp],
     "pcb_linear_bn_stats_rows_bf16": [_vp, _i64, _vp, _i64, _i64, _i, _i, _i, _vp, _i64, _i, _f, _vp, _vp, _vp, _vp, _vp,
-                                      _vp],
+                                      _vp, _vp, _vp],
     "pcb_dgrad_bn_rows_bf16": [_vp, _i64, _vp, _i64, _i64, _i, _i, _i, _vp, _i64, _vp, _vp, _vp, _vp, _i, _i, _vp, _i64,
-                               _vp, _vp, _vp, _vp],
-    "pcb_bn_apply_rows": [_vp, _i, _i64, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _i64, _vp, _vp, _vp, _f, _vp, _vp, _vp],
-    "pcb_bn_bwd_apply_rows": [_vp, _vp, _i, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp],
+                               _vp, _vp, _vp, _vp, _vp, _vp],
+    "pcb_bn_apply_rows": [_vp, _i, _i64, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _i64, _vp, _vp, _vp, _f, _vp, _vp, _vp,
+                          _i, _f, _vp, _vp],
+    "pcb_bn_pool_bwd_rows": [_vp, _i64, _vp, _vp, _vp, _i, _i64, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp],
+    "pcb_bn_bwd_apply_rows": [_vp, _vp, _i, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp],
     "pcb_scene_window_count_f32": [_vp, _i64, _i, _i, _i, _vp, _vp, _vp, _vp, _d, _d, _d, _i, _vp, _vp],
     "pcb_scene_window_fill_f32": [_vp, _i64, _i, _i, _i, _vp, _vp, _vp, _vp, _d, _d, _d, _i, _vp, _vp, ctypes.c_uint, _vp, _vp],
     "pcb_scene_blocks_f32": [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i64, _i, _d, _d, _d, ctypes.c_uint, _vp, _vp, _vp],
@@ -64,7 +66,7 @@ _SIGNATURES = {
 }
 
 EXPORTS = ["pcb_version", "pcb_error_string", "pcb_bn_work_floats", "pcb_nll_rows_blocks", "pcb_gemm_work_floats",
-           "pcb_gemm_tickets", "pcb_bn_set_coop_sms", *_SIGNATURES]
+           "pcb_gemm_tickets", "pcb_gemm_max_groups", "pcb_bn_set_coop_sms", *_SIGNATURES]
 
 
 class PcbError(RuntimeError):
@@ -92,6 +94,8 @@ def lib():
         l.pcb_gemm_work_floats.argtypes = [_i64, _i, _i]
         l.pcb_gemm_tickets.restype = _i
         l.pcb_gemm_tickets.argtypes = []
+        l.pcb_gemm_max_groups.restype = _i
+        l.pcb_gemm_max_groups.argtypes = []
         l.pcb_bn_set_coop_sms.restype = _i
         l.pcb_bn_set_coop_sms.argtypes = [_i]
         for name, args in _SIGNATURES.items():

@@ -403,6 +403,12 @@ struct BnFwdArgs {
     int C, Cv, pool_k, relu, nparts;                   // C = row pitch (multiple of 4), Cv <= C real channels
     int64_t out_pitch;                                 // row pitch of out (C, or wider when out is a column slice)
     float eps, momentum;
+    // bn_apply kernels only: group partials (n, mean, M2) [groups][3][C] left by the statistics GEMM's first fold level
+    // (gemm_rows.cu, deferred mode); every CTA merges them for its constants, CTA 0 also writes mean / invstd / var_out
+    const float *gparts;
+    float *var_out;
+    int groups, rs;                                    // rs: row lanes per pooling group (bn_apply_pooled_kernel)
+    void *ymax;                                        // pooled: y of the winning row [M / pool_k][C] (may be NULL)
 };
 
 template <typename T, int V>
@@ -593,29 +599,35 @@ struct BwdGroups : BwdBase<T, V> {
         typename VecIO<T, V>::Raw g;
         typename AmIO<V>::Raw am;
     };
+    // a unit is one of `rs` contiguous row slices (kp rows each) of a pooling group: unit u = group * rs + slice
+    int rs, kp;
     __device__ __forceinline__ void init(int c) { this->consts(c, APPLY); }
-    __device__ __forceinline__ Pack load(int64_t g, int c) const
+    __device__ __forceinline__ Pack load(int64_t u, int c) const
     {
+        const int64_t g = rs > 1 ? u / rs : u;
         Pack p;
         p.g = VecIO<T, V>::ldraw(this->gz + g * this->gpitch + c);
         p.am = AmIO<V>::ld(this->argmax + g * this->C + c);
         return p;
     }
     template <typename Sink>
-    __device__ __forceinline__ void walk(const Pack &p, int64_t grp, int c, Sink sink) const
+    __device__ __forceinline__ void walk(const Pack &p, int64_t u, int c, Sink sink) const
     {
         float g[V];
         VecIO<T, V>::cvt(p.g, g);
+        const int64_t grp = rs > 1 ? u / rs : u;
+        const int k_lo = (int)(u - grp * rs) * kp;
+        const int k_hi = k_lo + kp < this->pool_k ? k_lo + kp : this->pool_k;
         const int64_t r0 = grp * this->pool_k;
         const T *row = this->y + r0 * this->C + c;
-        for (int k0 = 0; k0 < this->pool_k; k0 += KB) {
+        for (int k0 = k_lo; k0 < k_hi; k0 += KB) {
             typename VecIO<T, V>::Raw t[KB];
 #pragma unroll
             for (int j = 0; j < KB; ++j)
-                if (k0 + j < this->pool_k) t[j] = VecIO<T, V>::ldraw(row + (size_t)(k0 + j) * this->C);
+                if (k0 + j < k_hi) t[j] = VecIO<T, V>::ldraw(row + (size_t)(k0 + j) * this->C);
 #pragma unroll
             for (int j = 0; j < KB; ++j)
-                if (k0 + j < this->pool_k) {
+                if (k0 + j < k_hi) {
                     float dy[V], yh[V];
                     this->row(t[j], g, p.am, k0 + j, dy, yh);
                     sink(r0 + k0 + j, dy, yh);
@@ -640,6 +652,7 @@ struct BnBwdArgs {
     float *work;
     int64_t M, upc, gz_pitch;
     int C, Cv, pool_k, relu, nparts;
+    int rs;                                                // pooled: row slices per pooling group (units = groups * rs)
 };
 
 template <typename T, int V, typename F>
@@ -665,7 +678,8 @@ bn_bwd_fused_kernel(const BnBwdArgs a)
         if (pooled) {
             BwdGroups<T, V, false, 4> f;
             bwd_fill<T, V>(f, a);
-            column_reduce<3, V, 1>(f, a.M / a.pool_k, C, a.upc, parts, s_part);
+            f.rs = a.rs, f.kp = (a.pool_k + a.rs - 1) / a.rs;
+            column_reduce<3, V, 1>(f, a.M / a.pool_k * a.rs, C, a.upc, parts, s_part);
         } else {
             BwdRows<T, V, false> f;
             bwd_fill<T, V>(f, a);
@@ -719,7 +733,8 @@ bn_bwd_fused_kernel(const BnBwdArgs a)
         BwdGroups<T, V, true, 4> f;
         bwd_fill<T, V>(f, a);
         f.s_const = s_const;
-        row_stream<V, 1>(f, a.M / a.pool_k, C);
+        f.rs = a.rs, f.kp = (a.pool_k + a.rs - 1) / a.rs;
+        row_stream<V, 1>(f, a.M / a.pool_k * a.rs, C);
     } else {
         BwdRows<T, V, true> f;
         bwd_fill<T, V>(f, a);
@@ -733,6 +748,75 @@ bn_bwd_fused_kernel(const BnBwdArgs a)
 // Elementwise halves on their own (ordinary launches, no grid barrier): used when the per-channel statistics come
 // out of the epilogue of the tensor-core GEMM that produced y (gemm_rows.cu: EPI_STATS forward, EPI_BNBWD backward).
 // ---------------------------------------------------------------------------------------------
+// group partials of channel c (gemm_rows.cu, deferred fold): every load in flight at once, then four independent merge
+// chains over contiguous quarters of the groups (the chain of <= 37 dependent Chan updates, a division each, would sit
+// on the start-up path of every CTA), joined in quarter order -- a fixed tree, so the result is deterministic
+constexpr int kGroupBatch = 20;                             // 592 CTAs / 32 per group = 19 groups: one round trip
+template <bool CHAN>
+__device__ __forceinline__ void fold_group_parts(const float *gparts, int groups, int C, int c, float &n, float &m, float &q)
+{
+    n = m = q = 0.f;
+    for (int j0 = 0; j0 < groups; j0 += kGroupBatch) {
+        float en[kGroupBatch], em[kGroupBatch], eq[kGroupBatch];
+#pragma unroll
+        for (int u = 0; u < kGroupBatch; ++u) {
+            const bool ok = j0 + u < groups;
+            const float *e = gparts + (size_t)(ok ? j0 + u : 0) * 3 * C + c;
+            en[u] = (CHAN && ok) ? __ldcg(e) : 0.f;
+            em[u] = ok ? __ldcg(e + C) : 0.f;
+            eq[u] = ok ? __ldcg(e + 2 * (size_t)C) : 0.f;
+        }
+        float an[4] = {0.f, 0.f, 0.f, 0.f}, am[4] = {0.f, 0.f, 0.f, 0.f}, aq[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int u = 0; u < kGroupBatch; ++u) {
+            constexpr int QN = kGroupBatch / 4;
+            if (CHAN) chan_merge(an[u / QN], am[u / QN], aq[u / QN], en[u], em[u], eq[u]);
+            else am[u / QN] += em[u], aq[u / QN] += eq[u];
+        }
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+            if (CHAN) chan_merge(n, m, q, an[h], am[h], aq[h]);
+            else m += am[h], q += aq[h];
+        }
+    }
+}
+
+// per-channel constants [sc | sh] of the forward elementwise pass into shared memory; CTA 0 owns the running statistics
+// (and, with deferred statistics, the mean / invstd / var arrays that the backward pass reads)
+__device__ __forceinline__ void fwd_apply_consts(const BnFwdArgs &a, float *s_const)
+{
+    const int C = a.C;
+    const float Mf = (float)a.M;
+    for (int c = threadIdx.x; c < C; c += kBnThreads) {
+        const bool real = c < a.Cv;                         // pad channels (zero columns of y) produce zeros
+        float m = 0.f, is = 0.f, var = 0.f;
+        if (a.gparts) {
+            if (real) {
+                float n, q;
+                fold_group_parts<true>(a.gparts, a.groups, C, c, n, m, q);
+                var = fmaxf(q / Mf, 0.f);
+                is = rsqrtf(var + a.eps);
+            }
+            if (blockIdx.x == 0) a.mean[c] = m, a.invstd[c] = is, a.var_out[c] = var;
+        } else if (real) {
+            m = a.mean[c], is = a.invstd[c];
+            if (a.var) var = a.var[c];
+        }
+        const float sc = real ? is * a.gamma[c] : 0.f;
+        s_const[c] = sc;
+        s_const[C + c] = real ? a.beta[c] - m * sc : 0.f;
+        if (blockIdx.x == 0 && a.running_mean && real) {
+            // running statistics as torch.nn.functional.batch_norm updates them (momentum, unbiased variance; the conv
+            // bias that was folded out of y is added back to the mean)
+            const float b = a.bias ? a.bias[c] : 0.f;
+            a.running_mean[c] = (1.f - a.momentum) * a.running_mean[c] + a.momentum * (m + b);
+            const float unbiased = a.M > 1 ? var * (Mf / (float)(a.M - 1)) : var;
+            a.running_var[c] = (1.f - a.momentum) * a.running_var[c] + a.momentum * unbiased;
+        }
+    }
+    __syncthreads();
+}
+
 template <typename T, int V>
 __global__ void __launch_bounds__(kBnThreads)
 bn_apply_rows_kernel(const BnFwdArgs a)
@@ -740,9 +824,10 @@ bn_apply_rows_kernel(const BnFwdArgs a)
     const int C = a.C;
     __shared__ float s_buf[2][kBnThreads][V];
     float *s_const = nullptr;
-    if (blockIdx.x == 0 && a.running_mean) {
-        // running statistics as torch.nn.functional.batch_norm updates them (momentum, unbiased variance; the conv bias
-        // that was folded out of y is added back to the mean)
+    if (C <= kBnThreads * V) {
+        s_const = &s_buf[0][0][0];
+        fwd_apply_consts(a, s_const);
+    } else if (blockIdx.x == 0 && a.running_mean) {         // very wide rows (never deferred): constants per thread
         const float Mf = (float)a.M;
         for (int c = threadIdx.x; c < a.Cv; c += kBnThreads) {
             const float b = a.bias ? a.bias[c] : 0.f, var = a.var[c];
@@ -750,16 +835,6 @@ bn_apply_rows_kernel(const BnFwdArgs a)
             const float unbiased = a.M > 1 ? var * (Mf / (float)(a.M - 1)) : var;
             a.running_var[c] = (1.f - a.momentum) * a.running_var[c] + a.momentum * unbiased;
         }
-    }
-    if (C <= kBnThreads * V) {
-        s_const = &s_buf[0][0][0];
-        for (int c = threadIdx.x; c < C; c += kBnThreads) {
-            const bool real = c < a.Cv;                     // pad channels (zero columns of y) produce zeros
-            const float sc = real ? a.invstd[c] * a.gamma[c] : 0.f;
-            s_const[c] = sc;
-            s_const[C + c] = real ? a.beta[c] - a.mean[c] * sc : 0.f;
-        }
-        __syncthreads();
     }
     if (a.pool_k > 1) {
         FwdApplyPooled<T, V, 8> f;
@@ -771,6 +846,90 @@ bn_apply_rows_kernel(const BnFwdArgs a)
         f.y = (const T *)a.y, f.out = (T *)a.out, f.mean = a.mean, f.invstd = a.invstd, f.gamma = a.gamma, f.beta = a.beta;
         f.C = C, f.relu = a.relu, f.s_const = s_const, f.opitch = a.out_pitch;
         row_stream<V, PCB_BN_U>(f, a.M, C);
+    }
+}
+
+// Pooled layers (max over pool_k consecutive rows): a.rs row lanes share one pooling group, each takes a contiguous
+// slice of its rows, the lanes' (max, first index) pairs are merged in lane order through shared memory -- same result
+// as one thread walking the whole group, a.rs times the threads (the last layers of the set-abstraction MLPs have only
+// 256 .. 4096 groups: one thread per (group, 8 channels) left 16 .. 64 CTAs on 148 SMs).  C / V <= kBnThreads.
+template <typename T, int V>
+__global__ void __launch_bounds__(kBnThreads)
+bn_apply_pooled_kernel(const BnFwdArgs a)
+{
+    constexpr int KB = 8;
+    const int C = a.C;
+    __shared__ float s_const[2 * kBnThreads * V];
+    __shared__ float s_best[kBnThreads][V];
+    __shared__ float s_yb[kBnThreads][V];
+    __shared__ int s_bi[kBnThreads][V];
+    fwd_apply_consts(a, s_const);
+    const int TX = C / V, TY = kBnThreads / TX, rs = a.rs;
+    const int gpi = TY / rs;                                // pooling groups per CTA iteration
+    const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
+    const int gl = ty / rs, sl = ty - gl * rs;
+    const bool lane_ok = ty < gpi * rs;
+    const int c = tx * V;
+    const int pool_k = a.pool_k, kp = (pool_k + rs - 1) / rs;
+    const int k_lo = sl * kp, k_hi = k_lo + kp < pool_k ? k_lo + kp : pool_k;
+    const int64_t groups = a.M / pool_k;
+    const T *y = (const T *)a.y;
+    T *out = (T *)a.out;
+    float sc[V], sh[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) sc[i] = s_const[c + i], sh[i] = s_const[C + c + i];
+    for (int64_t g0 = (int64_t)blockIdx.x * gpi; g0 < groups; g0 += (int64_t)gridDim.x * gpi) {
+        const int64_t g = g0 + gl;
+        const bool act = lane_ok && g < groups;
+        float best[V], yb[V];
+        int bi[V];
+#pragma unroll
+        for (int i = 0; i < V; ++i) best[i] = -INFINITY, yb[i] = 0.f, bi[i] = k_lo;
+        if (act) {
+            const T *row = y + (g * pool_k) * C + c;
+            for (int k0 = k_lo; k0 < k_hi; k0 += KB) {
+                typename VecIO<T, V>::Raw t[KB];
+#pragma unroll
+                for (int j = 0; j < KB; ++j)
+                    if (k0 + j < k_hi) t[j] = VecIO<T, V>::ldraw(row + (size_t)(k0 + j) * C);
+#pragma unroll
+                for (int j = 0; j < KB; ++j)
+                    if (k0 + j < k_hi) {
+                        float v[V];
+                        VecIO<T, V>::cvt(t[j], v);
+#pragma unroll
+                        for (int i = 0; i < V; ++i) {
+                            float z = fmaf(v[i], sc[i], sh[i]);
+                            if (a.relu) z = fmaxf(z, 0.f);
+                            if (k0 + j == k_lo || z > best[i]) best[i] = z, yb[i] = v[i], bi[i] = k0 + j;
+                        }
+                    }
+            }
+        }
+        if (rs > 1) {
+            if (act && sl > 0) {
+#pragma unroll
+                for (int i = 0; i < V; ++i)
+                    s_best[threadIdx.x][i] = best[i], s_yb[threadIdx.x][i] = yb[i], s_bi[threadIdx.x][i] = bi[i];
+            }
+            __syncthreads();
+            if (act && sl == 0) {
+                for (int j = 1; j < rs; ++j) {
+                    const int o = threadIdx.x + j * TX;     // lane sl = j of the same group and channels
+                    if (j * kp < pool_k) {
+#pragma unroll
+                        for (int i = 0; i < V; ++i)
+                            if (s_best[o][i] > best[i]) best[i] = s_best[o][i], yb[i] = s_yb[o][i], bi[i] = s_bi[o][i];
+                    }
+                }
+            }
+        }
+        if (act && sl == 0) {
+            VecIO<T, V>::store(out + g * a.out_pitch + c, best);
+            if (a.argmax) AmIO<V>::st(a.argmax + g * C + c, bi);
+            if (a.ymax) VecIO<T, V>::store((T *)a.ymax + g * C + c, yb);       // exact: yb is the stored value of y
+        }
+        if (rs > 1) __syncthreads();
     }
 }
 
@@ -820,6 +979,11 @@ struct BnBwdApplyArgs {
     const float *mean, *invstd, *gamma, *sums;              // sums: [>= 2][C] = sum dy, sum dy*yhat
     int64_t M;
     int C, Cv;
+    // deferred: group partials (0, sum dy*yhat, sum dy) [groups][3][C] of the data-gradient GEMM's first fold level;
+    // every CTA adds them up in group order, CTA 0 writes sums_out [3][C] = (sum dy, sum dy*yhat, 0)
+    const float *gparts;
+    float *sums_out;
+    int groups;
 };
 
 constexpr int kBnApplyMaxC = 1024;
@@ -837,8 +1001,16 @@ bn_bwd_apply_rows_kernel(const BnBwdApplyArgs a)
         s_const[c] = real ? -a.mean[c] * is : 0.f;
         s_const[C + c] = is;
         s_const[2 * C + c] = real ? is * a.gamma[c] : 0.f;
-        s_const[3 * C + c] = real ? a.sums[c] * invM : 0.f;
-        s_const[4 * C + c] = real ? a.sums[C + c] * invM : 0.f;
+        float s0 = 0.f, s1 = 0.f;
+        if (a.gparts) {
+            float n;
+            if (real) fold_group_parts<false>(a.gparts, a.groups, C, c, n, s1, s0);
+            if (blockIdx.x == 0) a.sums_out[c] = s0, a.sums_out[C + c] = s1, a.sums_out[2 * C + c] = 0.f;
+        } else if (real) {
+            s0 = a.sums[c], s1 = a.sums[C + c];
+        }
+        s_const[3 * C + c] = s0 * invM;
+        s_const[4 * C + c] = s1 * invM;
     }
     __syncthreads();
     BwdApplyDy<T, V> f;
@@ -846,16 +1018,192 @@ bn_bwd_apply_rows_kernel(const BnBwdApplyArgs a)
     row_stream<V, PCB_BN_UB>(f, a.M, C);
 }
 
-// grid of an elementwise launch: every thread row gets work, at most 8 CTAs per SM
-static int stream_grid(int64_t units, int C, int V)
+// ---------------------------------------------------------------------------------------------
+// Backward of a POOLED last layer without a cooperative launch.  Only the winning row of a pooling group receives a
+// gradient, so the two BatchNorm sums need gz, argmax and the pre-activation of the winning rows (ymax, written by
+// bn_apply_pooled_kernel) -- M / pool_k rows instead of M: a small sums kernel (<= kPoolSumCtas CTAs, each leaves
+// its partial (0, sum dy*yhat, sum dy) like a fold group of the statistics GEMM), then ONE streaming pass
+// (bn_pool_bwd_apply_kernel) whose CTAs add those partials up while they set up their constants.  y is read once.
+// ---------------------------------------------------------------------------------------------
+constexpr int kPoolSumCtas = 32;
+
+struct BnPoolSumArgs {
+    const void *gz, *ymax;
+    const float *mean, *invstd, *gamma, *beta;
+    float *gparts;                                         // [gridDim.x][3][C]
+    int64_t groups, gz_pitch;
+    int C, Cv, relu;
+};
+
+template <typename T, int V>
+__global__ void __launch_bounds__(kBnThreads)
+bn_pool_sums_kernel(const BnPoolSumArgs a)
+{
+    const int C = a.C;
+    const Lanes L(C, V);
+    __shared__ float s_acc[2][kBnThreads][V];
+    const T *gz = (const T *)a.gz, *ym = (const T *)a.ymax;
+    float *out = a.gparts + (size_t)blockIdx.x * 3 * C;
+    for (int cg0 = 0; cg0 < L.CV; cg0 += L.TX) {
+        const int cgi = cg0 + L.tx, c = cgi * V;
+        float acc[2][V];
+#pragma unroll
+        for (int i = 0; i < V; ++i) acc[0][i] = acc[1][i] = 0.f;
+        if (L.ty < L.TY && cgi < L.CV) {
+            float nm[V], is[V], sc[V], sh[V];
+#pragma unroll
+            for (int i = 0; i < V; ++i) {
+                const bool real = c + i < a.Cv;
+                const float m = real ? a.mean[c + i] : 0.f;
+                is[i] = real ? a.invstd[c + i] : 0.f;
+                nm[i] = -m * is[i];
+                sc[i] = real ? is[i] * a.gamma[c + i] : 0.f;  // same expressions as the forward pass
+                sh[i] = real ? a.beta[c + i] - m * sc[i] : 0.f;
+            }
+            const int64_t stride = (int64_t)gridDim.x * L.TY;
+            for (int64_t g = (int64_t)blockIdx.x * L.TY + L.ty; g < a.groups; g += 4 * stride) {
+                typename VecIO<T, V>::Raw rg[4], ry[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (g + j * stride < a.groups) {
+                        rg[j] = VecIO<T, V>::ldraw(gz + (g + j * stride) * a.gz_pitch + c);
+                        ry[j] = VecIO<T, V>::ldraw(ym + (g + j * stride) * C + c);
+                    }
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (g + j * stride < a.groups) {
+                        float gv[V], yv[V];
+                        VecIO<T, V>::cvt(rg[j], gv);
+                        VecIO<T, V>::cvt(ry[j], yv);
+#pragma unroll
+                        for (int i = 0; i < V; ++i) {
+                            const float yh = fmaf(yv[i], is[i], nm[i]);
+                            const float z = fmaf(yv[i], sc[i], sh[i]);
+                            const float dy = (!a.relu || z > 0.f) ? gv[i] : 0.f;
+                            acc[0][i] += dy;
+                            acc[1][i] = fmaf(dy, yh, acc[1][i]);
+                        }
+                    }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < V; ++i) s_acc[0][threadIdx.x][i] = acc[0][i], s_acc[1][threadIdx.x][i] = acc[1][i];
+        __syncthreads();
+        if (L.ty == 0 && cgi < L.CV) {
+#pragma unroll
+            for (int i = 0; i < V; ++i) {
+                float s0 = 0.f, s1 = 0.f;
+                for (int y = 0; y < L.TY; ++y) s0 += s_acc[0][y * L.TX + L.tx][i], s1 += s_acc[1][y * L.TX + L.tx][i];
+                const bool real = c + i < a.Cv;
+                out[c + i] = 0.f, out[C + c + i] = real ? s1 : 0.f, out[2 * C + c + i] = real ? s0 : 0.f;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+struct BnPoolBwdArgs {
+    BnBwdArgs b;                                           // gz, y, argmax, gy, statistics; work -> sums_out [3][C]
+    const float *gparts;
+    int groups;
+};
+
+template <typename T, int V>
+__global__ void __launch_bounds__(kBnThreads)
+bn_pool_bwd_apply_kernel(const BnPoolBwdArgs p)
+{
+    const BnBwdArgs &a = p.b;
+    const int C = a.C;
+    __shared__ float s_const[6 * kBnApplyMaxC];
+    const float invM = 1.f / (float)a.M;
+    for (int c = threadIdx.x; c < C; c += kBnThreads) {
+        const bool real = c < a.Cv;                         // pad channel: every constant zero -> gy = 0
+        const float m = real ? a.mean[c] : 0.f, is = real ? a.invstd[c] : 0.f;
+        const float sc = real ? is * a.gamma[c] : 0.f;
+        float n, s0 = 0.f, s1 = 0.f;
+        if (real) fold_group_parts<false>(p.gparts, p.groups, C, c, n, s1, s0);
+        if (blockIdx.x == 0) a.work[c] = s0, a.work[C + c] = s1, a.work[2 * C + c] = 0.f;
+        s_const[c] = -m * is;
+        s_const[C + c] = is;
+        s_const[2 * C + c] = sc;
+        s_const[3 * C + c] = real ? a.beta[c] - m * sc : 0.f;
+        s_const[4 * C + c] = s0 * invM;
+        s_const[5 * C + c] = s1 * invM;
+    }
+    __syncthreads();
+    BwdGroups<T, V, true, 4> f;
+    bwd_fill<T, V>(f, a);
+    f.s_const = s_const;
+    f.rs = a.rs, f.kp = (a.pool_k + a.rs - 1) / a.rs;
+    row_stream<V, 1>(f, a.M / a.pool_k * a.rs, C);
+}
+
+// Row slices per pooling group: the smallest power of two that puts >= 512 threads' worth of (unit, channel group)
+// pairs on every SM (2 resident CTAs of 256 threads), while a slice keeps >= min_rows rows (loads in flight per thread) -- at most 16.
+static int pool_row_slices(int64_t groups, int CV, int pool_k, int min_rows)
+{
+    static const int forced = [] { const char *e = getenv("PCB_POOL_RS"); return e ? atoi(e) : 0; }();   // experiments
+    if (forced > 0) return forced <= pool_k ? forced : 1;
+    int rs = 1;
+    while (rs < 16 && pool_k / (rs * 2) >= min_rows && groups * rs * CV < (int64_t)PCB_NUM_SMS * 512) rs *= 2;
+    return rs;
+}
+
+// CTAs of `kernel` that are resident at once (occupancy query cached per device): the elementwise kernels loop with a
+// grid stride, and every CTA pays a start-up cost (per-channel constants, with deferred statistics a fold over the
+// group partials: ~2 us) -- one wave of persistent CTAs pays it once
+template <typename K>
+static int resident_ctas(K kernel, int (&occ_cache)[kMaxDevices])
+{
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int occ = (dev >= 0 && dev < kMaxDevices) ? occ_cache[dev] : 0;
+    if (occ == 0) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kBnThreads, 0) != cudaSuccess || occ < 1) occ = 1;
+        if (dev >= 0 && dev < kMaxDevices) occ_cache[dev] = occ;
+    }
+    return occ * PCB_NUM_SMS;
+}
+
+// grid of an elementwise launch: every thread row gets work, at most `cap` CTAs (one resident wave)
+static int stream_grid(int64_t units, int C, int V, int cap)
 {
     const int CV = C / V;
     const int TX = CV < kBnThreads ? CV : kBnThreads;
     const int TY = kBnThreads / TX;
     const int64_t want = ceil_div(units, (int64_t)TY * 4);
-    const int64_t cap = (int64_t)PCB_NUM_SMS * 8;
     const int64_t g = want < cap ? want : cap;
     return g < 1 ? 1 : (int)g;
+}
+
+template <typename T, int V>
+static void bn_apply_launch(const BnFwdArgs &a, int64_t units, cudaStream_t st)
+{
+    static int occ[kMaxDevices] = {};
+    const int cap = resident_ctas(bn_apply_rows_kernel<T, V>, occ);
+    bn_apply_rows_kernel<T, V><<<stream_grid(units, a.C, V, cap), kBnThreads, 0, st>>>(a);
+}
+
+template <typename T, int V>
+static void bn_apply_pooled_launch(BnFwdArgs a, int64_t units, cudaStream_t st)
+{
+    static int occ[kMaxDevices] = {};
+    const int cap = resident_ctas(bn_apply_pooled_kernel<T, V>, occ);
+    // row lanes: a power of two that divides into the CTA's thread rows
+    const int TY = kBnThreads / (a.C / V);
+    int rs = pool_row_slices(units, a.C / V, a.pool_k, 2);
+    while (rs > TY) rs >>= 1;
+    a.rs = rs;
+    const int64_t want = ceil_div(units, TY / rs);
+    bn_apply_pooled_kernel<T, V><<<(int)(want < cap ? want : cap), kBnThreads, 0, st>>>(a);
+}
+
+template <typename T, int V>
+static void bn_bwd_apply_launch(const BnBwdApplyArgs &a, cudaStream_t st)
+{
+    static int occ[kMaxDevices] = {};
+    const int cap = resident_ctas(bn_bwd_apply_rows_kernel<T, V>, occ);
+    bn_bwd_apply_rows_kernel<T, V><<<stream_grid(a.M, a.C, V, cap), kBnThreads, 0, st>>>(a);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -941,7 +1289,8 @@ static int bn_bwd_launch(BnBwdArgs a, cudaStream_t st)
 {
     static int occ_cache[kMaxDevices] = {};
     const int cap = coop_capacity(bn_bwd_fused_kernel<T, V>, occ_cache);
-    const Plan p = make_plan(a.M / a.pool_k, a.C, V, cap);
+    a.rs = pool_row_slices(a.M / a.pool_k, a.C / V, a.pool_k, 4);
+    const Plan p = make_plan(a.M / a.pool_k * a.rs, a.C, V, cap);
     a.upc = p.upc, a.nparts = p.nparts;
     return coop_launch(bn_bwd_fused_kernel<T, V>, p.grid, a, st);
 }
@@ -981,7 +1330,7 @@ PCB_API int pcb_bn_fwd_rows(const void *y, int dtype, int64_t M, int C, int Cv, 
     PCB_BN_CHECK(M, C, pool_k);
     PCB_REQUIRE(Cv > 0 && Cv <= C && (Cv == C || C <= 1024), PCB_ERANGE);   // padded rows use the shared-memory constants
     PCB_REQUIRE(!running_mean || running_var, PCB_EINVAL);
-    BnFwdArgs a;
+    BnFwdArgs a = {};
     a.y = y, a.out = out, a.argmax = argmax, a.bias = bias, a.gamma = gamma, a.beta = beta;
     a.running_mean = running_mean, a.running_var = running_var;
     a.mean = mean, a.invstd = invstd, a.work = work, a.M = M, a.C = C, a.Cv = Cv, a.pool_k = pool_k, a.relu = relu;
@@ -1001,7 +1350,7 @@ PCB_API int pcb_bn_bwd_rows(const void *gz, int64_t gz_pitch, const void *y, con
     PCB_BN_CHECK(M, C, pool_k);
     PCB_REQUIRE(Cv > 0 && Cv <= C, PCB_ERANGE);
     PCB_REQUIRE(pool_k == 1 || argmax, PCB_EINVAL);
-    BnBwdArgs a;
+    BnBwdArgs a = {};
     a.gz = gz, a.y = y, a.argmax = argmax, a.gy = gy, a.mean = mean, a.invstd = invstd, a.gamma = gamma, a.beta = beta;
     a.work = work, a.M = M, a.C = C, a.Cv = Cv, a.pool_k = pool_k, a.relu = relu, a.upc = 0, a.nparts = 0;
     a.gz_pitch = gz_pitch > 0 ? gz_pitch : C;
@@ -1015,50 +1364,111 @@ PCB_API int pcb_bn_bwd_rows(const void *gz, int64_t gz_pitch, const void *y, con
 // Elementwise half of the forward pass with given statistics (mean / invstd / var from the GEMM epilogue):
 // out = [max over pool_k rows of] act(BN(y)); ordinary launch.  With running_mean != NULL the first CTA also updates the
 // running statistics from mean / var (bias: the conv bias that was folded out of y, may be NULL).
-PCB_API int pcb_bn_apply_rows(const void *y, int dtype, int64_t M, int C, int Cv, int pool_k, const float *mean,
-                              const float *invstd, const float *gamma, const float *beta, int relu, void *out,
-                              int64_t out_pitch, unsigned char *argmax, const float *var, const float *bias, float momentum,
-                              float *running_mean, float *running_var, pcb_stream_t stream)
+// Deferred statistics (gparts != NULL): mean / invstd / var are OUTPUTS -- every CTA merges the `groups` group partials
+// (n, mean, M2) [groups][3][C] that pcb_linear_bn_stats_rows_bf16 left, CTA 0 writes the three arrays (eps as given).
+// ymax (pooled layers, may be NULL): [M / pool_k][C] pre-activation y of the winning rows, for pcb_bn_pool_bwd_rows.
+PCB_API int pcb_bn_apply_rows(const void *y, int dtype, int64_t M, int C, int Cv, int pool_k, float *mean,
+                              float *invstd, const float *gamma, const float *beta, int relu, void *out,
+                              int64_t out_pitch, unsigned char *argmax, float *var, const float *bias, float momentum,
+                              float *running_mean, float *running_var, const float *gparts, int groups, float eps,
+                              void *ymax, pcb_stream_t stream)
 {
     PCB_REQUIRE(y && gamma && beta && mean && invstd && out, PCB_EINVAL);
     PCB_REQUIRE(!running_mean || (running_var && var), PCB_EINVAL);
+    PCB_REQUIRE(!gparts || (var && groups >= 1), PCB_EINVAL);
     PCB_BN_CHECK(M, C, pool_k);
     PCB_REQUIRE(Cv > 0 && Cv <= C && (Cv == C || C <= 1024), PCB_ERANGE);
     BnFwdArgs a = {};
     a.y = y, a.out = out, a.argmax = argmax, a.gamma = gamma, a.beta = beta;
-    a.mean = const_cast<float *>(mean), a.invstd = const_cast<float *>(invstd), a.M = M, a.C = C, a.Cv = Cv;
+    a.mean = mean, a.invstd = invstd, a.M = M, a.C = C, a.Cv = Cv;
     a.pool_k = pool_k, a.relu = relu, a.out_pitch = out_pitch > 0 ? out_pitch : C;
     a.var = var, a.bias = bias, a.momentum = momentum, a.running_mean = running_mean, a.running_var = running_var;
+    a.gparts = gparts, a.var_out = var, a.groups = groups, a.eps = eps, a.rs = 1, a.ymax = ymax;
+    PCB_REQUIRE(!ymax || (pool_k > 1 && C / (dtype && C % 8 == 0 ? 8 : 4) <= kBnThreads), PCB_ERANGE);
     PCB_REQUIRE(a.out_pitch >= C && a.out_pitch % 4 == 0, PCB_ERANGE);
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t units = M / pool_k;
-    if (!dtype) {
-        bn_apply_rows_kernel<float, 4><<<stream_grid(units, C, 4), kBnThreads, 0, st>>>(a);
-    } else if (C % 8 == 0 && a.out_pitch % 8 == 0 && al16(y) && al16(out)) {
-        bn_apply_rows_kernel<__nv_bfloat16, 8><<<stream_grid(units, C, 8), kBnThreads, 0, st>>>(a);
-    } else {
-        bn_apply_rows_kernel<__nv_bfloat16, 4><<<stream_grid(units, C, 4), kBnThreads, 0, st>>>(a);
+    const bool v8 = dtype && C % 8 == 0 && a.out_pitch % 8 == 0 && al16(y) && al16(out);
+    const int V = v8 ? 8 : 4;
+    PCB_REQUIRE(!gparts || C <= kBnThreads * V, PCB_ERANGE);    // deferred statistics go through the shared constants
+    if (pool_k > 1 && C / V <= kBnThreads) {
+        if (!dtype) bn_apply_pooled_launch<float, 4>(a, units, st);
+        else if (v8) bn_apply_pooled_launch<__nv_bfloat16, 8>(a, units, st);
+        else bn_apply_pooled_launch<__nv_bfloat16, 4>(a, units, st);
+        PCB_RETURN_LAUNCH_STATUS();
     }
+    if (!dtype) bn_apply_launch<float, 4>(a, units, st);
+    else if (v8) bn_apply_launch<__nv_bfloat16, 8>(a, units, st);
+    else bn_apply_launch<__nv_bfloat16, 4>(a, units, st);
     PCB_RETURN_LAUNCH_STATUS();
 }
 
 // Elementwise half of the backward pass: gy = gamma * invstd * (dy - sums[0] / M - yhat * sums[1] / M) from the masked
 // gradient dy and the column sums that the data-gradient GEMM's epilogue produced (pcb_dgrad_bn_rows_bf16).  gy may be dy.
+// Deferred sums (gparts != NULL): `sums` [3][C] is an OUTPUT, folded from the `groups` group partials of that GEMM.
 PCB_API int pcb_bn_bwd_apply_rows(const void *dy, const void *y, int dtype, int64_t M, int C, int Cv, const float *mean,
-                                  const float *invstd, const float *gamma, const float *sums, void *gy, pcb_stream_t stream)
+                                  const float *invstd, const float *gamma, float *sums, void *gy, const float *gparts,
+                                  int groups, pcb_stream_t stream)
 {
     PCB_REQUIRE(dy && y && mean && invstd && gamma && sums && gy, PCB_EINVAL);
     PCB_REQUIRE(M > 0 && C > 0 && C % 4 == 0 && C <= kBnApplyMaxC && (dtype == 0 || dtype == 1), PCB_ERANGE);
-    PCB_REQUIRE(Cv > 0 && Cv <= C, PCB_ERANGE);
-    BnBwdApplyArgs a;
+    PCB_REQUIRE(Cv > 0 && Cv <= C && (!gparts || groups >= 1), PCB_ERANGE);
+    BnBwdApplyArgs a = {};
     a.dy = dy, a.y = y, a.gy = gy, a.mean = mean, a.invstd = invstd, a.gamma = gamma, a.sums = sums, a.M = M, a.C = C, a.Cv = Cv;
+    a.gparts = gparts, a.sums_out = sums, a.groups = groups;
     cudaStream_t st = (cudaStream_t)stream;
+    if (!dtype) bn_bwd_apply_launch<float, 4>(a, st);
+    else if (C % 8 == 0 && al16(y) && al16(dy) && al16(gy)) bn_bwd_apply_launch<__nv_bfloat16, 8>(a, st);
+    else bn_bwd_apply_launch<__nv_bfloat16, 4>(a, st);
+    PCB_RETURN_LAUNCH_STATUS();
+}
+
+// Backward of a pooled last layer (pool_k > 1) in two ordinary launches: the BatchNorm sums from gz / ymax / the
+// statistics alone (M / pool_k rows), then gy in one pass over y.  Same results as pcb_bn_bwd_rows up to summation
+// order; work: >= 3 * C * (1 + 32) floats, work[0 : 3C] = (sum dy, sum dy * yhat, 0) on return.
+PCB_API int pcb_bn_pool_bwd_rows(const void *gz, int64_t gz_pitch, const void *ymax, const void *y,
+                                 const unsigned char *argmax, int dtype, int64_t M, int C, int Cv, int pool_k,
+                                 const float *mean, const float *invstd, const float *gamma, const float *beta, int relu,
+                                 float *work, void *gy, pcb_stream_t stream)
+{
+    PCB_REQUIRE(gz && ymax && y && argmax && mean && invstd && gamma && beta && work && gy, PCB_EINVAL);
+    PCB_BN_CHECK(M, C, pool_k);
+    PCB_REQUIRE(pool_k > 1 && Cv > 0 && Cv <= C && C <= kBnApplyMaxC, PCB_ERANGE);
+    const int64_t gp = gz_pitch > 0 ? gz_pitch : C;
+    PCB_REQUIRE(gp >= C && gp % 4 == 0, PCB_ERANGE);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t groups = M / pool_k;
+    const bool v8 = dtype && C % 8 == 0 && gp % 8 == 0 && al16(y) && al16(gz) && al16(gy) && al16(ymax);
+    const int V = v8 ? 8 : 4;
+    BnPoolSumArgs sa;
+    sa.gz = gz, sa.ymax = ymax, sa.mean = mean, sa.invstd = invstd, sa.gamma = gamma, sa.beta = beta;
+    sa.gparts = work + 3 * (size_t)C, sa.groups = groups, sa.gz_pitch = gp, sa.C = C, sa.Cv = Cv, sa.relu = relu;
+    const int CV = C / V, TX = CV < kBnThreads ? CV : kBnThreads, TY = kBnThreads / TX;
+    int64_t sgrid = ceil_div(groups, (int64_t)TY * 4);
+    if (sgrid > kPoolSumCtas) sgrid = kPoolSumCtas;
+    if (sgrid < 1) sgrid = 1;
+    BnPoolBwdArgs pa = {};
+    BnBwdArgs &a = pa.b;
+    a.gz = gz, a.y = y, a.argmax = argmax, a.gy = gy, a.mean = mean, a.invstd = invstd, a.gamma = gamma, a.beta = beta;
+    a.work = work, a.M = M, a.C = C, a.Cv = Cv, a.pool_k = pool_k, a.relu = relu, a.gz_pitch = gp;
+    a.rs = pool_row_slices(groups, C / V, pool_k, 4);
+    pa.gparts = sa.gparts, pa.groups = (int)sgrid;
+    const int64_t units = groups * a.rs;
     if (!dtype) {
-        bn_bwd_apply_rows_kernel<float, 4><<<stream_grid(M, C, 4), kBnThreads, 0, st>>>(a);
-    } else if (C % 8 == 0 && al16(y) && al16(dy) && al16(gy)) {
-        bn_bwd_apply_rows_kernel<__nv_bfloat16, 8><<<stream_grid(M, C, 8), kBnThreads, 0, st>>>(a);
+        static int occ[kMaxDevices] = {};
+        bn_pool_sums_kernel<float, 4><<<(int)sgrid, kBnThreads, 0, st>>>(sa);
+        const int cap = resident_ctas(bn_pool_bwd_apply_kernel<float, 4>, occ);
+        bn_pool_bwd_apply_kernel<float, 4><<<stream_grid(units * 4, C, 4, cap), kBnThreads, 0, st>>>(pa);
+    } else if (v8) {
+        static int occ[kMaxDevices] = {};
+        bn_pool_sums_kernel<__nv_bfloat16, 8><<<(int)sgrid, kBnThreads, 0, st>>>(sa);
+        const int cap = resident_ctas(bn_pool_bwd_apply_kernel<__nv_bfloat16, 8>, occ);
+        bn_pool_bwd_apply_kernel<__nv_bfloat16, 8><<<stream_grid(units * 4, C, 8, cap), kBnThreads, 0, st>>>(pa);
     } else {
-        bn_bwd_apply_rows_kernel<__nv_bfloat16, 4><<<stream_grid(M, C, 4), kBnThreads, 0, st>>>(a);
+        static int occ[kMaxDevices] = {};
+        bn_pool_sums_kernel<__nv_bfloat16, 4><<<(int)sgrid, kBnThreads, 0, st>>>(sa);
+        const int cap = resident_ctas(bn_pool_bwd_apply_kernel<__nv_bfloat16, 4>, occ);
+        bn_pool_bwd_apply_kernel<__nv_bfloat16, 4><<<stream_grid(units * 4, C, 4, cap), kBnThreads, 0, st>>>(pa);
     }
     PCB_RETURN_LAUNCH_STATUS();
 }

@@ -61,6 +61,11 @@ struct GemmParams {
     const float *bn_mean, *bn_invstd, *gamma, *beta;   // [Cv]
     int relu;
     float *sums;                 // [3][N]: sum dy, sum dy*yhat, 0 (gradient of the folded conv bias)
+    // deferred final fold (either statistics epilogue): when set, the kernel stops after the first fold level and leaves
+    // the group partials [groups][3][N] here -- (n, mean, M2) or (0, sum dy*yhat, sum dy) -- for the elementwise kernel
+    // that consumes the statistics anyway (pcb_bn_apply_rows / pcb_bn_bwd_apply_rows fold them at their start): the
+    // second "last arriver" level (fence + ticket + fold, ~4 us of serial latency per launch) disappears
+    float *gparts;
 };
 
 __device__ __forceinline__ void unpack8(const uint4 &t, float v[8])
@@ -70,18 +75,6 @@ __device__ __forceinline__ void unpack8(const uint4 &t, float v[8])
     for (int i = 0; i < 4; ++i) {
         v[2 * i] = __uint_as_float(w[i] << 16);
         v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
-    }
-}
-
-// Chan's pairwise update: (n, mean, m2) <- (n, mean, m2) + (cn, cm, cq)
-__device__ __forceinline__ void chan_merge(float &n, float &mean, float &m2, float cn, float cm, float cq)
-{
-    const float tot = n + cn;
-    if (tot > 0.f) {
-        const float w = cn / tot, d = cm - mean;
-        mean = fmaf(d, w, mean);
-        m2 = m2 + cq + d * d * n * w;
-        n = tot;
     }
 }
 
@@ -202,14 +195,15 @@ __device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c)
 __device__ __forceinline__ uint64_t bf2_to_f2(unsigned w) { return (uint64_t)(w << 16) | ((uint64_t)(w & 0xffff0000u) << 32); }
 
 // `cnt` partial triples (n, mean | sum, M2 | sum) of column c, `stride` floats apart, merged in index order; the loads
-// of eight partials are in flight together (the fold is a chain of L2 round trips otherwise)
+// of sixteen partials are in flight together (the fold is a chain of L2 round trips otherwise)
 template <int EPI>
 __device__ __forceinline__ void fold_range(const float *base, int cnt, size_t stride, int BN, float &n, float &m, float &q)
 {
-    for (int j0 = 0; j0 < cnt; j0 += 8) {
-        float en[8], em[8], eq[8];
+    constexpr int FB = 16;                                                   // partials in flight per thread
+    for (int j0 = 0; j0 < cnt; j0 += FB) {
+        float en[FB], em[FB], eq[FB];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
+        for (int u = 0; u < FB; ++u) {
             const bool ok = j0 + u < cnt;
             const float *e = base + (size_t)(ok ? j0 + u : 0) * stride;
             en[u] = (EPI == EPI_STATS && ok) ? __ldcg(e) : 0.f;
@@ -217,7 +211,7 @@ __device__ __forceinline__ void fold_range(const float *base, int cnt, size_t st
             eq[u] = ok ? __ldcg(e + 2 * BN) : 0.f;
         }
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
+        for (int u = 0; u < FB; ++u) {
             if (EPI == EPI_STATS) chan_merge(n, m, q, en[u], em[u], eq[u]);
             else m += em[u], q += eq[u];
         }
@@ -533,7 +527,15 @@ gemm_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             float n, m, q;
             fold_cols<EPI>(lvl0 + (size_t)g_lo * 3 * BN, g_hi - g_lo, BN, s_comb, n, m, q);
             bool final_level = G == 1;
-            if (!final_level) {
+            if (p.gparts) {                                                  // deferred: the consumer merges the groups
+                if (tid < BN && n0 + tid < p.N) {
+                    float *o = p.gparts + (size_t)grp * 3 * p.N + n0 + tid;
+                    const bool real = n0 + tid < p.Cv;
+                    o[0] = real ? n : 0.f, o[p.N] = real ? m : 0.f, o[2 * (size_t)p.N] = real ? q : 0.f;
+                }
+                if (tid == 0) tick[1 + grp] = 0u;
+                final_level = false;
+            } else if (!final_level) {
                 if (tid < BN) {
                     float *o = lvl1 + (size_t)grp * 3 * BN;
                     o[tid] = n, o[BN + tid] = m, o[2 * BN + tid] = q;
@@ -694,7 +696,7 @@ struct GemmOperands {
 };
 
 template <int EPI>
-static int gemm_launch(GemmParams &p, const GemmOperands &o, cudaStream_t st)
+static int gemm_launch(GemmParams &p, const GemmOperands &o, cudaStream_t st, int *groups_out = nullptr)
 {
     static bool attr_set[kMaxDevices] = {};
     int dev = 0;
@@ -716,6 +718,7 @@ static int gemm_launch(GemmParams &p, const GemmOperands &o, cudaStream_t st)
     p.mtiles = g.mtiles, p.ntiles = g.ntiles, p.stages = g.stages;
     p.sshift = g.stages == 4 ? 2 : 1;
     p.wshift = g.wsub == 64 ? 6 : (g.wsub == 32 ? 5 : 4);
+    if (groups_out) *groups_out = g.groups;
     CUtensorMap tmA, tmB, tmC, tmY;
     if (int rc = make_map(&tmA, o.A, p.M, p.K, o.lda, 128, g.BK)) return rc;
     if (int rc = make_map(&tmB, o.B, o.Nb, p.K, o.ldb, g.BN, g.BK)) return rc;
@@ -759,6 +762,9 @@ PCB_API int64_t pcb_gemm_work_floats(int64_t M, int N, int K)
 // ticket words a statistics GEMM may use: ntiles * (1 + groups) <= this
 PCB_API int pcb_gemm_tickets(void) { return 1024; }
 
+// upper bound of the fold groups of one statistics GEMM (<= 8 CTAs per SM): rows of a deferred `gparts` buffer
+PCB_API int pcb_gemm_max_groups(void) { return (PCB_NUM_SMS * 8 + kFoldGroup - 1) / kFoldGroup; }
+
 // y[M, N] = x[M, K] . w[Nw, K]^T (rows >= Nw of the result are zero columns), bf16
 PCB_API int pcb_linear_rows_bf16(const void *x, int64_t ldx, const void *w, int64_t ldw, int64_t M, int N, int Nw, int K,
                                  void *y, int64_t ldy, pcb_stream_t stream)
@@ -776,7 +782,8 @@ PCB_API int pcb_linear_rows_bf16(const void *x, int64_t ldx, const void *w, int6
 // turns them into the running statistics).  work: pcb_gemm_work_floats floats; tickets: zeroed words.
 PCB_API int pcb_linear_bn_stats_rows_bf16(const void *x, int64_t ldx, const void *w, int64_t ldw, int64_t M, int N, int Nw,
                                           int K, void *y, int64_t ldy, int Cv, float eps, float *mean, float *invstd,
-                                          float *var, float *work, unsigned *tickets, pcb_stream_t stream)
+                                          float *var, float *work, unsigned *tickets, float *gparts, int *groups_out,
+                                          pcb_stream_t stream)
 {
     GemmParams p = {};
     GemmOperands o = {};
@@ -784,10 +791,11 @@ PCB_API int pcb_linear_bn_stats_rows_bf16(const void *x, int64_t ldx, const void
     p.M = M, p.N = N, p.K = K;
     const int rc = gemm_check(p, o);
     if (rc) return rc;
-    PCB_REQUIRE(mean && invstd && var && work && tickets && Cv > 0 && Cv <= N, PCB_EINVAL);
+    PCB_REQUIRE(work && tickets && Cv > 0 && Cv <= N, PCB_EINVAL);
+    PCB_REQUIRE(gparts ? groups_out != nullptr : (mean && invstd && var), PCB_EINVAL);
     p.Cv = Cv, p.eps = eps, p.mean = mean, p.invstd = invstd, p.var = var;
-    p.parts = work, p.tickets = tickets;
-    return gemm_launch<EPI_STATS>(p, o, (cudaStream_t)stream);
+    p.parts = work, p.tickets = tickets, p.gparts = gparts;
+    return gemm_launch<EPI_STATS>(p, o, (cudaStream_t)stream, groups_out);
 }
 
 // data gradient of a layer whose INPUT was z = relu(BN(y)) of the previous layer:
@@ -796,7 +804,8 @@ PCB_API int pcb_linear_bn_stats_rows_bf16(const void *x, int64_t ldx, const void
 PCB_API int pcb_dgrad_bn_rows_bf16(const void *gy, int64_t ldg, const void *wt, int64_t ldwt, int64_t M, int N, int Nw, int K,
                                    const void *yprev, int64_t ldyp, const float *mean, const float *invstd,
                                    const float *gamma, const float *beta, int Cv, int relu, void *dy, int64_t lddy,
-                                   float *sums, float *work, unsigned *tickets, pcb_stream_t stream)
+                                   float *sums, float *work, unsigned *tickets, float *gparts, int *groups_out,
+                                   pcb_stream_t stream)
 {
     GemmParams p = {};
     GemmOperands o = {};
@@ -804,9 +813,10 @@ PCB_API int pcb_dgrad_bn_rows_bf16(const void *gy, int64_t ldg, const void *wt, 
     p.M = M, p.N = N, p.K = K;
     const int rc = gemm_check(p, o);
     if (rc) return rc;
-    PCB_REQUIRE(yprev && mean && invstd && gamma && beta && sums && work && tickets, PCB_EINVAL);
+    PCB_REQUIRE(yprev && mean && invstd && gamma && beta && work && tickets, PCB_EINVAL);
+    PCB_REQUIRE(gparts ? groups_out != nullptr : sums != nullptr, PCB_EINVAL);
     PCB_REQUIRE(Cv > 0 && Cv <= N && ldyp >= N && ldyp % 8 == 0 && al16(yprev), PCB_ERANGE);
     p.Cv = Cv, p.bn_mean = mean, p.bn_invstd = invstd, p.gamma = gamma;
-    p.beta = beta, p.relu = relu, p.sums = sums, p.parts = work, p.tickets = tickets;
-    return gemm_launch<EPI_BNBWD>(p, o, (cudaStream_t)stream);
+    p.beta = beta, p.relu = relu, p.sums = sums, p.parts = work, p.tickets = tickets, p.gparts = gparts;
+    return gemm_launch<EPI_BNBWD>(p, o, (cudaStream_t)stream, groups_out);
 }

@@ -114,6 +114,18 @@ __device__ __forceinline__ float row_sumsq_aten(const float *v, int C, int strid
     return fin;
 }
 
+// Chan's pairwise update of (count, mean, M2): (n, mean, m2) <- (n, mean, m2) + (cn, cm, cq)
+__device__ __forceinline__ void chan_merge(float &n, float &mean, float &m2, float cn, float cm, float cq)
+{
+    const float tot = n + cn;
+    if (tot > 0.f) {
+        const float w = cn / tot, d = cm - mean;
+        mean = fmaf(d, w, mean);
+        m2 = m2 + cq + d * d * n * w;
+        n = tot;
+    }
+}
+
 // Division by a runtime-constant 32-bit divisor in two instructions (mul.hi + shift); the
 // element index -> (row, channel) -> (cloud, ...) decompositions of these kernels were the
 // instruction-issue bottleneck with native 64-bit division (round-1 ncu: 70 % issue, 2 % DRAM).

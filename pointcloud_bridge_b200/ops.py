@@ -7,6 +7,7 @@ device: there is no CPU / eager fallback on this path.
 """
 from __future__ import annotations
 
+import ctypes
 import os
 
 import torch
@@ -989,6 +990,16 @@ def _ru8(n: int) -> int:
     return -(-n // 8) * 8
 
 
+_max_groups = 0
+
+
+def _gemm_max_groups() -> int:
+    global _max_groups
+    if not _max_groups:
+        _max_groups = int(_lib.lib().pcb_gemm_max_groups())
+    return _max_groups
+
+
 def _weight_pair(w: torch.Tensor):
     """(w as bf16 [n8, k8], its transpose [k8, n8]), zero padded: the step runner's shadows, or cast on the spot."""
     w2 = w.flatten(1)
@@ -1158,9 +1169,14 @@ class _MlpRows(torch.autograd.Function):
                     bn.num_batches_tracked.add_(1)
             g32, b32 = params[4 * l + 2].detach().float(), params[4 * l + 3].detach().float()
             bias = params[4 * l + 1]
+            # statistics: the GEMM folds its CTAs' partial (count, mean, M2) triples per group of 32 CTAs and stops;
+            # the elementwise kernel that follows merges the <= 37 groups while it sets up its constants and writes
+            # mean / invstd / var (no second serial fold level at the end of the GEMM)
+            gparts = torch.empty(_gemm_max_groups(), 3, n8, dtype=torch.float32, device=dev)
+            groups = ctypes.c_int(0)
             _call("pcb_linear_bn_stats_rows_bf16", dev, cur.data_ptr(), cur.stride(0), wl.data_ptr(), wl.stride(0), M, n8,
                   min(wl.shape[0], n8), K, y.data_ptr(), y.stride(0), n, float(bn.eps),
-                  stats[0].data_ptr(), stats[1].data_ptr(), stats[2].data_ptr(), work.data_ptr(), tick.data_ptr(),
+                  None, None, None, work.data_ptr(), tick.data_ptr(), gparts.data_ptr(), ctypes.byref(groups),
                   alg_bytes=2 * M * (K + n8) + 2 * wl.numel())
             last = l == L - 1
             pk = pool_k if last else 1
@@ -1172,12 +1188,15 @@ class _MlpRows(torch.autograd.Function):
             if z is None:
                 z = torch.empty(Mo, n8, dtype=torch.bfloat16, device=dev)
             argmax = torch.empty(Mo, n8, dtype=torch.uint8, device=dev) if pk > 1 else None
+            # pooled: the pre-activation of every winning row, all the backward pass needs for its BatchNorm sums
+            ymax = torch.empty(Mo, n8, dtype=torch.bfloat16, device=dev) if pk > 1 else None
             _call("pcb_bn_apply_rows", dev, y.data_ptr(), 1, M, n8, n, pk, stats[0].data_ptr(), stats[1].data_ptr(),
                   g32.data_ptr(), b32.data_ptr(), 1, z.data_ptr(), z.stride(0),
                   argmax.data_ptr() if argmax is not None else None, stats[2].data_ptr(),
                   bias.data_ptr() if bias is not None else None, float(bn.momentum),
                   bn.running_mean.data_ptr() if track else None, bn.running_var.data_ptr() if track else None,
-                  alg_bytes=2 * (M + Mo) * n8 + (Mo * n8 if pk > 1 else 0))
+                  gparts.data_ptr(), int(groups.value), float(bn.eps), ymax.data_ptr() if ymax is not None else None,
+                  alg_bytes=2 * (M + Mo) * n8 + (3 * Mo * n8 if pk > 1 else 0))
             saved += [y, stats, g32, b32, wt]
             if not last:
                 saved.append(z)
@@ -1186,6 +1205,8 @@ class _MlpRows(torch.autograd.Function):
             metas.append((n, n8, K, bias is not None, _step_ctx.grad_view(w) if _step_ctx is not None else None,
                           tuple(w.shape)))
             cur = z
+        if pool_k > 1:
+            saved.append(ymax)
         ctx.save_for_backward(*saved)
         ctx.metas, ctx.pool_k, ctx.M = metas, int(pool_k), M
         return cur
@@ -1210,10 +1231,17 @@ class _MlpRows(torch.autograd.Function):
             gz = gz.contiguous()
         gy = torch.empty_like(y)
         work = _bn_work(n8, dev)
-        _call("pcb_bn_bwd_rows", dev, gz.data_ptr(), gz.stride(0), y.data_ptr(),
-              argmax.data_ptr() if argmax is not None else None, 1, M, n8, n, pool_k, stats[0].data_ptr(),
-              stats[1].data_ptr(), g32.data_ptr(), b32.data_ptr(), 1, work.data_ptr(), gy.data_ptr(),
-              alg_bytes=(2 * y.numel() + gz.numel()) * 2 + (gz.numel() if pool_k > 1 else 0))
+        if pool_k > 1:
+            # two ordinary launches: sums over the M / pool_k winning rows, then gy in one pass over y
+            ymax = sv[1 + 6 * L]
+            _call("pcb_bn_pool_bwd_rows", dev, gz.data_ptr(), gz.stride(0), ymax.data_ptr(), y.data_ptr(), argmax.data_ptr(),
+                  1, M, n8, n, pool_k, stats[0].data_ptr(), stats[1].data_ptr(), g32.data_ptr(), b32.data_ptr(), 1,
+                  work.data_ptr(), gy.data_ptr(), launches=2,
+                  alg_bytes=2 * y.numel() * 2 + gz.numel() * 5 + ymax.numel() * 2)
+        else:
+            _call("pcb_bn_bwd_rows", dev, gz.data_ptr(), gz.stride(0), y.data_ptr(), None, 1, M, n8, n, pool_k,
+                  stats[0].data_ptr(), stats[1].data_ptr(), g32.data_ptr(), b32.data_ptr(), 1, work.data_ptr(),
+                  gy.data_ptr(), alg_bytes=(2 * y.numel() + gz.numel()) * 2)
         sums = work[:3 * n8].view(3, n8)
         for l in range(L - 1, -1, -1):
             n, n8, K, has_bias, gview, wshape = ctx.metas[l]
@@ -1239,12 +1267,16 @@ class _MlpRows(torch.autograd.Function):
                 Kc = min(gy.shape[1], wt.shape[1])
                 work = torch.empty(max(int(lib.pcb_gemm_work_floats(M, np8, Kc)), 1), dtype=torch.float32, device=dev)
                 tick = _tickets(dev)
+                gparts = torch.empty(_gemm_max_groups(), 3, np8, dtype=torch.float32, device=dev)
+                groups = ctypes.c_int(0)
                 _call("pcb_dgrad_bn_rows_bf16", dev, gy.data_ptr(), gy.stride(0), wt.data_ptr(), wt.stride(0), M, np8,
                       min(wt.shape[0], np8), Kc, yp.data_ptr(), yp.stride(0), statsp[0].data_ptr(), statsp[1].data_ptr(),
-                      gp.data_ptr(), bp.data_ptr(), npv, 1, dy.data_ptr(), dy.stride(0), sums.data_ptr(), work.data_ptr(),
-                      tick.data_ptr(), alg_bytes=2 * M * (Kc + 2 * np8) + 2 * wt.numel())
+                      gp.data_ptr(), bp.data_ptr(), npv, 1, dy.data_ptr(), dy.stride(0), None, work.data_ptr(),
+                      tick.data_ptr(), gparts.data_ptr(), ctypes.byref(groups),
+                      alg_bytes=2 * M * (Kc + 2 * np8) + 2 * wt.numel())
                 _call("pcb_bn_bwd_apply_rows", dev, dy.data_ptr(), yp.data_ptr(), 1, M, np8, npv, statsp[0].data_ptr(),
-                      statsp[1].data_ptr(), gp.data_ptr(), sums.data_ptr(), dy.data_ptr(), alg_bytes=6 * M * np8)
+                      statsp[1].data_ptr(), gp.data_ptr(), sums.data_ptr(), dy.data_ptr(), gparts.data_ptr(),
+                      int(groups.value), alg_bytes=6 * M * np8)
                 gy = dy
         gx = None
         if ctx.needs_input_grad[0]:

@@ -56,8 +56,12 @@ def _bn(n, seed):
     return bn
 
 
-@pytest.mark.parametrize("M,K,N", [(1000, 16, 16), (65536, 32, 64), (4173, 104, 200), (1024, 1536, 256), (300, 520, 512)])
-def test_linear_bn_stats_epilogue(M, K, N):
+@pytest.mark.parametrize("deferred", [False, True])
+@pytest.mark.parametrize("M,K,N", [(1000, 16, 16), (65536, 32, 64), (4173, 104, 200), (1024, 1536, 256), (300, 520, 512),
+                                   (524288, 16, 32)])
+def test_linear_bn_stats_epilogue(M, K, N, deferred):
+    """deferred: the GEMM leaves per-group (count, mean, M2) triples, the elementwise kernel merges them."""
+    import ctypes
     lib = _lib.lib()
     g = torch.Generator(device=DEV).manual_seed(7 * M + K)
     Cv = N - 4 if N == 200 else N                        # 196 real channels carried as 200
@@ -75,16 +79,24 @@ def test_linear_bn_stats_epilogue(M, K, N):
         stats = torch.full((3, N), float("nan"), device=DEV)
         work = torch.empty(max(int(lib.pcb_gemm_work_floats(M, N, K)), 1), device=DEV)
         tick = ops._tickets(torch.device(DEV))
+        gparts = torch.full((lib.pcb_gemm_max_groups(), 3, N), float("nan"), device=DEV) if deferred else None
+        groups = ctypes.c_int(0)
         ops._call("pcb_linear_bn_stats_rows_bf16", x.device, x.data_ptr(), x.stride(0), w.data_ptr(), w.stride(0), M, N, N, K,
                   y.data_ptr(), y.stride(0), Cv, 1e-5,
-                  stats[0].data_ptr(), stats[1].data_ptr(), stats[2].data_ptr(), work.data_ptr(), tick.data_ptr())
-        # the elementwise kernel that follows owns the running statistics
+                  None if deferred else stats[0].data_ptr(), None if deferred else stats[1].data_ptr(),
+                  None if deferred else stats[2].data_ptr(), work.data_ptr(), tick.data_ptr(),
+                  gparts.data_ptr() if deferred else None, ctypes.byref(groups))
+        assert 1 <= groups.value <= lib.pcb_gemm_max_groups()
+        # the elementwise kernel that follows owns the running statistics (and, deferred, the final merge)
         z = torch.empty_like(y)
         ones, zeros = torch.ones(Cv, device=DEV), torch.zeros(Cv, device=DEV)
         ops._call("pcb_bn_apply_rows", y.device, y.data_ptr(), 1, M, N, Cv, 1, stats[0].data_ptr(), stats[1].data_ptr(),
                   ones.data_ptr(), zeros.data_ptr(), 1, z.data_ptr(), z.stride(0), None, stats[2].data_ptr(),
-                  bias.data_ptr(), 0.1, rm.data_ptr(), rv.data_ptr())
+                  bias.data_ptr(), 0.1, rm.data_ptr(), rv.data_ptr(), gparts.data_ptr() if deferred else None,
+                  groups.value, 1e-5, None)
         torch.cuda.synchronize()
+        zr = torch.relu((y.float()[:, :Cv] - stats[0, :Cv]) * stats[1, :Cv])
+        assert torch.allclose(z.float()[:, :Cv], zr, rtol=2.0 ** -7, atol=1e-5)
         assert int(tick.abs().sum()) == 0                 # tickets are left zeroed
         outs.append((y, stats, rm, rv))
     y, stats, rm, rv = outs[0]
@@ -102,10 +114,12 @@ def test_linear_bn_stats_epilogue(M, K, N):
     assert torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][0], outs[1][0])
 
 
+@pytest.mark.parametrize("deferred", [False, True])
 @pytest.mark.parametrize("M,K,N,relu", [(1000, 16, 16, 1), (65536, 64, 32, 1), (4173, 256, 200, 1), (300, 512, 520, 1),
                                          (2048, 128, 128, 0)])
-def test_dgrad_bn_epilogue_and_apply(M, K, N, relu):
+def test_dgrad_bn_epilogue_and_apply(M, K, N, relu, deferred):
     """gz = gy . wt^T through the previous layer's BN + ReLU: dy, the two column sums and the final gy."""
+    import ctypes
     lib = _lib.lib()
     g = torch.Generator(device=DEV).manual_seed(3 * M + N)
     Cv = N - 4 if N == 200 else N
@@ -124,10 +138,14 @@ def test_dgrad_bn_epilogue_and_apply(M, K, N, relu):
     sums = torch.full((3, N), float("nan"), device=DEV)
     work = torch.empty(max(int(lib.pcb_gemm_work_floats(M, N, K)), 1), device=DEV)
     tick = ops._tickets(torch.device(DEV))
+    gparts = torch.full((lib.pcb_gemm_max_groups(), 3, N), float("nan"), device=DEV) if deferred else None
+    groups = ctypes.c_int(0)
     ops._call("pcb_dgrad_bn_rows_bf16", gy.device, gy.data_ptr(), gy.stride(0), wt.data_ptr(), wt.stride(0), M, N, N, K,
               yprev.data_ptr(), yprev.stride(0), mean.data_ptr(), invstd.data_ptr(), gamma.data_ptr(), beta.data_ptr(), Cv,
-              relu, dy.data_ptr(), dy.stride(0), sums.data_ptr(), work.data_ptr(), tick.data_ptr())
+              relu, dy.data_ptr(), dy.stride(0), None if deferred else sums.data_ptr(), work.data_ptr(), tick.data_ptr(),
+              gparts.data_ptr() if deferred else None, ctypes.byref(groups))
     torch.cuda.synchronize()
+    assert int(tick.abs().sum()) == 0
     gz = gy.float() @ wt.float().t()
     yh = (yf - mean) * invstd
     z = yh * gamma + beta
@@ -141,15 +159,17 @@ def test_dgrad_bn_epilogue_and_apply(M, K, N, relu):
     tol = ref_dy.abs() * 2.0 ** -7 + 1e-5 * float(gz.abs().max())
     assert not (((d - ref_dy).abs() > tol) & ~edge).any()
     dq = d[:, :Cv]
+    # elementwise half, in place (deferred: it also adds up the group partials into `sums`)
+    out = dy.clone()
+    ops._call("pcb_bn_bwd_apply_rows", gy.device, out.data_ptr(), yprev.data_ptr(), 1, M, N, Cv, mean.data_ptr(),
+              invstd.data_ptr(), gamma.data_ptr(), sums.data_ptr(), out.data_ptr(), gparts.data_ptr() if deferred else None,
+              groups.value)
+    torch.cuda.synchronize()
     assert torch.allclose(sums[0, :Cv], dq.sum(0), rtol=1e-4, atol=1e-4 * float(dq.abs().sum(0).max()))
     assert torch.allclose(sums[1, :Cv], (dq * yh).sum(0), rtol=1e-4, atol=1e-4 * float((dq * yh).abs().sum(0).max()))
     assert float(sums[2].abs().max()) == 0.0
     if Cv < N:
         assert float(sums[:, Cv:].abs().max()) == 0.0 and float(d[:, Cv:].abs().max()) == 0.0
-    # elementwise half, in place
-    out = dy.clone()
-    ops._call("pcb_bn_bwd_apply_rows", gy.device, out.data_ptr(), yprev.data_ptr(), 1, M, N, Cv, mean.data_ptr(),
-              invstd.data_ptr(), gamma.data_ptr(), sums.data_ptr(), out.data_ptr())
     ref = gamma * invstd * (dq - sums[0, :Cv] / M - yh * sums[1, :Cv] / M)
     o = out.float()
     assert torch.allclose(o[:, :Cv], ref, rtol=2.0 ** -7, atol=2.0 ** -8 * float(ref.abs().max()))
@@ -157,7 +177,9 @@ def test_dgrad_bn_epilogue_and_apply(M, K, N, relu):
         assert float(o[:, Cv:].abs().max()) == 0.0
 
 
-@pytest.mark.parametrize("M,C,Cv,pool_k", [(4096, 64, 64, 1), (8192, 200, 196, 32), (1024, 512, 512, 16), (300, 8, 5, 1)])
+@pytest.mark.parametrize("M,C,Cv,pool_k", [(4096, 64, 64, 1), (8192, 200, 196, 32), (1024, 512, 512, 16), (300, 8, 5, 1),
+                                            (4096, 512, 512, 32), (16384, 256, 256, 16), (2 * 20 * 3, 32, 32, 20),
+                                            (65536, 32, 32, 16), (33 * 7, 16, 12, 33), (128 * 128, 128, 128, 128)])
 def test_bn_apply_rows(M, C, Cv, pool_k):
     g = torch.Generator(device=DEV).manual_seed(M + C)
     y = torch.zeros(M, C, device=DEV)
@@ -170,12 +192,50 @@ def test_bn_apply_rows(M, C, Cv, pool_k):
     wide = torch.full((M // pool_k, C + 16), 7.0, device=DEV, dtype=torch.bfloat16)
     out = wide[:, 8:8 + C]
     am = torch.empty(M // pool_k, C, device=DEV, dtype=torch.uint8) if pool_k > 1 else None
+    ymax = torch.full((M // pool_k, C), 3.0, device=DEV, dtype=torch.bfloat16) if pool_k > 1 else None
     ops._call("pcb_bn_apply_rows", y.device, y.data_ptr(), 1, M, C, Cv, pool_k, mean.data_ptr(), invstd.data_ptr(),
               gamma.data_ptr(), beta.data_ptr(), 1, out.data_ptr(), out.stride(0), am.data_ptr() if am is not None else None,
-              None, None, 0.0, None, None)
-    z = torch.relu((y.float()[:, :Cv] - mean[:Cv]) * invstd[:Cv] * gamma + beta)
+              None, None, 0.0, None, None, None, 0, 1e-5, ymax.data_ptr() if ymax is not None else None)
+    zfull = torch.relu((y.float()[:, :Cv] - mean[:Cv]) * invstd[:Cv] * gamma + beta)
+    z = zfull
     if pool_k > 1:
-        z, idx = z.view(-1, pool_k, Cv).max(dim=1)
+        z, idx = zfull.view(-1, pool_k, Cv).max(dim=1)
+        # the recorded argmax points at a row holding the maximum and is the FIRST such row (torch.max's tie rule on
+        # the kernel's own values: ReLU produces many exact ties at 0)
+        a = am[:, :Cv].long()
+        zk = torch.relu(torch.addcmul((beta - mean[:Cv] * (invstd[:Cv] * gamma)), y.float()[:, :Cv], invstd[:Cv] * gamma))
+        zk = zk.view(-1, pool_k, Cv)
+        picked = zk.gather(1, a[:, None, :]).squeeze(1)
+        assert torch.equal(picked, zk.max(dim=1)[0])
+        first = (zk == zk.max(dim=1, keepdim=True)[0]).float().argmax(dim=1)
+        assert torch.equal(a, first)
+        # ymax: the stored pre-activation of the winning row, bit for bit
+        yw = y[:, :Cv].reshape(-1, pool_k, Cv).gather(1, a[:, None, :]).squeeze(1)
+        assert torch.equal(ymax[:, :Cv], yw)
+        # backward of the pooled layer in two ordinary launches == the cooperative kernel up to summation order
+        lib = _lib.lib()
+        gz_w = torch.randn(M // pool_k, C + 8, device=DEV, generator=g).to(torch.bfloat16)
+        gz = gz_w[:, :C]
+        gam, bet = torch.zeros(C, device=DEV), torch.zeros(C, device=DEV)
+        gam[:Cv], bet[:Cv] = gamma, beta
+        res = []
+        for entry in ("pcb_bn_bwd_rows", "pcb_bn_pool_bwd_rows"):
+            work = torch.full((int(lib.pcb_bn_work_floats(C)),), float("nan"), device=DEV)
+            gy = torch.full_like(y, 5.0)
+            if entry == "pcb_bn_bwd_rows":
+                ops._call(entry, y.device, gz.data_ptr(), gz.stride(0), y.data_ptr(), am.data_ptr(), 1, M, C, Cv, pool_k,
+                          mean.data_ptr(), invstd.data_ptr(), gam.data_ptr(), bet.data_ptr(), 1, work.data_ptr(), gy.data_ptr())
+            else:
+                ops._call(entry, y.device, gz.data_ptr(), gz.stride(0), ymax.data_ptr(), y.data_ptr(), am.data_ptr(), 1, M, C,
+                          Cv, pool_k, mean.data_ptr(), invstd.data_ptr(), gam.data_ptr(), bet.data_ptr(), 1, work.data_ptr(),
+                          gy.data_ptr())
+            torch.cuda.synchronize()
+            res.append((work[:3 * C].view(3, C).clone(), gy.float()))
+        (s_a, gy_a), (s_b, gy_b) = res
+        scale = float(s_a[:2, :Cv].abs().max()) + 1e-6
+        assert torch.allclose(s_a[:2, :Cv], s_b[:2, :Cv], rtol=1e-4, atol=1e-5 * scale)
+        assert float(s_b[2].abs().max()) == 0.0 and float(s_b[:, Cv:].abs().max() if Cv < C else 0.0) == 0.0
+        assert torch.allclose(gy_a, gy_b, rtol=2.0 ** -7, atol=2.0 ** -8 * float(gy_a.abs().max()) + 1e-6)
     o = out.float()
     assert torch.allclose(o[:, :Cv], z, rtol=2.0 ** -7, atol=1e-6)
     assert float(o[:, Cv:].abs().max()) == 0.0 if Cv < C else True

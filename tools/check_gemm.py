@@ -55,7 +55,8 @@ for M, K, N in SHAPES:
         work = torch.empty(max(int(lib.pcb_gemm_work_floats(M, N, K)), 1), device=dev)
         tick = ops._tickets(dev)
         ops._call("pcb_linear_bn_stats_rows_bf16", dev, x.data_ptr(), K, w.data_ptr(), K, M, N, N, K, y.data_ptr(), N, N,
-                  1e-5, stats[0].data_ptr(), stats[1].data_ptr(), stats[2].data_ptr(), work.data_ptr(), tick.data_ptr())
+                  1e-5, stats[0].data_ptr(), stats[1].data_ptr(), stats[2].data_ptr(), work.data_ptr(), tick.data_ptr(),
+                  None, None)
         torch.cuda.synchronize()
         ok = diagnose(y, ref, "stats-y")
         yf = y.float()
@@ -81,7 +82,7 @@ for M, K, N in SHAPES:
         tick = ops._tickets(dev)
         ops._call("pcb_dgrad_bn_rows_bf16", dev, x.data_ptr(), K, w.data_ptr(), K, M, N, N, K, yprev.data_ptr(), N,
                   mean.data_ptr(), invstd.data_ptr(), gamma.data_ptr(), beta.data_ptr(), N, 1, dy.data_ptr(), N,
-                  sums.data_ptr(), work.data_ptr(), tick.data_ptr())
+                  sums.data_ptr(), work.data_ptr(), tick.data_ptr(), None, None)
         torch.cuda.synchronize()
         yh = (yf - mean) * invstd
         z = yh * gamma + beta

@@ -1,5 +1,6 @@
 """Per-layer timing of the tcgen05 training GEMMs (csrc/gemm_rows.cu) on the layer shapes of the MSG train step
 (B = 16), next to torch.mm (cuBLAS) on the same operands.  CUDA events over `reps` back-to-back launches."""
+import ctypes
 import os
 import sys
 
@@ -67,9 +68,15 @@ for name, M, K, N in LAYERS:
     work = torch.empty(max(int(lib.pcb_gemm_work_floats(M, N, K)), 1), device=dev)
     tick = ops._tickets(dev)
     t_plain = timed(lambda: ops.gemm_rows(x, w, N, out=y))
+    # as the training path runs it: the GEMM stops after its first fold level (group partials), the elementwise kernel
+    # that follows merges the groups (PCB_GEMM_FULL_FOLD=1: the GEMM folds to the end itself)
+    full = os.environ.get("PCB_GEMM_FULL_FOLD", "0") == "1"
+    gparts = torch.empty(lib.pcb_gemm_max_groups(), 3, N, device=dev)
+    groups = ctypes.c_int(0)
     t_stats = timed(lambda: ops._call("pcb_linear_bn_stats_rows_bf16", dev, x.data_ptr(), K, w.data_ptr(), K, M, N, N, K,
                                       y.data_ptr(), N, N, 1e-5, stats[0].data_ptr(), stats[1].data_ptr(),
-                                      stats[2].data_ptr(), work.data_ptr(), tick.data_ptr()))
+                                      stats[2].data_ptr(), work.data_ptr(), tick.data_ptr(),
+                                      None if full else gparts.data_ptr(), ctypes.byref(groups)))
     t_mm = timed(lambda: torch.mm(x, w.t(), out=y))
     # data gradient of this layer through the previous layer's BN: gz [M, K] = gy [M, N] . W; y_prev [M, K]
     t_dg = t_mmd = float("nan")
@@ -81,10 +88,11 @@ for name, M, K, N in LAYERS:
         gamma, beta = torch.ones(K, device=dev), torch.zeros(K, device=dev)
         sums = torch.empty(3, K, device=dev)
         work2 = torch.empty(max(int(lib.pcb_gemm_work_floats(M, K, N)), 1), device=dev)
+        gparts2 = torch.empty(lib.pcb_gemm_max_groups(), 3, K, device=dev)
         t_dg = timed(lambda: ops._call("pcb_dgrad_bn_rows_bf16", dev, gy.data_ptr(), N, wt.data_ptr(), N, M, K, K, N,
                                        yprev.data_ptr(), K, mean.data_ptr(), invstd.data_ptr(), gamma.data_ptr(),
                                        beta.data_ptr(), K, 1, dy.data_ptr(), K, sums.data_ptr(), work2.data_ptr(),
-                                       tick.data_ptr()))
+                                       tick.data_ptr(), None if full else gparts2.data_ptr(), ctypes.byref(groups)))
         t_mmd = timed(lambda: torch.mm(gy, w, out=dy))
     gbs = 2 * M * (K + N) / t_stats / 1e3
     print("%-11s %8d %5d %5d | %8.1f %8.1f %8.1f | %8.0f %8.3f | %8.1f %8.1f" % (name, M, K, N, t_plain, t_stats, t_mm, gbs,
