@@ -821,6 +821,8 @@ template <typename T, int V>
 __global__ void __launch_bounds__(kBnThreads)
 bn_apply_rows_kernel(const BnFwdArgs a)
 {
+    pdl_wait();
+    pdl_trigger();
     const int C = a.C;
     __shared__ float s_buf[2][kBnThreads][V];
     float *s_const = nullptr;
@@ -857,6 +859,8 @@ template <typename T, int V>
 __global__ void __launch_bounds__(kBnThreads)
 bn_apply_pooled_kernel(const BnFwdArgs a)
 {
+    pdl_wait();
+    pdl_trigger();
     constexpr int KB = 8;
     const int C = a.C;
     __shared__ float s_const[2 * kBnThreads * V];
@@ -992,6 +996,8 @@ template <typename T, int V>
 __global__ void __launch_bounds__(kBnThreads)
 bn_bwd_apply_rows_kernel(const BnBwdApplyArgs a)
 {
+    pdl_wait();
+    pdl_trigger();
     const int C = a.C;
     __shared__ float s_const[5 * kBnApplyMaxC];
     const float invM = 1.f / (float)a.M;
@@ -1039,6 +1045,8 @@ template <typename T, int V>
 __global__ void __launch_bounds__(kBnThreads)
 bn_pool_sums_kernel(const BnPoolSumArgs a)
 {
+    pdl_wait();
+    pdl_trigger();
     const int C = a.C;
     const Lanes L(C, V);
     __shared__ float s_acc[2][kBnThreads][V];
@@ -1112,6 +1120,8 @@ template <typename T, int V>
 __global__ void __launch_bounds__(kBnThreads)
 bn_pool_bwd_apply_kernel(const BnPoolBwdArgs p)
 {
+    pdl_wait();
+    pdl_trigger();
     const BnBwdArgs &a = p.b;
     const int C = a.C;
     __shared__ float s_const[6 * kBnApplyMaxC];
@@ -1181,7 +1191,7 @@ static void bn_apply_launch(const BnFwdArgs &a, int64_t units, cudaStream_t st)
 {
     static int occ[kMaxDevices] = {};
     const int cap = resident_ctas(bn_apply_rows_kernel<T, V>, occ);
-    bn_apply_rows_kernel<T, V><<<stream_grid(units, a.C, V, cap), kBnThreads, 0, st>>>(a);
+    launch_pdl(bn_apply_rows_kernel<T, V>, dim3(stream_grid(units, a.C, V, cap)), dim3(kBnThreads), 0, st, a);
 }
 
 template <typename T, int V>
@@ -1195,7 +1205,16 @@ static void bn_apply_pooled_launch(BnFwdArgs a, int64_t units, cudaStream_t st)
     while (rs > TY) rs >>= 1;
     a.rs = rs;
     const int64_t want = ceil_div(units, TY / rs);
-    bn_apply_pooled_kernel<T, V><<<(int)(want < cap ? want : cap), kBnThreads, 0, st>>>(a);
+    launch_pdl(bn_apply_pooled_kernel<T, V>, dim3((unsigned)(want < cap ? want : cap)), dim3(kBnThreads), 0, st, a);
+}
+
+template <typename T, int V>
+static void bn_pool_bwd_launch(const BnPoolSumArgs &sa, const BnPoolBwdArgs &pa, int sgrid, int64_t units, cudaStream_t st)
+{
+    static int occ[kMaxDevices] = {};
+    launch_pdl(bn_pool_sums_kernel<T, V>, dim3((unsigned)sgrid), dim3(kBnThreads), 0, st, sa);
+    const int cap = resident_ctas(bn_pool_bwd_apply_kernel<T, V>, occ);
+    launch_pdl(bn_pool_bwd_apply_kernel<T, V>, dim3(stream_grid(units * 4, pa.b.C, V, cap)), dim3(kBnThreads), 0, st, pa);
 }
 
 template <typename T, int V>
@@ -1203,7 +1222,7 @@ static void bn_bwd_apply_launch(const BnBwdApplyArgs &a, cudaStream_t st)
 {
     static int occ[kMaxDevices] = {};
     const int cap = resident_ctas(bn_bwd_apply_rows_kernel<T, V>, occ);
-    bn_bwd_apply_rows_kernel<T, V><<<stream_grid(a.M, a.C, V, cap), kBnThreads, 0, st>>>(a);
+    launch_pdl(bn_bwd_apply_rows_kernel<T, V>, dim3(stream_grid(a.M, a.C, V, cap)), dim3(kBnThreads), 0, st, a);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1454,21 +1473,8 @@ PCB_API int pcb_bn_pool_bwd_rows(const void *gz, int64_t gz_pitch, const void *y
     a.rs = pool_row_slices(groups, C / V, pool_k, 4);
     pa.gparts = sa.gparts, pa.groups = (int)sgrid;
     const int64_t units = groups * a.rs;
-    if (!dtype) {
-        static int occ[kMaxDevices] = {};
-        bn_pool_sums_kernel<float, 4><<<(int)sgrid, kBnThreads, 0, st>>>(sa);
-        const int cap = resident_ctas(bn_pool_bwd_apply_kernel<float, 4>, occ);
-        bn_pool_bwd_apply_kernel<float, 4><<<stream_grid(units * 4, C, 4, cap), kBnThreads, 0, st>>>(pa);
-    } else if (v8) {
-        static int occ[kMaxDevices] = {};
-        bn_pool_sums_kernel<__nv_bfloat16, 8><<<(int)sgrid, kBnThreads, 0, st>>>(sa);
-        const int cap = resident_ctas(bn_pool_bwd_apply_kernel<__nv_bfloat16, 8>, occ);
-        bn_pool_bwd_apply_kernel<__nv_bfloat16, 8><<<stream_grid(units * 4, C, 8, cap), kBnThreads, 0, st>>>(pa);
-    } else {
-        static int occ[kMaxDevices] = {};
-        bn_pool_sums_kernel<__nv_bfloat16, 4><<<(int)sgrid, kBnThreads, 0, st>>>(sa);
-        const int cap = resident_ctas(bn_pool_bwd_apply_kernel<__nv_bfloat16, 4>, occ);
-        bn_pool_bwd_apply_kernel<__nv_bfloat16, 4><<<stream_grid(units * 4, C, 4, cap), kBnThreads, 0, st>>>(pa);
-    }
+    if (!dtype) bn_pool_bwd_launch<float, 4>(sa, pa, (int)sgrid, units, st);
+    else if (v8) bn_pool_bwd_launch<__nv_bfloat16, 8>(sa, pa, (int)sgrid, units, st);
+    else bn_pool_bwd_launch<__nv_bfloat16, 4>(sa, pa, (int)sgrid, units, st);
     PCB_RETURN_LAUNCH_STATUS();
 }

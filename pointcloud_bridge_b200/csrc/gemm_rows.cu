@@ -281,6 +281,13 @@ gemm_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (EPI == EPI_BNBWD) tma_prefetch_desc(&tmY);
     }
     if (warp == 0) tmem_alloc(smem_u32(&s_tmem), (uint32_t)tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    // everything above is CTA-local (barriers, TMEM columns, descriptor prefetch): it may overlap the predecessor's
+    // tail.  From here on the kernel reads global memory; its own successor may start its prologue now.
+    pdl_wait();
+    pdl_trigger();
     if (EPI == EPI_BNBWD) {
         for (int c = tid; c < BN; c += kGemmThreads) {
             const int gc = n0 + c;
@@ -293,9 +300,7 @@ gemm_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             s_const[3 * BN + c] = real ? p.beta[gc] - m * sc : 0.f;
         }
     }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
+    if (EPI == EPI_BNBWD) __syncthreads();
     const uint32_t tmem_base = s_tmem;
     const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
     const uint32_t idesc = umma_idesc_bf16_m128(BN);
@@ -728,8 +733,8 @@ static int gemm_launch(GemmParams &p, const GemmOperands &o, cudaStream_t st, in
     } else {
         tmY = tmC;
     }
-    gemm_rows_kernel<EPI><<<dim3((unsigned)g.grid_x, (unsigned)g.ntiles), kGemmThreads, g.smem, st>>>(tmA, tmB, tmC, tmY, p);
-    PCB_RETURN_LAUNCH_STATUS();
+    return (int)launch_pdl(gemm_rows_kernel<EPI>, dim3((unsigned)g.grid_x, (unsigned)g.ntiles), dim3(kGemmThreads), g.smem, st,
+                           tmA, tmB, tmC, tmY, p);
 }
 
 static inline bool al16(const void *q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; }

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../../include/pcbridge.h"
 
@@ -35,6 +36,39 @@ static inline cudaError_t smem_optin_once(K kernel, int bytes, bool (&flags)[kMa
 }
 
 __host__ __device__ __forceinline__ int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ---- programmatic dependent launch (PDL) -------------------------------------------------------------------------
+// The training step is ~250 dependent kernels of 5-30 us: the launch latency between two of them and the prologue of
+// the second (barrier init, TMEM allocation, descriptor prefetch, per-channel constants) are a measurable part of it.
+// Kernels launched through launch_pdl() may start while their predecessor in the stream is still draining:
+//   * pdl_wait() blocks until the PREVIOUS kernel has completed and its writes are visible -- it comes before the
+//     first access to global memory (everything before it is CTA-local setup);
+//   * pdl_trigger(), always AFTER pdl_wait(), lets the NEXT kernel's CTAs be scheduled once every CTA of this one
+//     has passed its own wait (they take the SM slots that this kernel's tail leaves idle and run their prologue).
+//     Wait-then-trigger keeps the overlap one kernel deep: when a kernel's prologue runs, everything before its
+//     immediate predecessor has completed.
+// Without the launch attribute (ordinary launch, PCB_NO_PDL=1) both are no-ops and the stream order is the usual one.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+static inline bool pdl_enabled()
+{
+    static const bool on = [] { const char *e = getenv("PCB_NO_PDL"); return !(e && e[0] == '1'); }();
+    return on;
+}
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                     Args &&...args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = attr, cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 // |p|^2 exactly as ATen's CPU sum(v**2, -1) evaluates it for three components:
 // (x*x + y*y) + z*z, every operation rounded, no FMA.

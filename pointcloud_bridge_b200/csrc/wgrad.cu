@@ -62,6 +62,8 @@ wgrad_rows_kernel(const __nv_bfloat16 *__restrict__ gy, const __nv_bfloat16 *__r
                   int ldgy, int ldx, int tiles_k, int64_t rows_per_split, float *__restrict__ gw, int ldw)
 {
     extern __shared__ __align__(128) unsigned char smem[];
+    pdl_wait();
+    pdl_trigger();
     const int tile = blockIdx.x;
     const int n0 = (tile / tiles_k) * kWgTile, k0 = (tile % tiles_k) * kWgTile;
     const int64_t rbeg = (int64_t)blockIdx.y * rows_per_split;
@@ -205,7 +207,6 @@ PCB_API int pcb_wgrad_rows_bf16(const void *gy, const void *x, int64_t M, int N,
     static bool attr_set[kMaxDevices] = {};
     if (cudaError_t e = smem_optin_once(wgrad_rows_kernel, (int)smem, attr_set)) return (int)e;
     dim3 grid((unsigned)tiles, (unsigned)splits);
-    wgrad_rows_kernel<<<grid, kWgThreads, smem, (cudaStream_t)stream>>>(
-        (const __nv_bfloat16 *)gy, (const __nv_bfloat16 *)x, M, N, K, ldgy, ldx, tiles_k, rows_per_split, gw, ldw);
-    PCB_RETURN_LAUNCH_STATUS();
+    return (int)launch_pdl(wgrad_rows_kernel, grid, dim3(kWgThreads), smem, (cudaStream_t)stream, (const __nv_bfloat16 *)gy,
+                           (const __nv_bfloat16 *)x, M, N, K, ldgy, ldx, tiles_k, rows_per_split, gw, ldw);
 }

@@ -183,6 +183,11 @@ class Trainer:
         # batch trains -- and the captured step contains no farthest point sampling, ball query or three-NN at all.
         self._use_chain = hasattr(net, "index_chain") and os.environ.get("PCB_NO_INDEX_PREFETCH", "0") != "1"
         self._static_pre = None
+        # the index chain of the next batch starts when the running step reaches its small middle layers
+        # (ops.mark_mid_step); an external event, so that a captured step records it on every replay
+        self._mid_event = torch.cuda.Event(external=True) \
+            if self._use_chain and os.environ.get("PCB_MID_STEP_CHAIN", "1") != "0" else None
+        self._mid_armed = False
 
     @torch.no_grad()
     def last_pred(self, class_dim: int = 1) -> torch.Tensor:
@@ -218,6 +223,13 @@ class Trainer:
     def _fwd_bwd(self, inputs, labels, loss_inputs, pre=None):
         self.bucket.zero()
         kw = {} if pre is None else {"pre": pre}
+        ops.set_mid_step_event(self._mid_event)
+        try:
+            return self._fwd_bwd_marked(inputs, labels, loss_inputs, kw)
+        finally:
+            ops.set_mid_step_event(None)
+
+    def _fwd_bwd_marked(self, inputs, labels, loss_inputs, kw):
         with self._ctx:
             self._ctx.counters.append(self.opt.step_t)      # advanced with the BN counters in one multi-tensor add
             if self.loss_fn is None:       # plain mean NLL: the heads hand their logits rows to the loss kernel
@@ -311,7 +323,10 @@ class Trainer:
         with torch.cuda.stream(self._pf_stream):
             for b, t in zip(self._pf_bufs, srcs):
                 b.copy_(t, non_blocking=True)
-            # sampling / grouping indices of that batch, on the same side stream: they overlap the running step
+            # sampling / grouping indices of that batch, on the same side stream: they overlap the running step, from
+            # the point where its small middle layers begin (the input copies above start right away)
+            if self._mid_event is not None and self._mid_armed and self._use_chain:
+                self._pf_stream.wait_event(self._mid_event)
             self._pf_pre = self.net.index_chain(self._pf_bufs[0]) if self._use_chain else None
             self._pf_ready = torch.cuda.Event()
             self._pf_ready.record(self._pf_stream)
@@ -330,6 +345,7 @@ class Trainer:
                 t.record_stream(main)
         self._mark_consumed = True
         loss = self.step(*bufs[:ni], labels=bufs[ni], loss_inputs=tuple(bufs[ni + 1:ni + 1 + nl]), pre=pre)
+        self._mid_armed = True              # a step is in flight: its mid-step marker will be recorded
         if self._mark_consumed:             # eager step: the staging buffers were read throughout
             self._note_consumed()
         return loss

@@ -71,6 +71,26 @@ def _call(name: str, dev: torch.device, *args, launches: int = 1, alg_bytes: int
     _lib.count_launches(launches)
 
 
+# Mid-step marker.  A step runner that computes the sampling / grouping indices of the NEXT batch on a side stream
+# (engine.Trainer.prefetch) wants that chain -- farthest point sampling: 16 persistent CTAs for a third of a
+# millisecond -- to run while the CURRENT step is in its small middle layers (a few dozen to a few hundred CTAs per
+# kernel, SMs idle), not while the first set-abstraction levels stream hundreds of MB with every SM busy: there every
+# persistent grid sized for 148 SMs gets a ragged second wave (+0.4 ms per step, tools/step_timing.py).  The
+# networks call mark_mid_step() where their small layers begin; the runner registers an event (an EXTERNAL event, so
+# that a captured step records it on every replay) and makes the side stream wait for it.
+_mid_step_event = None
+
+
+def set_mid_step_event(ev) -> None:
+    global _mid_step_event
+    _mid_step_event = ev
+
+
+def mark_mid_step() -> None:
+    if _mid_step_event is not None:
+        _mid_step_event.record()
+
+
 # Source of the FPS start indices.  None: the reference's own draw, torch.randint on the CPU
 # default generator followed by a host->device copy (pointnet_util.py:79).  A callable
 # (B, N, device) -> LongTensor[B] lets a CUDA-graph runner substitute static device buffers that
@@ -907,6 +927,7 @@ class StepContext:
     def __enter__(self):
         global _step_ctx
         self.counters = []
+        self.side_streams = set()
         if not self.external_refresh:
             self.refresh_shadows()
         _step_ctx = self
@@ -915,6 +936,9 @@ class StepContext:
     def __exit__(self, *exc):
         global _step_ctx
         _step_ctx = None
+        for st in self.side_streams:                      # weight gradients launched next to the backward chain
+            torch.cuda.current_stream().wait_stream(st)
+        self.side_streams = set()
         if self.counters:
             torch._foreach_add_(self.counters, 1)
         return False
@@ -946,6 +970,24 @@ def wgrad_rows_supported(gy, x) -> bool:
             and gy.data_ptr() % 16 == 0 and x.data_ptr() % 16 == 0)
 
 
+# The weight gradient of a layer is a leaf of the backward pass: nothing reads it before the optimizer.  Inside a step
+# runner (StepContext) it is launched on a side stream right after the gradient rows it contracts exist, so it runs
+# next to the data-gradient chain of the layers below instead of in front of it (the kernels of this step are 5-30 us
+# each and mostly latency-bound: two of them share the SMs almost for free); the step joins the side stream before
+# the gradients are packed (StepContext.__exit__).  In a captured step this is a fork / join of the graph.
+_WGRAD_SIDE = os.environ.get("PCB_NO_WGRAD_SIDE_STREAM", "0") != "1"
+_wgrad_streams: dict[int, torch.cuda.Stream] = {}
+
+
+def _wgrad_stream(dev: torch.device) -> torch.cuda.Stream:
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    st = _wgrad_streams.get(key)
+    if st is None:
+        st = torch.cuda.Stream(device=dev)
+        _wgrad_streams[key] = st
+    return st
+
+
 @torch.no_grad()
 def wgrad_rows(gy, x, k: int | None = None, out: torch.Tensor | None = None, n: int | None = None) -> torch.Tensor:
     """gy [M,Np][:, :n]^T @ x [M,Kp][:, :k] in fp32 (bf16 operands, rows = the long contraction dimension;
@@ -953,21 +995,33 @@ def wgrad_rows(gy, x, k: int | None = None, out: torch.Tensor | None = None, n: 
     M = gy.shape[0]
     n = gy.shape[1] if n is None else n
     k = x.shape[1] if k is None else k
+    side = None
     if out is None:
         out = torch.zeros(n, k, dtype=torch.float32, device=gy.device)
-    _call("pcb_wgrad_rows_bf16", gy.device, gy.data_ptr(), x.data_ptr(), M, n, k, gy.shape[1], x.shape[1],
-          out.data_ptr(), out.stride(0), alg_bytes=2 * M * (gy.shape[1] + x.shape[1]) + 4 * n * k)
+    elif _WGRAD_SIDE and _step_ctx is not None and _timer is None:
+        side = _wgrad_stream(gy.device)
+    args = ("pcb_wgrad_rows_bf16", gy.device, gy.data_ptr(), x.data_ptr(), M, n, k, gy.shape[1], x.shape[1],
+            out.data_ptr(), out.stride(0))
+    nbytes = 2 * M * (gy.shape[1] + x.shape[1]) + 4 * n * k
+    if side is None:
+        _call(*args, alg_bytes=nbytes)
+        return out
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        _call(*args, alg_bytes=nbytes)
+    gy.record_stream(side)                                # the caching allocator must not hand these rows out again
+    x.record_stream(side)                                 # before the side stream has read them
+    _step_ctx.side_streams.add(side)
     return out
 
 
 # ---------------------------------------------------------------------------------------------
 # tensor-core GEMMs on rows (csrc/gemm_rows.cu): tcgen05.mma, fp32 accumulation in TMEM, BatchNorm sums in the epilogue
 # ---------------------------------------------------------------------------------------------
-# PCB_OWN_GEMM=1 routes the training MLPs through the tcgen05 GEMMs of csrc/gemm_rows.cu (BatchNorm sums in the epilogue).
-# Round-2 measurements (profiles/r2_gemm_rows.md): correct on every layer shape, but 2.5-3x slower than the library GEMM on
-# these memory-bound, few-hundred-flop-per-byte shapes (per-tile instruction overhead of the epilogue), so the default
-# stays the library GEMM + cooperative BN row kernels until the kernel is at parity.
-_OWN_GEMM = os.environ.get("PCB_OWN_GEMM", "0") == "1"
+# The training MLPs run on the tcgen05 GEMMs of csrc/gemm_rows.cu (BatchNorm sums in the epilogue); PCB_OWN_GEMM=0 selects
+# the round-1 composition (library GEMM + cooperative BN row kernels), kept as the yardstick of tests/test_gpu_gemm_rows.py
+# and for fp32 parity runs.  Measurements: profiles/r2_gemm_rows.md.
+_OWN_GEMM = os.environ.get("PCB_OWN_GEMM", "1") == "1"
 _ticket_pool: dict[int, list] = {}
 
 

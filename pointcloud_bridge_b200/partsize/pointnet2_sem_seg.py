@@ -35,6 +35,7 @@ class get_model(nn.Module):
         l0_points, l0_xyz = xyz, xyz[:, :3, :]
         l1_xyz, l1_points = self.sa1(l0_xyz, l0_points, sa[0])
         l2_xyz, l2_points = self.sa2(l1_xyz, l1_points, sa[1])
+        ops.mark_mid_step()                                  # the small layers begin (engine.Trainer.prefetch)
         l3_xyz, l3_points = self.sa3(l2_xyz, l2_points, sa[2])
         l4_xyz, l4_points = self.sa4(l3_xyz, l3_points, sa[3])
         l3_points = self.fp4(l3_xyz, l4_xyz, l3_points, l4_points, fp[0])
