@@ -18,6 +18,8 @@ adam_flat_kernel(float *__restrict__ p, const float *__restrict__ g, float *__re
                  const int64_t *__restrict__ step_ptr, const int *__restrict__ shadow_index,
                  const int *__restrict__ shadow_index_t, __nv_bfloat16 *__restrict__ shadow)
 {
+    pdl_wait();
+    pdl_trigger();
     const float step = (float)step_ptr[0];
     const float lr = lr_ptr[0];
     const float bc1 = 1.f - powf(beta1, step);
@@ -57,7 +59,7 @@ PCB_API int pcb_adam_flat_f32(float *param, const float *grad, float *exp_avg, f
     int64_t blocks = ceil_div(n, 256);
     const int64_t cap = (int64_t)PCB_NUM_SMS * 16;
     if (blocks > cap) blocks = cap;
-    adam_flat_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2,
+    launch_pdl(adam_flat_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2,
                                                                         eps, weight_decay, step, shadow_index,
                                                                         shadow_index_t, (__nv_bfloat16 *)shadow_bf16);
     PCB_RETURN_LAUNCH_STATUS();

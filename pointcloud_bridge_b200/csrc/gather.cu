@@ -230,6 +230,8 @@ group_points_chunk_kernel(const float *__restrict__ xyz, const PT *__restrict__ 
                           FastDiv dK, FastDiv dS, int xyz_first, int points_cf, int clamp, int vec_ok, unsigned RG,
                           unsigned rows, OT *__restrict__ out)
 {
+    pdl_wait();
+    pdl_trigger();
     // dQ.d = chunks per row = pitch / 8
     const unsigned t = blockIdx.x * kThreads + threadIdx.x;
     const unsigned rg = dQ.div(t);
@@ -322,6 +324,8 @@ group_tile_kernel(const float *__restrict__ xyz, const PT *__restrict__ points, 
                   const int64_t *__restrict__ idx, int N, int D, int C, FastDiv dK, FastDiv dS, FastDiv dW,
                   int xyz_first, int clamp, int TR, unsigned rows, OT *__restrict__ out)
 {
+    pdl_wait();
+    pdl_trigger();
     __shared__ int s_src[kTileMaxRows];                // b * N + i of the gathered point, -1: index out of range
     __shared__ unsigned s_bs[kTileMaxRows];            // b * S + s (centroid row)
     const unsigned row0 = blockIdx.x * (unsigned)TR;
@@ -418,6 +422,8 @@ group_points_bwd_vec_kernel(const GT *__restrict__ gout, const int64_t *__restri
                             FastDiv dDV, FastDiv dSK, int foff, int clamp, int aligned, unsigned total,
                             float *__restrict__ gpoints)
 {
+    pdl_wait();
+    pdl_trigger();
     const unsigned t = blockIdx.x * kThreads + threadIdx.x;
     if (t >= total) return;
     const unsigned rowg = dDV.div(t);
@@ -743,6 +749,8 @@ fp_concat_chunk_kernel(const T1 *__restrict__ p1, const T2 *__restrict__ p2, con
                        const float *__restrict__ w, int S, int D1, int D2, int k, FastDiv dQ, FastDiv dN,
                        unsigned total, __nv_bfloat16 *__restrict__ out)
 {
+    pdl_wait();
+    pdl_trigger();
     const unsigned t = blockIdx.x * kThreads + threadIdx.x;
     if (t >= total) return;
     const unsigned rowg = dQ.div(t);                   // b*N + n
@@ -777,6 +785,8 @@ fp_concat_bwd_vec_kernel(const __nv_bfloat16 *__restrict__ gout, const int64_t *
                          const float *__restrict__ w, int S, int D1, int D2, int k, int pitch, FastDiv dDV, FastDiv dN,
                          unsigned total, float *__restrict__ gp2)
 {
+    pdl_wait();
+    pdl_trigger();
     const unsigned t = blockIdx.x * kThreads + threadIdx.x;
     if (t >= total) return;
     const unsigned rowg = dDV.div(t);
@@ -933,13 +943,13 @@ static int group_points_launch(const float *xyz, const PT *points, const float *
         const unsigned tiles = (nrows + TR - 1) / TR;
         const bool tile_ok = !points_cf && (int64_t)nb * N < (1ll << 31);
         if (tile_ok && pts && C % 8 == 0 && aligned16(o) && D % 8 == 0 && !xyz_first && C == D + 8 && aligned16(pts)) {
-            group_tile_kernel<OT, PT, true><<<tiles, kThreads, 0, st>>>(
+            launch_pdl(group_tile_kernel<OT, PT, true>, dim3(tiles), dim3(kThreads), 0, st, 
                 xyz + (size_t)b0 * N * 3, pts, new_xyz + (size_t)b0 * S * 3, idx + (size_t)b0 * S * K, N, D, C,
                 make_fastdiv(K), make_fastdiv(S), make_fastdiv(D / 8), xyz_first, clamp, TR, nrows, o);
             continue;
         }
         if (tile_ok && !(C % 8 == 0 && aligned16(o))) { // any layout / pitch, one element per item
-            group_tile_kernel<OT, PT, false><<<tiles, kThreads, 0, st>>>(
+            launch_pdl(group_tile_kernel<OT, PT, false>, dim3(tiles), dim3(kThreads), 0, st, 
                 xyz + (size_t)b0 * N * 3, pts, new_xyz + (size_t)b0 * S * 3, idx + (size_t)b0 * S * K, N, D, C,
                 make_fastdiv(K), make_fastdiv(S), make_fastdiv(C), xyz_first, clamp, TR, nrows, o);
             continue;
@@ -948,7 +958,7 @@ static int group_points_launch(const float *xyz, const PT *points, const float *
             const int vec_ok = pts && !points_cf && D % 8 == 0 && aligned16(pts);
             const unsigned rows = (unsigned)((int64_t)nb * S * K);
             const unsigned RG = (rows + kGroupU - 1) / kGroupU;
-            group_points_chunk_kernel<OT, PT><<<blocks_for((int64_t)RG * (C / 8)), kThreads, 0, st>>>(
+            launch_pdl(group_points_chunk_kernel<OT, PT>, dim3(blocks_for((int64_t)RG * (C / 8))), dim3(kThreads), 0, st, 
                 xyz + (size_t)b0 * N * 3, pts, new_xyz + (size_t)b0 * S * 3, idx + (size_t)b0 * S * K, N, D,
                 make_fastdiv(C / 8), make_fastdiv(K), make_fastdiv(S), xyz_first, points_cf, clamp, vec_ok, RG, rows, o);
             continue;
@@ -982,7 +992,7 @@ static int group_points_bwd_launch(const GT *grad_out, const int64_t *idx, int B
             const int foff = xyz_first ? 3 : 0;
             const int al = (sizeof(GT) == 4 ? (C % 4 == 0 && foff % 4 == 0 && aligned16(go))
                                             : (C % 4 == 0 && foff % 4 == 0 && (reinterpret_cast<uintptr_t>(go) & 7) == 0));
-            group_points_bwd_vec_kernel<GT><<<blocks_for(total / 4), kThreads, 0, st>>>(
+            launch_pdl(group_points_bwd_vec_kernel<GT>, dim3(blocks_for(total / 4)), dim3(kThreads), 0, st, 
                 go, idx + (size_t)b0 * S * K, N, D, C, make_fastdiv(D / 4), make_fastdiv((unsigned)(S * K)), foff, clamp,
                 al, total / 4, gp);
             continue;
@@ -1135,7 +1145,7 @@ static int fp_concat_launch(const void *p1, const void *p2, const int64_t *idx, 
         const int nb = B - b0 < step ? B - b0 : step;
         const unsigned total = (unsigned)((int64_t)nb * N * (pitch / 2));
         if (D1 % 8 == 0 && D2 % 8 == 0 && pitch % 8 == 0 && aligned16(out) && aligned16(p2) && (!p1 || aligned16(p1))) {
-            fp_concat_chunk_kernel<T1, T2><<<blocks_for(total / 4), kThreads, 0, st>>>(
+            launch_pdl(fp_concat_chunk_kernel<T1, T2>, dim3(blocks_for(total / 4)), dim3(kThreads), 0, st, 
                 p1 ? (const T1 *)p1 + (size_t)b0 * N * D1 : nullptr, (const T2 *)p2 + (size_t)b0 * S * D2,
                 idx + (size_t)b0 * N * k, w + (size_t)b0 * N * k, S, D1, D2, k, make_fastdiv(pitch / 8), make_fastdiv(N),
                 total / 4, (__nv_bfloat16 *)out + (size_t)b0 * N * pitch);
@@ -1178,7 +1188,7 @@ PCB_API int pcb_fp_concat_bwd_bf16(const void *grad_out, const int64_t *idx, con
         const unsigned total = (unsigned)((int64_t)nb * N * D2);
         if (D1 % 4 == 0 && D2 % 4 == 0 && pitch % 4 == 0 && (reinterpret_cast<uintptr_t>(grad_out) & 7) == 0 &&
             aligned16(grad_points2)) {
-            fp_concat_bwd_vec_kernel<<<blocks_for(total / 4), kThreads, 0, (cudaStream_t)stream>>>(
+            launch_pdl(fp_concat_bwd_vec_kernel, dim3(blocks_for(total / 4)), dim3(kThreads), 0, (cudaStream_t)stream, 
                 (const __nv_bfloat16 *)grad_out + (size_t)b0 * N * pitch, idx + (size_t)b0 * N * k,
                 weight + (size_t)b0 * N * k, S, D1, D2, k, pitch, make_fastdiv(D2 / 4), make_fastdiv(N), total / 4,
                 grad_points2 + (size_t)b0 * S * D2);

@@ -27,6 +27,8 @@ __global__ void __launch_bounds__(kNllThreads)
 nll_rows_fwd_kernel(const T *__restrict__ x, const float *__restrict__ bias, const int64_t *__restrict__ labels, int64_t M,
                     int classes, int pitch, float *__restrict__ partial)
 {
+    pdl_wait();
+    pdl_trigger();
     __shared__ float s_red[kNllThreads / 32];
     float acc = 0.f;
     for (int64_t r = (int64_t)blockIdx.x * kNllThreads + threadIdx.x; r < M; r += (int64_t)gridDim.x * kNllThreads) {
@@ -66,6 +68,8 @@ __global__ void __launch_bounds__(kNllThreads)
 nll_rows_bwd_kernel(const T *__restrict__ x, const float *__restrict__ bias, const int64_t *__restrict__ labels, int64_t M,
                     int classes, int pitch, const float *__restrict__ gscale, T *__restrict__ dx, float *__restrict__ gbias)
 {
+    pdl_wait();
+    pdl_trigger();
     __shared__ float s_gb[kNllThreads / 32][kNllMaxClasses];
     float gb[kNllMaxClasses];
 #pragma unroll
@@ -135,10 +139,10 @@ PCB_API int pcb_nll_rows_fwd(const void *logits, int dtype, const float *bias, c
     PCB_REQUIRE(M > 0 && classes > 0 && classes <= kNllMaxClasses && pitch >= classes && (dtype == 0 || dtype == 1), PCB_ERANGE);
     const int blocks = pcb_nll_rows_blocks(M);
     if (dtype)
-        nll_rows_fwd_kernel<<<blocks, kNllThreads, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)logits, bias, labels, M,
+        launch_pdl(nll_rows_fwd_kernel<__nv_bfloat16>, dim3(blocks), dim3(kNllThreads), 0, (cudaStream_t)stream, (const __nv_bfloat16 *)logits, bias, labels, M,
                                                                             classes, pitch, partial);
     else
-        nll_rows_fwd_kernel<<<blocks, kNllThreads, 0, (cudaStream_t)stream>>>((const float *)logits, bias, labels, M, classes,
+        launch_pdl(nll_rows_fwd_kernel<float>, dim3(blocks), dim3(kNllThreads), 0, (cudaStream_t)stream, (const float *)logits, bias, labels, M, classes,
                                                                             pitch, partial);
     PCB_RETURN_LAUNCH_STATUS();
 }
@@ -150,11 +154,11 @@ PCB_API int pcb_nll_rows_bwd(const void *logits, int dtype, const float *bias, c
     PCB_REQUIRE(M > 0 && classes > 0 && classes <= kNllMaxClasses && pitch >= classes && (dtype == 0 || dtype == 1), PCB_ERANGE);
     const int blocks = pcb_nll_rows_blocks(M);
     if (dtype)
-        nll_rows_bwd_kernel<<<blocks, kNllThreads, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)logits, bias, labels, M,
+        launch_pdl(nll_rows_bwd_kernel<__nv_bfloat16>, dim3(blocks), dim3(kNllThreads), 0, (cudaStream_t)stream, (const __nv_bfloat16 *)logits, bias, labels, M,
                                                                             classes, pitch, grad_loss,
                                                                             (__nv_bfloat16 *)grad_logits, grad_bias);
     else
-        nll_rows_bwd_kernel<<<blocks, kNllThreads, 0, (cudaStream_t)stream>>>((const float *)logits, bias, labels, M, classes,
+        launch_pdl(nll_rows_bwd_kernel<float>, dim3(blocks), dim3(kNllThreads), 0, (cudaStream_t)stream, (const float *)logits, bias, labels, M, classes,
                                                                             pitch, grad_loss, (float *)grad_logits, grad_bias);
     PCB_RETURN_LAUNCH_STATUS();
 }
