@@ -257,6 +257,17 @@ int pcb_adam_flat_f32(float *param, const float *grad, float *exp_avg, float *ex
                       float beta1, float beta2, float eps, float weight_decay, const int64_t *step,
                       const int *shadow_index, const int *shadow_index_t, void *shadow_bf16, pcb_stream_t stream);
 
+/* ---- section 8f rank 3: input rows of BridgeStructureEncoding in one kernel
+ *          Highway_bridge/models/attention_modules.py:552-574 (absolute position encoding), :590-597 (neighbours - centre),
+ *          :622-687 (get_structure_features: 13 statistics per point), :603-613 (expand + cat)
+ * xyz [B,N,3] fp32, idx [B,N,k] int64 (the k nearest neighbours of every point, pcb_knn_cdist_f32), 2 <= k <= 32;
+ * freqs: HOST array of F <= 8 frequencies (the module's `freqs` buffer), grid_size > 0.
+ * rows (may be NULL) [B*N*k, pitch]: [sin/cos encoding (6F) | neighbour - centre (3) | statistics (13) | 0 pad], fp32
+ * (out_bf16 == 0) or bf16; pitch >= 6F + 16, multiple of 8.  feat (may be NULL) [B*N, 13] fp32: the statistics alone.
+ * Covariance accumulated in float64, eigenvalues by the float64 closed form of pcb_eigvalsh3_f32; no host sync. */
+int pcb_structure_rows_f32(const float *xyz, const int64_t *idx, int B, int N, int k, const float *freqs, int F,
+                           float grid_size, int out_bf16, int pitch, void *rows, float *feat, pcb_stream_t stream);
+
 /* ---- a11 (training): shared-MLP contractions on the tcgen05 tensor cores, BatchNorm statistics in the epilogue
  *          pointnet_util.py:213-217, 275-277, 343-345; pointnet2_sem_seg.py:43-46; pointnet2_utils.py:150-154, 353-356;
  *          DGCNN.py:134-148  (1x1 Conv2d / Conv1d = [M,K] x [K,N] on point-major rows)

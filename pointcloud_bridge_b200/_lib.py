@@ -56,6 +56,7 @@ _SIGNATURES = {
     "pcb_nll_rows_fwd": [_vp, _i, _vp, _vp, _i64, _i, _i, _vp, _vp],
     "pcb_nll_rows_bwd": [_vp, _i, _vp, _vp, _i64, _i, _i, _vp, _vp, _vp, _vp],
     "pcb_eigvalsh3_f32": [_vp, _i64, _vp, _vp],
+    "pcb_structure_rows_f32": [_vp, _vp, _i, _i, _i, _vp, _i, _f, _i, _i, _vp, _vp, _vp],
     "pcb_knn_f32": [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp],
     "pcb_knn_cdist_f32": [_vp, _i, _i, _i, _vp, _vp, _vp],
     "pcb_graph_feature_f32": [_vp, _vp, _i, _i, _i, _i, _vp, _vp],

@@ -5,8 +5,10 @@ GeometricFeatureExtraction (:241-269) and CompositeFeatureFusion (:756-773), wit
 reference's constructor arguments and parameter names.
 
 Hot-path content: the `torch.cdist -> topk -> gather` neighbourhoods (:584-597, :736-743)
-become one fused kNN kernel (no [B,N,N] matrices) and one grouping kernel.  The per-point
-statistics of `get_structure_features` stay PyTorch ops.
+become one fused kNN kernel (no [B,N,N] matrices); the position encoding, the neighbour offsets, the
+13 per-point statistics of `get_structure_features` and the expand / cat into the encoder MLP's input
+rows are ONE kernel (csrc/structure.cu, SURVEY.md section 8f rank 3) in training and evaluation;
+`get_structure_features` itself stays available as the reference-shaped PyTorch composition.
 The file's unused classes (BoundaryAwareModule, EnhancedPositionalEncoding, compute_normals)
 are not on the path and are not provided.
 """
@@ -18,6 +20,11 @@ import torch.nn as nn
 from .. import ops
 from ..partsize.pointnet_util import _cf_view, _rows
 from .pointnet2_utils import seq_rows
+
+import os
+
+# PCB_NO_FUSED_STRUCTURE=1: the PyTorch composition of get_structure_features (kept as the test yardstick)
+_FUSED_STRUCTURE = os.environ.get("PCB_NO_FUSED_STRUCTURE", "0") != "1"
 
 __all__ = ["BridgeStructureEncoding", "ColorFeatureExtraction", "GeometricFeatureExtraction",
            "CompositeFeatureFusion", "knn_cdist", "square_distance", "index_points"]
@@ -91,13 +98,22 @@ class BridgeStructureEncoding(nn.Module):
         B, N, _ = xyz.shape
         k = min(self.k, N)
         idx = knn_cdist(xyz, k)
-        rel_pos = ops.group_points(xyz, None, xyz, idx, xyz_first=True)       # neighbours - centre [B,N,k,3]
-        per_point = torch.cat([self.compute_absolute_position_encoding(xyz),
-                               self.get_structure_features(rel_pos)], dim=-1)  # [B,N,6F+13]
-        a = self.abs_pos_dim
-        rows = torch.cat([per_point[:, :, None, :a].expand(-1, -1, k, -1), rel_pos,
-                          per_point[:, :, None, a:].expand(-1, -1, k, -1)], dim=-1)
-        y = seq_rows(self.structure_mlp, rows.reshape(B * N * k, self.total_dim))
+        if xyz.is_cuda and 2 <= k <= 32 and self.freq_bands <= 8 and _FUSED_STRUCTURE:
+            # one kernel: position encoding + neighbour offsets + the 13 statistics + expand / cat into the MLP's rows
+            # (fp32 rows in parity mode, bf16 rows under bf16 autocast); same solver in training and evaluation
+            lp = torch.is_autocast_enabled() and torch.get_autocast_dtype("cuda") == torch.bfloat16
+            if getattr(self, "_freqs_host", None) is None:
+                self._freqs_host = [float(f) for f in self.freqs.tolist()]     # once: the buffer is a constant
+            rows, _ = ops.structure_rows(xyz, idx, self._freqs_host, self.grid_size, bf16=lp)
+            rows = rows if rows.shape[1] == self.total_dim else rows[:, :self.total_dim]
+        else:
+            rel_pos = ops.group_points(xyz, None, xyz, idx, xyz_first=True)   # neighbours - centre [B,N,k,3]
+            per_point = torch.cat([self.compute_absolute_position_encoding(xyz),
+                                   self.get_structure_features(rel_pos)], dim=-1)  # [B,N,6F+13]
+            a = self.abs_pos_dim
+            rows = torch.cat([per_point[:, :, None, :a].expand(-1, -1, k, -1), rel_pos,
+                              per_point[:, :, None, a:].expand(-1, -1, k, -1)], dim=-1).reshape(B * N * k, self.total_dim)
+        y = seq_rows(self.structure_mlp, rows)
         return _cf_view(y.view(B * N, k, -1).max(dim=1)[0], B, N)
 
 

@@ -674,6 +674,29 @@ def eigvalsh3(a: torch.Tensor) -> torch.Tensor:
     return out
 
 
+@torch.no_grad()
+def structure_rows(xyz: torch.Tensor, idx: torch.Tensor, freqs, grid_size: float = 1.0, bf16: bool = False,
+                   rows: bool = True, feat: bool = False):
+    """Input rows of BridgeStructureEncoding (attention_modules.py:552-613, 622-687) in one kernel: xyz [B,N,3],
+    idx [B,N,k] (k nearest neighbours) -> rows [B*N*k, pitch] = [sin/cos encoding (6F) | neighbour - centre (3) | 13
+    structure statistics | zero pad to a multiple of 8] (fp32, or bf16 for the training MLP) and / or the statistics
+    alone [B,N,13].  No host synchronisation (the reference's eigh has one), nothing differentiable."""
+    xyz = _f32(xyz, "xyz")
+    idx = _i64(idx, "idx")
+    B, N, k = idx.shape
+    fr = [float(f) for f in (freqs.tolist() if isinstance(freqs, torch.Tensor) else freqs)]
+    F = len(fr)
+    pitch = _ru8(6 * F + 16)
+    dev = xyz.device
+    out_rows = torch.empty(B * N * k, pitch, dtype=torch.bfloat16 if bf16 else torch.float32, device=dev) if rows else None
+    out_feat = torch.empty(B, N, 13, dtype=torch.float32, device=dev) if feat else None
+    carr = (ctypes.c_float * max(F, 1))(*fr)
+    _call("pcb_structure_rows_f32", dev, xyz.data_ptr(), idx.data_ptr(), B, N, k, ctypes.cast(carr, ctypes.c_void_p), F,
+          float(grid_size), int(bf16), pitch, out_rows.data_ptr() if rows else None, out_feat.data_ptr() if feat else None,
+          alg_bytes=B * N * (12 + 8 * k) + (out_rows.numel() * out_rows.element_size() if rows else 0))
+    return out_rows, out_feat
+
+
 # ---------------------------------------------------------------------------------------------
 # mean NLL of the segmentation head straight from the classifier's logits rows
 # ---------------------------------------------------------------------------------------------

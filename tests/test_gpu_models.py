@@ -14,8 +14,9 @@ Tolerances (fp32 mode; north_star asks 1e-5 relative for fp32, 1e-2 for bf16):
     bit-exact at op level on the oracle's own features (tests/test_gpu_prims.py);
   * BriStruNet feeds eigenvalue ratios (e0 - e1) / (e0 + 1e-8) of near-singular 3x3 covariances
     into the net (attention_modules.py:631-633), ill-conditioned in fp32 (LAPACK on CPU vs
-    cuSOLVER on GPU).  Measured 6e-6 max on the fixture; asserted: FPS indices bit-exact,
-    median < 1e-5, p99 < 1e-3.
+    cuSOLVER on GPU; here one kernel with a float64 closed form, csrc/structure.cu, in training and evaluation).
+    Measured p50 2e-7 / p99 1.4e-6 / max 1e-5 on the fixture; asserted: FPS indices bit-exact, median < 1e-5,
+    p99 < 1e-4, max < 5e-4.
   * bf16 autocast: 1e-2 relative to max|ref| on the log-probabilities (mean) for MSG.
 """
 import contextlib
@@ -154,7 +155,7 @@ def test_bristrunet_forward_config4(g):
     err = np.abs(y.float().cpu().numpy() - ref) / (np.abs(ref).max() + 1e-12)
     print("bristrunet rel err: p50 %.2e p99 %.2e max %.2e" % (np.median(err), np.quantile(err, 0.99), err.max()))
     assert np.isfinite(y.float().cpu().numpy()).all()
-    assert np.median(err) < 1e-5 and np.quantile(err, 0.99) < 1e-3
+    assert np.median(err) < 1e-5 and np.quantile(err, 0.99) < 1e-4 and err.max() < 5e-4     # measured max 1e-5
     crit = hb_model.BridgeStructureLoss(num_classes=5, alpha=80, rel_margin=0.3).to(DEV)
     loss = crit(torch.from_numpy(ref).to(DEV), lab[:1], xyz[:1])
     assert abs(loss.item() - float(g["bri_loss"])) < 1e-4 * max(1.0, abs(float(g["bri_loss"])))
