@@ -304,6 +304,12 @@ int pcb_gemm_tickets(void);
 int pcb_gemm_max_groups(void);
 int pcb_linear_rows_bf16(const void *x, int64_t ldx, const void *w, int64_t ldw, int64_t M, int N, int Nw, int K, void *y,
                          int64_t ldy, pcb_stream_t stream);
+/* inference layer, BatchNorm folded into w / bias: y = act(x . w^T + bias) (act 0 identity, 1 ReLU, 2 leaky ReLU with
+ * `slope`; bias fp32 [Cv] or NULL); pool_k > 1 (divides 128 and M): only the max over every pool_k consecutive rows is
+ * written, y = [M / pool_k, ldy]  (pointnet_util.py:213-217, 273-279, 343-345; DGCNN.py:134-148 in evaluation mode) */
+int pcb_linear_bias_act_rows_bf16(const void *x, int64_t ldx, const void *w, int64_t ldw, int64_t M, int N, int Nw, int K,
+                                  const float *bias, int Cv, int act, float slope, int pool_k, void *y, int64_t ldy,
+                                  pcb_stream_t stream);
 int pcb_linear_bn_stats_rows_bf16(const void *x, int64_t ldx, const void *w, int64_t ldw, int64_t M, int N, int Nw, int K,
                                   void *y, int64_t ldy, int Cv, float eps, float *mean, float *invstd, float *var,
                                   float *work, unsigned *tickets, float *gparts, int *groups_out, pcb_stream_t stream);

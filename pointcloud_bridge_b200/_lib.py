@@ -40,6 +40,7 @@ _SIGNATURES = {
     "pcb_wgrad_rows_bf16": [_vp, _vp, _i64, _i, _i, _i, _i, _vp, _i, _vp],
     "pcb_adam_flat_f32": [_vp, _vp, _vp, _vp, _i64, _vp, _f, _f, _f, _f, _vp, _vp, _vp, _vp, _vp],
     "pcb_linear_rows_bf16": [_vp, _i64, _vp, _i64, _i64, _i, _i, _i, _vp, _i64, _vp],
+    "pcb_linear_bias_act_rows_bf16": [_vp, _i64, _vp, _i64, _i64, _i, _i, _i, _vp, _i, _i, _f, _i, _vp, _i64, _vp],
     "pcb_linear_bn_stats_rows_bf16": [_vp, _i64, _vp, _i64, _i64, _i, _i, _i, _vp, _i64, _i, _f, _vp, _vp, _vp, _vp, _vp,
                                       _vp, _vp, _vp],
     "pcb_dgrad_bn_rows_bf16": [_vp, _i64, _vp, _i64, _i64, _i, _i, _i, _vp, _i64, _vp, _vp, _vp, _vp, _i, _i, _vp, _i64,

@@ -42,7 +42,8 @@ namespace pcb {
 constexpr int kGemmThreads = 128;
 constexpr int kFoldGroup = 32;             // CTAs per first-level fold group
 constexpr int kCombFloats = 3 * 1024;      // row-group combine: rgroups * BN <= 1024 columns x (n, mean, M2)
-enum { EPI_STORE = 0, EPI_STATS = 1, EPI_BNBWD = 2 };
+enum { EPI_STORE = 0, EPI_STATS = 1, EPI_BNBWD = 2, EPI_BIAS = 3 };
+__host__ __device__ constexpr bool epi_has_stats(int epi) { return epi == EPI_STATS || epi == EPI_BNBWD; }
 
 struct GemmParams {
     int64_t M;
@@ -66,6 +67,13 @@ struct GemmParams {
     // that consumes the statistics anyway (pcb_bn_apply_rows / pcb_bn_bwd_apply_rows fold them at their start): the
     // second "last arriver" level (fence + ticket + fold, ~4 us of serial latency per launch) disappears
     float *gparts;
+    // EPI_BIAS (inference: conv with the BatchNorm folded in): out = act(acc + bias), act = identity / ReLU / leaky ReLU;
+    // pool_k > 1: only the max over every pool_k consecutive rows is written, to pooled [M / pool_k, ldp]
+    const float *bias;           // [Cv] or NULL
+    float slope;                 // act == 2: leaky slope
+    int act, pool_k;
+    void *pooled;
+    int64_t ldp;
 };
 
 __device__ __forceinline__ void unpack8(const uint4 &t, float v[8])
@@ -156,13 +164,13 @@ __host__ __device__ __forceinline__ GemmSmem gemm_smem_layout(int BN, int swzA, 
     s.nb = nslabs == 1 ? 1 : stages;                                         // resident weights when K fits one slab
     s.off_b = stages * s.a_bytes;
     int opnd = s.off_b + s.nb * s.b_bytes;
-    if (epi != EPI_STORE && opnd < kCombFloats * 4) opnd = kCombFloats * 4;  // the combine scratch aliases the operand ring
+    if (epi_has_stats(epi) && opnd < kCombFloats * 4) opnd = kCombFloats * 4;  // the combine scratch aliases the operand ring
     s.sub_bytes = 128 * wsub * 2;
     s.out_bytes = ((BN + wsub - 1) / wsub) * s.sub_bytes;
     s.off_out = (opnd + 1023) & ~1023;
     s.off_y = s.off_out + s.out_bytes;
     s.off_const = s.off_y + (epi == EPI_BNBWD ? 2 * s.out_bytes : 0);        // y tiles: double buffered
-    s.total = s.off_const + (epi == EPI_BNBWD ? 4 * BN * 4 : 0) + 1024;      // + slack for the 1024-byte alignment
+    s.total = s.off_const + (epi == EPI_BNBWD ? 4 * BN * 4 : (epi == EPI_BIAS ? BN * 4 : 0)) + 1024;   // + alignment slack
     return s;
 }
 
@@ -300,7 +308,10 @@ gemm_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             s_const[3 * BN + c] = real ? p.beta[gc] - m * sc : 0.f;
         }
     }
-    if (EPI == EPI_BNBWD) __syncthreads();
+    if (EPI == EPI_BIAS) {
+        for (int c = tid; c < BN; c += kGemmThreads) s_const[c] = (p.bias && n0 + c < p.Cv) ? p.bias[n0 + c] : 0.f;
+    }
+    if (EPI == EPI_BNBWD || EPI == EPI_BIAS) __syncthreads();
     const uint32_t tmem_base = s_tmem;
     const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
     const uint32_t idesc = umma_idesc_bf16_m128(BN);
@@ -330,7 +341,7 @@ gemm_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const uint32_t omask = (uint32_t)(pitchO >> 4) - 1u;                     // swizzle mask of the output / y tiles
     const int U = BN >> 3;                                                   // 16-byte column units of the tile
     const int rgroups = kGemmThreads / U;                                    // >= 4 (BN <= 256)
-    const bool st_active = EPI != EPI_STORE && tid < U * rgroups;
+    const bool st_active = epi_has_stats(EPI) && tid < U * rgroups;
     const int st_rg = tid / U, st_u = tid - st_rg * U;
     const int st_j = (st_u << 3) >> wshift, st_uu = st_u - ((st_j << wshift) >> 3);
     const uint32_t st_base = (uint32_t)(st_j * L.sub_bytes);
@@ -421,18 +432,48 @@ gemm_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     }
                 }
             }
+            if (EPI == EPI_BIAS) {
+#pragma unroll
+                for (int q = 0; q < 16; ++q) {
+                    float t = v[q] + s_const[c0 + q];
+                    if (p.act == 1) t = fmaxf(t, 0.f);
+                    else if (p.act == 2) t = t > 0.f ? t : t * p.slope;
+                    v[q] = t;
+                }
+            }
             sts128(sOut + off0, pack8(v));
             sts128(sOut + off1, pack8(v + 8));
         }
         tc_fence_before();                                                   // TMEM reads done before the next tile's MMAs
         proxy_fence();                                                       // generic-proxy writes -> TMA store reads
         __syncthreads();                                                     // (B) tile complete
-        if (tid == 0) {
+        if (EPI == EPI_BIAS && p.pool_k > 1) {
+            // max over every pool_k consecutive rows of the tile (pool_k divides 128 and M): thread = (16-byte column
+            // unit, pooling group), packed bf16 max, one 16-byte store per (group, unit) straight to the pooled rows
+            const int G = 128 / p.pool_k;
+            for (int it = tid; it < U * G; it += kGemmThreads) {
+                const int gq = it / U, u = it - gq * U;
+                const int r0 = gq * p.pool_k;
+                if (r0 >= rows || n0 + 8 * u >= p.N) continue;
+                const int j = (u << 3) >> wshift, uu = u - ((j << wshift) >> 3);
+                const uint32_t base = sOut + (uint32_t)(j * L.sub_bytes), col = (uint32_t)(uu * 16);
+                uint4 best = lds128(base + swz((uint32_t)(r0 * pitchO) + col, omask));
+                for (int r = 1; r < p.pool_k; ++r) {
+                    const uint4 w = lds128(base + swz((uint32_t)((r0 + r) * pitchO) + col, omask));
+                    __nv_bfloat162 *b2 = reinterpret_cast<__nv_bfloat162 *>(&best);
+                    const __nv_bfloat162 *w2 = reinterpret_cast<const __nv_bfloat162 *>(&w);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) b2[i] = __hmax2(b2[i], w2[i]);
+                }
+                __nv_bfloat16 *o = (__nv_bfloat16 *)p.pooled + ((m0 + r0) / p.pool_k) * p.ldp + n0 + 8 * u;
+                *reinterpret_cast<uint4 *>(o) = best;
+            }
+        } else if (tid == 0) {
             for (int j = 0; j < p.nsub; ++j)
                 if (n0 + j * wsub < p.N) tma_store_2d(&tmC, n0 + j * wsub, mt * 128, sOut + (uint32_t)(j * L.sub_bytes));
             bulk_commit();
         }
-        if (EPI != EPI_STORE && st_active) {
+        if (epi_has_stats(EPI) && st_active) {
             if (EPI == EPI_STATS) {
                 if (ti == 0 && st_rg < rows) {
                     const uint4 w = lds128(sOut + st_base + swz((uint32_t)(st_rg * pitchO) + st_col, omask));
@@ -485,7 +526,7 @@ gemm_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     if (tid == 0) bulk_wait_all0();                                          // the last store has left shared memory
 
-    if (EPI != EPI_STORE) {
+    if (epi_has_stats(EPI)) {
         // ---- per-CTA partial statistics: the row groups merged in a fixed order through shared memory (aliases the
         //      operand ring: every copy has been consumed and every MMA has completed)
         __syncthreads();
@@ -593,7 +634,7 @@ struct GemmPlan {
 
 // CTAs per SM the registers of each epilogue variant allow (cudaFuncGetAttributes once per device; the occupancy API
 // answered 1 in most launches -- measured with ncu, round 2 -- which serialised the whole design on one CTA per SM)
-static int g_reg_limit[3][kMaxDevices];
+static int g_reg_limit[4][kMaxDevices];
 
 static int gemm_force_span()                                                 // PCB_GEMM_SPAN=128: one swizzle mode for every K
 {
@@ -727,7 +768,11 @@ static int gemm_launch(GemmParams &p, const GemmOperands &o, cudaStream_t st, in
     CUtensorMap tmA, tmB, tmC, tmY;
     if (int rc = make_map(&tmA, o.A, p.M, p.K, o.lda, 128, g.BK)) return rc;
     if (int rc = make_map(&tmB, o.B, o.Nb, p.K, o.ldb, g.BN, g.BK)) return rc;
-    if (int rc = make_map(&tmC, o.C, p.M, p.N, o.ldc, 128, g.wsub)) return rc;
+    if (EPI == EPI_BIAS && p.pool_k > 1) {
+        tmC = tmA;                                                           // never stored through: the epilogue pools
+    } else if (int rc = make_map(&tmC, o.C, p.M, p.N, o.ldc, 128, g.wsub)) {
+        return rc;
+    }
     if (EPI == EPI_BNBWD) {
         if (int rc = make_map(&tmY, o.Y, p.M, p.N, o.ldy, 128, g.wsub)) return rc;
     } else {
@@ -824,4 +869,24 @@ PCB_API int pcb_dgrad_bn_rows_bf16(const void *gy, int64_t ldg, const void *wt, 
     p.Cv = Cv, p.bn_mean = mean, p.bn_invstd = invstd, p.gamma = gamma;
     p.beta = beta, p.relu = relu, p.sums = sums, p.parts = work, p.tickets = tickets, p.gparts = gparts;
     return gemm_launch<EPI_BNBWD>(p, o, (cudaStream_t)stream, groups_out);
+}
+
+// Inference layer (1x1 conv with the BatchNorm folded into w / bias): y = act(x . w^T + bias), act 0 identity /
+// 1 ReLU / 2 leaky ReLU(slope), bf16 in / out, bias fp32 [Cv] or NULL.  pool_k > 1 (must divide 128 and M): only
+// the max over every pool_k consecutive rows is written, y = [M / pool_k, ldy] -- the max over the neighbours of a
+// set-abstraction / EdgeConv block without the [M, N] tensor ever reaching memory.
+PCB_API int pcb_linear_bias_act_rows_bf16(const void *x, int64_t ldx, const void *w, int64_t ldw, int64_t M, int N, int Nw,
+                                          int K, const float *bias, int Cv, int act, float slope, int pool_k, void *y,
+                                          int64_t ldy, pcb_stream_t stream)
+{
+    GemmParams p = {};
+    GemmOperands o = {};
+    o.A = x, o.B = w, o.C = y, o.lda = ldx, o.ldb = ldw, o.ldc = ldy, o.Nb = Nw;
+    p.M = M, p.N = N, p.K = K;
+    const int rc = gemm_check(p, o);
+    if (rc) return rc;
+    PCB_REQUIRE(act >= 0 && act <= 2 && Cv >= 0 && Cv <= N, PCB_EINVAL);
+    PCB_REQUIRE(pool_k >= 1 && (pool_k == 1 || (pool_k <= 128 && 128 % pool_k == 0 && M % pool_k == 0)), PCB_ERANGE);
+    p.bias = bias, p.Cv = Cv, p.act = act, p.slope = slope, p.pool_k = pool_k, p.pooled = y, p.ldp = ldy;
+    return gemm_launch<EPI_BIAS>(p, o, (cudaStream_t)stream);
 }

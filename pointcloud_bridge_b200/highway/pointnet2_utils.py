@@ -99,6 +99,13 @@ def seq_rows(seq: nn.Sequential, x):
                 true_c = w.shape[0]
                 i += 3
                 continue
+            if isinstance(nxt, (nn.BatchNorm1d, nn.BatchNorm2d)) and type(nxt2) is nn.ReLU and not nxt.training \
+                    and x.is_cuda and x.dim() == 2 and ops.fused_inference_enabled():
+                # evaluation under bf16 autocast: BatchNorm folded in, bias + ReLU in the GEMM epilogue
+                x = ops.mlp_rows_infer(x, ops.folded_mlp(layer, id(nxt), [layer], [nxt]))
+                true_c = w.shape[0]
+                i += 3
+                continue
             if ops._step_ctx is not None and x.is_cuda and ops._step_ctx.shadow(w) is not None:
                 if x.shape[1] % 8:
                     x = F.pad(x, (0, -x.shape[1] % 8))                   # aligned rows for forward / dgrad / wgrad

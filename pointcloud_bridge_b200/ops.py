@@ -819,6 +819,77 @@ class PackedMLP:
         self.ok = self.smem <= 200 * 1024 and maxw <= 256 and self.nlayers <= 3
 
 
+class FoldedMLP:
+    """Eval-mode (conv 1x1 -> BatchNorm -> activation) stack folded to W', b' per layer as row-major bf16 weights
+    [n8, k8] (zero padded) + fp32 bias [n8]: the operands of the bias / activation epilogue of the tcgen05 GEMM
+    (csrc/gemm_rows.cu, EPI_BIAS) -- every layer width, any number of layers."""
+
+    def __init__(self, convs, bns):
+        dev = convs[0].weight.device
+        self.w, self.b, self.n = [], [], []
+        with torch.no_grad():
+            for conv, bn in zip(convs, bns):
+                w = conv.weight.flatten(1).float()
+                b = conv.bias.float() if conv.bias is not None else torch.zeros(w.shape[0], device=dev)
+                if bn is not None:
+                    scale = bn.weight.float() / torch.sqrt(bn.running_var.float() + bn.eps)
+                    w = w * scale[:, None]
+                    b = (b - bn.running_mean.float()) * scale + bn.bias.float()
+                n8, k8 = _ru8(w.shape[0]), _ru8(w.shape[1])
+                wp = torch.zeros(n8, k8, device=dev)
+                wp[:w.shape[0], :w.shape[1]] = w
+                bp = torch.zeros(n8, device=dev)
+                bp[:w.shape[0]] = b
+                self.w.append(wp.to(torch.bfloat16).contiguous())
+                self.b.append(bp.contiguous())
+                self.n.append(w.shape[0])
+        self.cout = self.n[-1]
+
+
+def folded_mlp(owner, key, convs, bns):
+    """Cache of FoldedMLP per module, invalidated like packed_mlp."""
+    ver = (_param_generation,) + tuple(t._version for m in list(convs) + [b for b in bns if b is not None]
+                                       for t in list(m.parameters()) + list(m.buffers()))
+    cache = owner.__dict__.setdefault("_pcb_folded", {})
+    hit = cache.get(key)
+    if hit is None or hit[0] != ver:
+        hit = (ver, FoldedMLP(convs, bns))
+        cache[key] = hit
+    return hit[1]
+
+
+@torch.no_grad()
+def mlp_rows_infer(x: torch.Tensor, folded: FoldedMLP, pool_k: int = 1, act: int = 1, slope: float = 0.0,
+                   last_act: bool = True) -> torch.Tensor:
+    """Inference shared MLP on rows: x [M, Cin] -> [M / pool_k, n8 of the last layer] bf16, every layer one tcgen05
+    GEMM whose epilogue adds the folded BatchNorm bias and applies the activation; the last layer's epilogue also
+    takes the max over every `pool_k` consecutive rows (the neighbour axis) when pool_k divides 128 -- the [M, C]
+    activation of the widest layer never reaches memory.  Replaces pointnet_util.py:213-217 / 273-279 / 343-345 in
+    evaluation mode for every layer shape (the one-kernel block of csrc/sa_fused.cu covers the narrow ones)."""
+    if x.dtype != torch.bfloat16:
+        x = x.to(torch.bfloat16)
+    if x.shape[1] % 8:
+        x = torch.nn.functional.pad(x, (0, -x.shape[1] % 8))
+    if not _rows_ok(x):
+        x = x.contiguous()
+    M = x.shape[0]
+    L = len(folded.w)
+    fuse_pool = pool_k > 1 and 128 % pool_k == 0 and M % pool_k == 0
+    for l, (w, b, n) in enumerate(zip(folded.w, folded.b, folded.n)):
+        last = l == L - 1
+        pk = pool_k if (last and fuse_pool) else 1
+        n8 = w.shape[0]
+        K = min(x.shape[1], w.shape[1])
+        y = torch.empty(M // pk, n8, dtype=torch.bfloat16, device=x.device)
+        _call("pcb_linear_bias_act_rows_bf16", x.device, x.data_ptr(), x.stride(0), w.data_ptr(), w.stride(0), M, n8, n8, K,
+              b.data_ptr(), n, int(act if (last_act or not last) else 0), float(slope), pk, y.data_ptr(), y.stride(0),
+              alg_bytes=2 * M * K + 2 * (M // pk) * n8 + 2 * w.numel())
+        x = y
+    if pool_k > 1 and not fuse_pool:
+        x = x.view(-1, pool_k, x.shape[1]).max(dim=1)[0]
+    return x
+
+
 # Bumped by everything that rewrites parameters or BatchNorm buffers behind autograd's back (the step runner's fused
 # Adam and BN kernels write through raw pointers, CUDA-graph replays run no Python at all): tensor `_version`
 # counters do not see those updates, so the folded-weight cache below also keys on this generation.

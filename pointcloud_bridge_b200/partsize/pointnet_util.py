@@ -155,6 +155,10 @@ def mlp_rows(x, convs, bns, pool_k=1, out=None):
     n = len(convs)
     if ops.mlp_rows_fused_supported(x, convs, bns, pool_k):
         x = ops.mlp_rows_fused(x, convs, bns, pool_k, out)        # the whole stack as one autograd node
+    elif x.is_cuda and ops.fused_inference_enabled() and not any(bn.training for bn in bns):
+        # evaluation under bf16 autocast: BatchNorm folded into the weights, one tcgen05 GEMM per layer with the
+        # bias + ReLU (+ max over the neighbours) in its epilogue -- every layer width
+        x = ops.mlp_rows_infer(x, ops.folded_mlp(convs[0], id(convs[-1]), convs, bns), pool_k)
     else:
         for i, (conv, bn) in enumerate(zip(convs, bns)):
             x = conv_bn_relu_rows(x, conv, bn, pool_k if i == n - 1 else 1, out if i == n - 1 else None)

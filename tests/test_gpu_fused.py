@@ -117,3 +117,50 @@ def test_networks_fused_vs_unfused_bf16(monkeypatch):
         print(type(net).__name__, "mean rel err vs fp32 reference: fused %.2e unfused %.2e" % (e_fused, e_plain))
         assert e_fused < 1e-2
         assert (outs[0].argmax(-1) == ref.argmax(-1)).mean() > 0.97
+
+
+@pytest.mark.parametrize("widths,M,K", [
+    ([131, 128, 128, 256], 64 * 32 * 2, 32),       # SSG sa3: wider than the one-kernel block takes
+    ([259, 256, 256, 512], 16 * 32 * 3, 32),       # SSG sa4 / MSG sa4 scale 0
+    ([515, 256, 384, 512], 16 * 16 * 2, 16),       # MSG sa4 scale 1
+    ([259, 128, 196, 256], 64 * 16 * 2, 16),       # MSG sa3: 196 channels carried as 200
+    ([1536, 256, 256], 300, 1),                    # feature propagation, ragged row count
+    ([12, 32, 32, 64], 20 * 50, 20),               # pool_k does not divide 128: max taken outside the epilogue
+])
+def test_mlp_rows_infer_every_layer_width(widths, M, K):
+    """BatchNorm-folded inference MLP on the tcgen05 GEMM with bias + ReLU (+ max over neighbours) epilogues
+    (ops.mlp_rows_infer) against the bf16-rounding emulation: the layers that the one-kernel block rejects."""
+    torch.manual_seed(M + K)
+    convs, bns = make_stack(widths, 7)
+    rows = torch.randn(M, widths[0], device=DEV)
+    out = ops.mlp_rows_infer(rows, ops.FoldedMLP(convs, bns), pool_k=K)[:, :widths[-1]].float()
+    ref = emulate(rows, convs, bns, K, 0.0)
+    assert out.shape == ref.shape
+    err = (out - ref).abs().max().item()
+    tol = 3 * 2 ** -8 * ref.abs().max().item() + 1e-6
+    print("mlp_rows_infer max err", err, "tol", tol)
+    assert err <= tol
+    assert (out - ref).abs().mean().item() <= 1e-3 * ref.abs().max().item()
+
+
+def test_eval_bf16_networks_launch_no_library_gemm_for_the_sa_layers(monkeypatch):
+    """SSG / MSG evaluation under bf16 autocast: every set-abstraction and feature-propagation MLP runs on kernels of
+    libpcbridge (one-kernel block or BatchNorm-folded tcgen05 GEMMs) -- checked through the C-ABI entry counter."""
+    g = parity.load("models.npz")
+    x9 = torch.from_numpy(synthetic.sem_seg_input(g["xyz"], g["rgb"])).to(DEV)
+    for net in (parity.seeded_fill_(ssg.get_model(13), 1), parity.seeded_fill_(msg.get_model(5), 2)):
+        net = net.to(DEV).eval()
+        seen = []
+        orig = ops._call
+
+        def spy(name, *a, **kw):
+            seen.append(name)
+            return orig(name, *a, **kw)
+        monkeypatch.setattr(ops, "_call", spy)
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+            net(x9[:1])
+        monkeypatch.setattr(ops, "_call", orig)
+        n_fused = seen.count("pcb_sa_fused_bf16")
+        n_gemm = seen.count("pcb_linear_bias_act_rows_bf16")
+        print(type(net).__module__, "one-kernel blocks:", n_fused, "folded GEMM layers:", n_gemm)
+        assert n_fused >= 2 and n_gemm >= 6 + 9            # wide SA layers + the feature-propagation stacks
