@@ -76,6 +76,12 @@ def _seg_head(net, feats_bcn):
     (pointnet2_sem_seg.py:43-47), evaluated on point-major rows."""
     x = _rows(feats_bcn)
     B, N, C = x.shape
+    if x.is_cuda and ops.fused_inference_enabled() and not net.bn1.training and not net.drop1.training:
+        # evaluation under bf16 autocast: conv1 + bn1 folded, ReLU in the epilogue; conv2 + bias on the same kernel
+        h = ops.mlp_rows_infer(x.reshape(B * N, C), ops.folded_mlp(net.conv1, 0, [net.conv1], [net.bn1]))
+        nc = net.conv2.weight.shape[0]
+        lg = ops.mlp_rows_infer(h, ops.folded_mlp(net.conv2, 0, [net.conv2], [None]), last_act=False)[:, :nc]
+        return F.log_softmax(lg.float(), dim=-1).view(B, N, -1)
     x = net.drop1(conv_bn_relu_rows(x.reshape(B * N, C), net.conv1, net.bn1))
     w, b = net.conv2.weight.flatten(1), net.conv2.bias
     nc = w.shape[0]
