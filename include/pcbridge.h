@@ -252,10 +252,12 @@ int pcb_nll_rows_bwd(const void *logits, int dtype, const float *bias, const int
  * captured CUDA graph follows a scheduler.  shadow_index [n] int32 (may be NULL): destination element of
  * parameter i in `shadow_bf16`, the bf16 copies of the GEMM weights ([N8, K8] zero padded), or -1;
  * shadow_index_t [n] (may be NULL): where the same element goes in the TRANSPOSED copy ([K8, N8], the operand of the
- * data-gradient GEMM), read only where shadow_index[i] >= 0. */
+ * data-gradient GEMM), read only where shadow_index[i] >= 0.  skip (may be NULL): [n] bytes, non-zero = the element
+ * belongs to a parameter that never receives a gradient and is left untouched, as torch.optim.Adam does for grad = None. */
 int pcb_adam_flat_f32(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, int64_t n, const float *lr,
                       float beta1, float beta2, float eps, float weight_decay, const int64_t *step,
-                      const int *shadow_index, const int *shadow_index_t, void *shadow_bf16, pcb_stream_t stream);
+                      const int *shadow_index, const int *shadow_index_t, void *shadow_bf16, const unsigned char *skip,
+                      pcb_stream_t stream);
 
 /* ---- section 8f rank 3: input rows of BridgeStructureEncoding in one kernel
  *          Highway_bridge/models/attention_modules.py:552-574 (absolute position encoding), :590-597 (neighbours - centre),

@@ -38,7 +38,7 @@ _SIGNATURES = {
     "pcb_fp_concat_bf16": [_vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp],
     "pcb_fp_concat_bwd_bf16": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp],
     "pcb_wgrad_rows_bf16": [_vp, _vp, _i64, _i, _i, _i, _i, _vp, _i, _vp],
-    "pcb_adam_flat_f32": [_vp, _vp, _vp, _vp, _i64, _vp, _f, _f, _f, _f, _vp, _vp, _vp, _vp, _vp],
+    "pcb_adam_flat_f32": [_vp, _vp, _vp, _vp, _i64, _vp, _f, _f, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp],
     "pcb_linear_rows_bf16": [_vp, _i64, _vp, _i64, _i64, _i, _i, _i, _vp, _i64, _vp],
     "pcb_linear_bias_act_rows_bf16": [_vp, _i64, _vp, _i64, _i64, _i, _i, _i, _vp, _i, _i, _f, _i, _vp, _i64, _vp],
     "pcb_linear_bn_stats_rows_bf16": [_vp, _i64, _vp, _i64, _i64, _i, _i, _i, _vp, _i64, _i, _f, _vp, _vp, _vp, _vp, _vp,

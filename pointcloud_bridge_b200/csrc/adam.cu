@@ -16,7 +16,8 @@ __global__ void __launch_bounds__(256)
 adam_flat_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m, float *__restrict__ v,
                  int64_t n, const float *__restrict__ lr_ptr, float beta1, float beta2, float eps, float weight_decay,
                  const int64_t *__restrict__ step_ptr, const int *__restrict__ shadow_index,
-                 const int *__restrict__ shadow_index_t, __nv_bfloat16 *__restrict__ shadow)
+                 const int *__restrict__ shadow_index_t, __nv_bfloat16 *__restrict__ shadow,
+                 const unsigned char *__restrict__ skip)
 {
     pdl_wait();
     pdl_trigger();
@@ -26,6 +27,8 @@ adam_flat_kernel(float *__restrict__ p, const float *__restrict__ g, float *__re
     const float bc2_sqrt = sqrtf(1.f - powf(beta2, step));
     const float step_size = lr / bc1;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        // parameters that never receive a gradient (torch.optim.Adam skips grad = None: no weight decay, no state)
+        if (skip && skip[i]) continue;
         float pi = p[i];
         float gi = g[i];
         if (weight_decay != 0.f) gi += pi * weight_decay;
@@ -51,7 +54,7 @@ adam_flat_kernel(float *__restrict__ p, const float *__restrict__ g, float *__re
 PCB_API int pcb_adam_flat_f32(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, int64_t n,
                               const float *lr, float beta1, float beta2, float eps, float weight_decay,
                               const int64_t *step, const int *shadow_index, const int *shadow_index_t, void *shadow_bf16,
-                              pcb_stream_t stream)
+                              const unsigned char *skip, pcb_stream_t stream)
 {
     using namespace pcb;
     PCB_REQUIRE(param && grad && exp_avg && exp_avg_sq && lr && step, PCB_EINVAL);
@@ -61,6 +64,6 @@ PCB_API int pcb_adam_flat_f32(float *param, const float *grad, float *exp_avg, f
     if (blocks > cap) blocks = cap;
     launch_pdl(adam_flat_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2,
                                                                         eps, weight_decay, step, shadow_index,
-                                                                        shadow_index_t, (__nv_bfloat16 *)shadow_bf16);
+                                                                        shadow_index_t, (__nv_bfloat16 *)shadow_bf16, skip);
     PCB_RETURN_LAUNCH_STATUS();
 }

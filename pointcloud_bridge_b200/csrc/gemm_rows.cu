@@ -255,6 +255,9 @@ __device__ __forceinline__ void fold_cols(const float *base, int cnt, int BN, fl
     __syncthreads();
 }
 
+// minimum CTAs per SM: the statistics epilogues are issue-latency bound with 4 warps per scheduler (ncu: 10.2 M warp
+// instructions per launch against 4.5 M of the plain GEMM, issue slots 31 % busy, occupancy limited by 122 registers):
+// forcing 5 CTAs per SM (96 registers, 4-byte spill) measured SLOWER (statistics 392 -> 396 us, data gradient 460 -> 496 us over the 20 layer shapes): kept at 4
 template <int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 4)
 gemm_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,

@@ -102,6 +102,7 @@ class FlatAdam:
         self.lr_t = torch.full((1,), float(lr), dtype=torch.float32, device=flat_param.device)
         self.betas, self.eps, self.weight_decay = betas, eps, weight_decay
         self.shadow_index, self.shadow_flat, self.shadow_index_t = shadow_index, shadow_flat, shadow_index_t
+        self.skip = None                   # uint8 [n]: elements of parameters that never receive a gradient (Trainer)
 
     def set_lr(self, lr: float) -> None:
         self.lr_t.fill_(float(lr))
@@ -117,7 +118,7 @@ class FlatAdam:
                   self.shadow_index.data_ptr() if self.shadow_index is not None else None,
                   self.shadow_index_t.data_ptr() if self.shadow_index_t is not None and self.shadow_index is not None else None,
                   self.shadow_flat.data_ptr() if self.shadow_index is not None else None,
-                  alg_bytes=self.p.numel() * 32)
+                  self.skip.data_ptr() if self.skip is not None else None, alg_bytes=self.p.numel() * 32)
 
     def state_dict(self):
         return {"step": self.step_t.clone(), "exp_avg": self.exp_avg.clone(), "exp_avg_sq": self.exp_avg_sq.clone(),
@@ -188,6 +189,7 @@ class Trainer:
         self._mid_event = torch.cuda.Event(external=True) \
             if self._use_chain and os.environ.get("PCB_MID_STEP_CHAIN", "1") != "0" else None
         self._mid_armed = False
+        self.frozen = None                 # indices of parameters that never receive a gradient (known after step 1)
 
     @torch.no_grad()
     def last_pred(self, class_dim: int = 1) -> torch.Tensor:
@@ -252,8 +254,25 @@ class Trainer:
     def _multi(self):
         return pdist.is_dist() and torch.distributed.get_world_size() > 1
 
+    def _mark_gradient_less(self):
+        """After the first backward pass: parameters with neither a `.grad` nor an in-place weight gradient (modules the
+        forward never reaches -- EnhancedPointNet2.geometric1 / cls_head) are left alone by the optimizer, as
+        torch.optim.Adam leaves grad = None parameters alone (no weight decay, no state)."""
+        self.frozen = [i for i, p in enumerate(self.bucket.params)
+                       if p.grad is None and id(p) not in self._ctx.gviews_used]
+        if self.frozen:
+            skip = torch.zeros(self.flat_param.numel(), dtype=torch.uint8, device=self.flat_param.device)
+            off = 0
+            for i, p in enumerate(self.bucket.params):
+                if i in set(self.frozen):
+                    skip[off:off + p.numel()] = 1
+                off += p.numel()
+            self.opt.skip = skip
+
     def _step_eager(self, inputs, labels, loss_inputs, pre=None):
         loss = self._fwd_bwd(inputs, labels, loss_inputs, pre)
+        if self.frozen is None:
+            self._mark_gradient_less()
         self.bucket.pack()
         if self._multi():
             self.bucket.allreduce_mean()

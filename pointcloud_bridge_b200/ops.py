@@ -1006,6 +1006,7 @@ class StepContext:
             self.shadow_index = torch.from_numpy(index).to(p0.device)
             self.shadow_index_t = torch.from_numpy(index_t).to(p0.device)
         self.external_refresh = False      # True: the optimizer kernel keeps the shadows current (engine.Trainer)
+        self.gviews_used = set()           # parameters whose weight gradient was written in place at least once
 
     def refresh_shadows(self):
         """fp32 parameters -> bf16 shadows (one multi-tensor copy + one copy per ragged weight)."""
@@ -1047,7 +1048,10 @@ class StepContext:
 
     def grad_view(self, w):
         base = w._base if w._base is not None else w
-        return self.grad_views.get(id(base))
+        v = self.grad_views.get(id(base))
+        if v is not None:
+            self.gviews_used.add(id(base))
+        return v
 
 
 _step_ctx = None

@@ -19,11 +19,16 @@ from .engine import Trainer
 __all__ = ["Runner", "adam_state_to_torch", "adam_state_from_torch"]
 
 
-def adam_state_to_torch(opt, params) -> dict:
-    """engine.FlatAdam state -> torch.optim.Adam.state_dict() layout for `params` (the order of model.parameters())."""
+def adam_state_to_torch(opt, params, frozen=()) -> dict:
+    """engine.FlatAdam state -> torch.optim.Adam.state_dict() layout for `params` (the order of model.parameters()).
+    frozen: indices of parameters that never received a gradient -- torch.optim.Adam keeps no state for them."""
     state, off = {}, 0
+    skip = set(frozen or ())
     for i, p in enumerate(params):
         n = p.numel()
+        if i in skip:
+            off += n
+            continue
         state[i] = {"step": opt.step_t.detach().clone().float().reshape(()).cpu(),
                     "exp_avg": opt.exp_avg[off:off + n].view_as(p).clone(),
                     "exp_avg_sq": opt.exp_avg_sq[off:off + n].view_as(p).clone()}
@@ -127,7 +132,7 @@ class Runner:
     # ---- checkpoints in the reference's format (train_MulSca_BriStruNet_CB.py:317-335) ------------
     def save_checkpoint(self, path, val_acc, val_loss, with_scheduler=True):
         ck = {"epoch": self.epoch, "model_state_dict": self.net.state_dict(),
-              "optimizer_state_dict": adam_state_to_torch(self.trainer.opt, self.trainer.bucket.params),
+              "optimizer_state_dict": adam_state_to_torch(self.trainer.opt, self.trainer.bucket.params, self.trainer.frozen),
               "val_acc": val_acc, "val_loss": val_loss}
         if with_scheduler:
             ck["scheduler_state_dict"] = self.scheduler.state_dict()

@@ -474,3 +474,33 @@ def test_msg_b16_benchmarked_configuration_pinned_to_reference(seed):
     med = lambda d: float(np.median(list(d.values())))
     assert med(dist[True]) <= 1.5 * med(dist[False]) + 0.02, (med(dist[True]), med(dist[False]))
     assert dist[True]["conv2.weight"] < 0.05 and dist[True]["conv2.bias"] < 0.05      # no BN stack below: plain bf16 noise
+
+
+def test_flat_adam_leaves_gradient_less_parameters_alone():
+    """EnhancedPointNet2 owns modules its forward never reaches (geometric1, cls_head): torch.optim.Adam skips their
+    grad = None parameters; the flat Adam kernel must not decay them towards zero either, and the converted optimizer
+    state has no entries for them."""
+    from pointcloud_bridge_b200 import runner
+    from pointcloud_bridge_b200.engine import Trainer
+    xyz, rgb, lab = synthetic.bridge_batch(9, 2, 1024)
+    txyz, trgb, tlab = (torch.from_numpy(a).to(DEV) for a in (xyz, rgb, lab))
+    torch.manual_seed(0)
+    net = hb_model.EnhancedPointNet2(5).to(DEV).train()
+    crit = hb_model.BridgeStructureLoss(num_classes=5, alpha=80, rel_margin=0.3).to(DEV)
+    tr = Trainer(net, loss_fn=lambda out, labels, pts: crit(out, labels, pts), lr=1e-2, weight_decay=1e-2, amp=True, graph=False)
+    before = {n: p.detach().clone() for n, p in net.named_parameters()}
+    for _ in range(2):
+        tr.step(txyz, trgb, labels=tlab, loss_inputs=(txyz,))
+    torch.cuda.synchronize()
+    names = [n for n, _ in net.named_parameters()]
+    frozen = {names[i] for i in tr.frozen}
+    assert frozen and all(n.startswith(("geometric1.", "cls_head.")) for n in frozen), sorted(frozen)[:5]
+    moved = 0
+    for n, p in net.named_parameters():
+        if n in frozen:
+            assert torch.equal(p.detach(), before[n]), n
+        else:
+            moved += int(not torch.equal(p.detach(), before[n]))
+    assert moved >= len(names) - len(frozen) - 2
+    sd = runner.adam_state_to_torch(tr.opt, tr.bucket.params, tr.frozen)
+    assert set(sd["state"]) == set(range(len(names))) - set(tr.frozen)
