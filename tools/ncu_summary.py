@@ -11,8 +11,14 @@ COLS = [("gpu__time_duration.sum", "time"), ("launch__grid_size", "grid"), ("lau
         ("dram__throughput.avg.pct_of_peak_sustained_elapsed", "DRAM %"),
         ("lts__t_sector_hit_rate.pct", "L2 hit %"),
         ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "SM %"),
-        ("sm__inst_executed_pipe_tensor.avg.pct_of_peak_sustained_active", "tensor pipe %"),
-        ("smsp__issue_active.avg.pct", "issue %"), ("sm__warps_active.avg.pct_of_peak_sustained_active", "occupancy %")]
+        ("sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed", "tensor pipe active %"),
+        ("sm__inst_executed_pipe_tc.avg.pct_of_peak_sustained_active", "tcgen05 issue %"),
+        ("sm__inst_executed_pipe_tmem.avg.pct_of_peak_sustained_active", "TMEM ld/st issue %"),
+        ("sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", "TMA unit active %"),
+        ("sm__issue_active.avg.pct_of_peak_sustained_elapsed", "issue %"),
+        ("smsp__inst_executed.sum", "warp inst"),
+        ("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smem bank conflicts"),
+        ("sm__warps_active.avg.pct_of_peak_sustained_active", "occupancy %")]
 
 
 def main():
