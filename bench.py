@@ -270,6 +270,14 @@ def run_ours(a):
     for i in range(max(a.warmup, 3) + (4 if trainer.graph else 0)):      # graph mode: 3 eager + capture first
         step_resident(i)
 
+    # A generation-2 pass of Python's garbage collector over the warm-up's objects (modules, graph captures, thousands of
+    # tensors) pauses the host for tens of milliseconds; when it falls between a step's start event and its graph launch
+    # the GPU idles inside the bracket.  Freeze what exists now (a training runner does the same after its first epoch).
+    import gc
+    gc.collect()
+    if os.environ.get("PCB_BENCH_GC_FREEZE", "1") != "0":
+        gc.freeze()
+
     # ---- value: K steps, inputs resident, device-timed, max over ranks; the K-step region is repeated a.repeats times
     # (each bracketed by barrier + synchronize on both sides) and the MEDIAN region is reported: one stalled replay in a
     # 20-step window otherwise moves the number by several per cent ----
@@ -286,6 +294,10 @@ def run_ours(a):
             per_step = [e0.elapsed_time(e1) for e0, e1 in evs]
             regions.append((pdist.max_over_ranks(sum(per_step), dev), per_step))     # K steps, flushes excluded
             gpu_launches = _lib.launches() - launches0
+    if os.environ.get("PCB_BENCH_DUMP_STEPS") == "1":       # diagnostics: every step of every region, per rank
+        for ri, (tot, steps_ms) in enumerate(regions):
+            print(f"[rank {rank}] region {ri}: {tot / a.steps:.3f} ms/step  " + " ".join(f"{t:.2f}" for t in steps_ms),
+                  file=sys.stderr, flush=True)
     regions.sort(key=lambda r: r[0])
     ms, per_step = regions[len(regions) // 2]
     per_step_sorted = sorted(per_step)
