@@ -89,6 +89,11 @@ def _seg_head(net, feats_bcn):
         # training runner: bias-free classifier rows (zero-padded to 8 columns when a bf16 shadow exists) go
         # straight into the loss kernel, which adds the bias (ops.nll_logit_rows)
         return ops.LogitRows(ops.linear_rows(x, w, pad_n=True), b, nc, B, N)
+    if x.is_cuda and x.dtype == torch.bfloat16 and ops.own_gemm_supported(x):
+        # bf16 rows: the classifier on the tcgen05 row GEMM as well (class columns zero-padded to 8), bias added on the rows
+        x = ops.linear_rows(x, w, pad_n=True)[:, :nc]
+        x = x if b is None else x + b.to(x.dtype)
+        return F.log_softmax(x.float(), dim=-1).view(B, N, -1)
     pad = (-nc) % 8 if x.is_cuda else 0
     if pad:                        # [M,5] bf16 rows are not 16-byte aligned: cuBLAS falls back to legacy kernels
         x = F.linear(x, F.pad(w, (0, 0, 0, pad)), F.pad(b, (0, pad)) if b is not None else None)[:, :nc]
