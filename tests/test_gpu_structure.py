@@ -70,3 +70,44 @@ def test_encoder_fused_rows_equal_composed_rows(train, monkeypatch):
     rel = float((outs[0] - outs[1]).norm() / outs[1].norm())
     print("encoder output, fused vs composed rows: rel L2 %.2e" % rel)
     assert rel < 2e-3
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_structure_kernel_against_the_reference_golden(tag):
+    """csrc/structure.cu against outputs of the UNMODIFIED reference class on CPU (tests/golden/structure.npz) and the
+    numpy oracle: neighbour sets, offsets, the 13 statistics, the position encoding, and the encoder's output with the
+    reference's seeded weights."""
+    import parity
+    from oracle import structure_oracle as so
+    g = parity.load("structure.npz")
+    xyz_np, idx_np, rel_np, feat_np, abs_np, out_np = (g[f"{tag}_{n}"] for n in ("xyz", "idx", "rel", "feat", "abs", "out"))
+    k = int(g[f"{tag}_k"])
+    xyz = torch.from_numpy(xyz_np).to(DEV)
+    B, N, _ = xyz.shape
+    # the kNN kernel finds the reference's neighbour SETS (order inside exact distance ties is unspecified in topk)
+    idx = ops.knn_cdist(xyz, k)
+    same = (np.sort(idx.cpu().numpy(), -1) == np.sort(idx_np, -1)).all(-1).mean()
+    assert same > 0.999, same
+    # on the reference's own indices: rows and statistics
+    ridx = torch.from_numpy(idx_np).to(DEV)
+    freqs = [1.0, 2.0, 4.0, 8.0]
+    rows, feat = ops.structure_rows(xyz, ridx, freqs, 1.0, bf16=False, feat=True)
+    r = rows.view(B, N, k, -1).cpu().numpy()
+    f = feat.cpu().numpy()
+    assert np.array_equal(r[..., 24:27], rel_np)
+    assert np.allclose(r[..., :24], np.broadcast_to(abs_np[:, :, None, :], r[..., :24].shape), rtol=0, atol=2e-6)
+    scale = float(np.abs(rel_np).max())
+    assert np.allclose(f[..., 3:], feat_np[..., 3:], rtol=2e-4, atol=2e-5 * scale)
+    ok = so.well_conditioned(rel_np)
+    err = np.abs(f[..., :3] - feat_np[..., :3]) / (np.abs(feat_np[..., :3]) + 1)
+    print("shape features vs the reference (well-conditioned neighbourhoods): max rel %.2e" % err[ok].max())
+    assert err[ok].max() < 2e-3
+    orows = so.rows(xyz_np, idx_np, np.asarray(freqs)).reshape(B, N, k, 40)              # the numpy oracle's rows
+    assert np.allclose(np.delete(r, [27, 28, 29], -1), np.delete(orows, [27, 28, 29], -1), rtol=2e-4, atol=2e-5 * scale)
+    # the whole encoder with the reference's weights, evaluation mode, fp32
+    enc = parity.seeded_fill_(am.BridgeStructureEncoding(channels=32, k_neighbors=k), 3).to(DEV).eval()
+    with torch.no_grad():
+        y = enc(xyz).float().cpu().numpy()
+    e = np.abs(y - out_np) / (np.abs(out_np).max() + 1e-12)
+    print("encoder output vs the reference: p50 %.2e p99 %.2e max %.2e" % (np.median(e), np.quantile(e, 0.99), e.max()))
+    assert np.median(e) < 1e-5 and np.quantile(e, 0.99) < 1e-3
