@@ -102,7 +102,13 @@ ball_query_kernel(const float *__restrict__ xyz, const float *__restrict__ new_x
 // memory as float4 (x, y, z, |p|^2): one LDS.128 per pair instead of four LDS.32.
 // ------------------------------------------------------------------------------------------
 constexpr int kBqMaxScales = 4;
-constexpr int kBqMultiChunk = 4096;          // points per pass: 12 B staging + 16 B float4 each = 112 KB
+#ifndef PCB_BQ_CHUNK
+#define PCB_BQ_CHUNK 4096
+#endif
+#ifndef PCB_BQ_MINB
+#define PCB_BQ_MINB 2                        // 62 registers: two CTAs (32 warps) per SM -- 140 -> 110 us at B = 16, 4096 -> 1024,
+#endif                                       // two radii; chunks of 2048 / 1024 points measured 114 / 122 us (round 2)
+constexpr int kBqMultiChunk = PCB_BQ_CHUNK;  // points per pass: 12 B staging + 16 B float4 each (4096: 112 KB)
 
 struct BqScales {
     float r2[kBqMaxScales];
@@ -114,7 +120,7 @@ struct BqScales {
 // (Serving 4 queries per warp from one candidate fetch was tried and was slower -- 0.31 ms against 0.175 ms
 // for the four launches of the MSG step: fewer, longer dependent chains per SM.  One query per warp with
 // 128 candidates per step is kept.)
-__global__ void __launch_bounds__(kBqWarps * 32, 1)
+__global__ void __launch_bounds__(kBqWarps * 32, PCB_BQ_MINB)
 ball_query_multi_kernel(const float *__restrict__ xyz, const float *__restrict__ new_xyz, int N, int S,
                         const BqScales p, int chunk, int use_bulk)
 {

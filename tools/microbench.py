@@ -89,6 +89,8 @@ def main():
         n, s = src.shape[1], q.shape[1]
         rec(tag, lambda src=src, q=q, r=r, ns=ns: ops.ball_query(r, ns, src, q), B * (12 * n + 12 * s + 8 * s * ns),
             B * s * n, "Gpairs_per_s")
+    rec("ballmulti_4096_1024_r.05-.1_n16-32", lambda: ops.ball_query_multi([0.05, 0.1], [16, 32], xyz, l1),
+        B * (12 * N + 12 * 1024 + 8 * 1024 * 48), B * 1024 * N, "Gpairs_per_s")
     ball = ops.ball_query(0.1, 32, xyz, l1)
     # --- gathers
     feat9 = torch.from_numpy(synthetic.sem_seg_input(xyz_np, rgb_np)).to(dev)              # [B,9,N]
