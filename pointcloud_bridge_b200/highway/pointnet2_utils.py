@@ -204,7 +204,7 @@ class MultiScaleSetAbstraction(nn.Module):
         B = xyz.shape[0]
         S = self.npoint
         new_xyz = index_points(xyz, farthest_point_sample(xyz, S))
-        outs = []
+        outs, forked = [], []
         # every radius in one scan of the cloud (the reference calls query_ball_point once per radius)
         idxs = ops.ball_query_multi(self.radius_list, self.nsample_list, xyz, new_xyz)
         for i, (radius, K) in enumerate(zip(self.radius_list, self.nsample_list)):
@@ -215,8 +215,25 @@ class MultiScaleSetAbstraction(nn.Module):
                 if pk.ok:
                     outs.append(ops.sa_fused(xyz, pts, new_xyz, idx, pk, xyz_first=True))
                     continue
-            grouped = ops.group_points(xyz, pts, new_xyz, idx, xyz_first=True, clamp=True, pad_to=8)
-            outs.append(mlp_rows(grouped.view(B * S * K, -1), self.conv_blocks[i], self.bn_blocks[i], pool_k=K))
+            # inside a step runner the scales run on their own streams (fork / join of the captured graph), grouping included
+            side = ops.scale_stream(xyz.device, i) if (i > 0 and self.training and xyz.is_cuda) else None
+            if side is None:
+                grouped = ops.group_points(xyz, pts, new_xyz, idx, xyz_first=True, clamp=True, pad_to=8)
+                outs.append(mlp_rows(grouped.view(B * S * K, -1), self.conv_blocks[i], self.bn_blocks[i], pool_k=K))
+                continue
+            main = torch.cuda.current_stream()
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                grouped = ops.group_points(xyz, pts, new_xyz, idx, xyz_first=True, clamp=True, pad_to=8)
+                o = mlp_rows(grouped.view(B * S * K, -1), self.conv_blocks[i], self.bn_blocks[i], pool_k=K)
+            for t in (xyz, pts, new_xyz, idx):
+                if t is not None:
+                    t.record_stream(side)
+            o.record_stream(main)
+            forked.append(side)
+            outs.append(o)
+        for side in forked:
+            torch.cuda.current_stream().wait_stream(side)
         return new_xyz, _cf_view(torch.cat(outs, dim=1), B, S)
 
 

@@ -1086,6 +1086,24 @@ def _wgrad_stream(dev: torch.device) -> torch.cuda.Stream:
     return st
 
 
+# The scales of a multi-scale set-abstraction level are independent chains of small kernels: inside a step runner each
+# scale after the first runs on its own stream (PCB_NO_SCALE_STREAMS=1 switches it off).
+_SCALE_STREAMS = os.environ.get("PCB_NO_SCALE_STREAMS", "0") != "1"
+_scale_streams: dict[tuple, torch.cuda.Stream] = {}
+
+
+def scale_stream(dev: torch.device, i: int):
+    """Stream of scale `i` of a multi-scale module, or None outside a step runner / when switched off."""
+    if not _SCALE_STREAMS or _step_ctx is None or _timer is not None:
+        return None
+    key = (dev.index if dev.index is not None else torch.cuda.current_device(), i)
+    st = _scale_streams.get(key)
+    if st is None:
+        st = torch.cuda.Stream(device=dev)
+        _scale_streams[key] = st
+    return st
+
+
 @torch.no_grad()
 def wgrad_rows(gy, x, k: int | None = None, out: torch.Tensor | None = None, n: int | None = None) -> torch.Tensor:
     """gy [M,Np][:, :n]^T @ x [M,Kp][:, :k] in fp32 (bf16 operands, rows = the long contraction dimension;

@@ -242,7 +242,7 @@ class PointNetSetAbstractionMsg(nn.Module):
         pts_r = _rows(points) if points is not None else None
         B = xyz_r.shape[0]
         S = self.npoint
-        outs, joined = [], None
+        outs, joined, forked = [], None, []
         if pre is not None:
             new_xyz, idxs = pre
         else:
@@ -270,7 +270,22 @@ class PointNetSetAbstractionMsg(nn.Module):
                 joined = torch.empty(B * S, sum(widths), dtype=grouped.dtype, device=grouped.device)
             off = sum(o.shape[1] for o in outs)
             slot = joined[:, off:off + self.conv_blocks[i][-1].weight.shape[0]] if joined is not None else None
-            outs.append(mlp_rows(grouped.view(B * S * K, -1), self.conv_blocks[i], self.bn_blocks[i], pool_k=K, out=slot))
+            # inside a step runner the scales of a level run on their own streams (a fork / join of the captured graph):
+            # they share nothing but their inputs, and the kernels of the small levels leave most SMs idle
+            side = ops.scale_stream(grouped.device, i) if (i > 0 and self.training and grouped.is_cuda) else None
+            if side is None:
+                outs.append(mlp_rows(grouped.view(B * S * K, -1), self.conv_blocks[i], self.bn_blocks[i], pool_k=K, out=slot))
+            else:
+                main = torch.cuda.current_stream()
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    o = mlp_rows(grouped.view(B * S * K, -1), self.conv_blocks[i], self.bn_blocks[i], pool_k=K, out=slot)
+                grouped.record_stream(side)
+                o.record_stream(main)
+                forked.append(side)
+                outs.append(o)
+        for side in forked:
+            torch.cuda.current_stream().wait_stream(side)
         if joined is not None and all(o.data_ptr() == joined.data_ptr() + joined.element_size() * sum(p.shape[1] for p in outs[:j])
                                       and o.stride(0) == joined.stride(0) for j, o in enumerate(outs)):
             y = ops.join_columns(joined, outs)
