@@ -53,6 +53,9 @@ __device__ unsigned long long g_bn_trace[8 * 1024];
 #define BN_STAMP(i)
 #endif
 constexpr int kBnThreads = 256;
+#ifndef PCB_BN_APPLY_MINB
+#define PCB_BN_APPLY_MINB 1   // min CTAs per SM of the ordinary-launch elementwise kernels (tuning switch)
+#endif
 constexpr int kBnMaxParts = PCB_NUM_SMS * 2;      // at most 2 CTAs per SM (register budget) -> <= 296 partials
 
 // VecIO<T, V>: V consecutive channels per thread, one 16-byte access for (float,4) and (bf16,8),
@@ -818,7 +821,7 @@ __device__ __forceinline__ void fwd_apply_consts(const BnFwdArgs &a, float *s_co
 }
 
 template <typename T, int V>
-__global__ void __launch_bounds__(kBnThreads)
+__global__ void __launch_bounds__(kBnThreads, PCB_BN_APPLY_MINB)
 bn_apply_rows_kernel(const BnFwdArgs a)
 {
     pdl_wait();
@@ -856,7 +859,7 @@ bn_apply_rows_kernel(const BnFwdArgs a)
 // as one thread walking the whole group, a.rs times the threads (the last layers of the set-abstraction MLPs have only
 // 256 .. 4096 groups: one thread per (group, 8 channels) left 16 .. 64 CTAs on 148 SMs).  C / V <= kBnThreads.
 template <typename T, int V>
-__global__ void __launch_bounds__(kBnThreads)
+__global__ void __launch_bounds__(kBnThreads, PCB_BN_APPLY_MINB)
 bn_apply_pooled_kernel(const BnFwdArgs a)
 {
     pdl_wait();
@@ -993,7 +996,7 @@ struct BnBwdApplyArgs {
 constexpr int kBnApplyMaxC = 1024;
 
 template <typename T, int V>
-__global__ void __launch_bounds__(kBnThreads)
+__global__ void __launch_bounds__(kBnThreads, PCB_BN_APPLY_MINB)
 bn_bwd_apply_rows_kernel(const BnBwdApplyArgs a)
 {
     pdl_wait();
@@ -1117,7 +1120,7 @@ struct BnPoolBwdArgs {
 };
 
 template <typename T, int V>
-__global__ void __launch_bounds__(kBnThreads)
+__global__ void __launch_bounds__(kBnThreads, PCB_BN_APPLY_MINB)
 bn_pool_bwd_apply_kernel(const BnPoolBwdArgs p)
 {
     pdl_wait();
