@@ -57,10 +57,11 @@ def workload_config(a, world):
             "e2e": "public API (engine.Trainer): batch i+1 copied H2D from pinned memory on a side stream while step i runs "
                    "(Trainer.prefetch), loss of step i copied D2H after the step and read by the host one step later; "
                    "wall clock over K steps incl. the L2 flush writes",
-            "launch": "eager" if a.no_graph else "one CUDA graph per step (zero+fwd+loss+bwd+Adam); the sampling / grouping "
-                      "indices of batch i+1 (FPS with start indices drawn on the CPU generator as the reference does, ball "
-                      "query, three-NN) are computed on a side stream while batch i trains and copied into the graph's "
-                      "static buffers before its replay",
+            "launch": "eager" if a.no_graph else "one CUDA graph per step (zero+fwd+loss+bwd+Adam; programmatic dependent launch "
+                      "between the kernels of libpcbridge, weight gradients and the scales of a multi-scale level on forked "
+                      "branches); the sampling / grouping indices of batch i+1 (FPS with start indices drawn on the CPU "
+                      "generator as the reference does, ball query, three-NN) are computed on a side stream from the "
+                      "mid-point of step i and copied into the graph's static buffers before its replay",
             "timed_region": "K steps bracketed by barrier+synchronize, per-step CUDA events summed; repeated --repeats "
                             "times, median region reported"}
 
@@ -408,8 +409,12 @@ def run_ours(a):
                 "avg_launch_ms": top["avg_launch_ms"], "launches_per_step": top["launches_per_step"],
                 "alg_bytes_per_launch": top["alg_bytes_per_launch"], "share_of_step": top["share_of_step"],
                 "note": "kernel family of ours with the largest share of the step (all layer shapes together); per-launch "
-                        "durations from CUDA events around every launch of an eager, spin-ahead instrumented pass, minus "
-                        "the measured duration of an empty event bracket",
+                        "durations from CUDA events around every launch of an eager, single-stream, spin-ahead "
+                        "instrumented pass, minus the measured duration of an empty event bracket.  Shares are kernel time "
+                        "over step time and add up to more than 1: inside the captured step the index chain, the weight "
+                        "gradients and the second scale of every multi-scale level run concurrently with the main chain, "
+                        "and programmatic dependent launch overlaps every kernel's prologue with its predecessor "
+                        "(profiles/r2_final_step_launches.md has the ncu launch list of the graph replay itself)",
                 "event_bracket_overhead_ms": round(evt_overhead_ms, 5),
                 "all_our_kernels_share_of_step": round(ours_share, 4), "kernels": kernels[:10]}
 

@@ -1406,13 +1406,13 @@ PCB_API int pcb_bn_apply_rows(const void *y, int dtype, int64_t M, int C, int Cv
     a.pool_k = pool_k, a.relu = relu, a.out_pitch = out_pitch > 0 ? out_pitch : C;
     a.var = var, a.bias = bias, a.momentum = momentum, a.running_mean = running_mean, a.running_var = running_var;
     a.gparts = gparts, a.var_out = var, a.groups = groups, a.eps = eps, a.rs = 1, a.ymax = ymax;
-    PCB_REQUIRE(!ymax || (pool_k > 1 && C / (dtype && C % 8 == 0 ? 8 : 4) <= kBnThreads), PCB_ERANGE);
     PCB_REQUIRE(a.out_pitch >= C && a.out_pitch % 4 == 0, PCB_ERANGE);
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t units = M / pool_k;
     const bool v8 = dtype && C % 8 == 0 && a.out_pitch % 8 == 0 && al16(y) && al16(out);
     const int V = v8 ? 8 : 4;
     PCB_REQUIRE(!gparts || C <= kBnThreads * V, PCB_ERANGE);    // deferred statistics go through the shared constants
+    PCB_REQUIRE(!ymax || (pool_k > 1 && C / V <= kBnThreads), PCB_ERANGE);   // only the row-lane kernel writes ymax
     if (pool_k > 1 && C / V <= kBnThreads) {
         if (!dtype) bn_apply_pooled_launch<float, 4>(a, units, st);
         else if (v8) bn_apply_pooled_launch<__nv_bfloat16, 8>(a, units, st);

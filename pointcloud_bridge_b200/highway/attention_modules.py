@@ -72,10 +72,9 @@ class BridgeStructureEncoding(nn.Module):
         flat = rel_pos.reshape(B * N, k, 3)
         cov = torch.bmm(flat.transpose(1, 2), flat) / (k - 1)
         try:
-            # training mode: sync-free closed-form kernel (the step stays CUDA-graph capturable); eval keeps
-            # torch.linalg.eigvalsh, the path pinned against the reference's logits
-            ev = (ops.eigvalsh3(cov) if (self.training and cov.is_cuda and not cov.requires_grad)
-                  else torch.linalg.eigvalsh(cov)).view(B, N, 3)
+            # the sync-free float64 closed form (csrc/eig3.cu) in training AND evaluation, like the fused rows kernel:
+            # one solver for both modes (a gradient through the covariance -- never needed on this path -- keeps eigvalsh)
+            ev = (ops.eigvalsh3(cov) if (cov.is_cuda and not cov.requires_grad) else torch.linalg.eigvalsh(cov)).view(B, N, 3)
             den = ev[..., 0] + 1e-8
             shape_feats = torch.stack([(ev[..., 0] - ev[..., 1]) / den, (ev[..., 1] - ev[..., 2]) / den,
                                        ev[..., 2] / den], dim=-1)

@@ -23,7 +23,7 @@ def test_structure_rows_match_the_pytorch_composition(B, N, k, F):
     idx = ops.knn_cdist(xyz, k)
     rows, feat = ops.structure_rows(xyz, idx, enc.freqs, enc.grid_size, bf16=False, feat=True)
     rel = ops.group_points(xyz, None, xyz, idx, xyz_first=True)              # [B,N,k,3], exact subtraction
-    ref_feat = enc.get_structure_features(rel)                               # PyTorch ops (cuSOLVER eigvalsh in eval)
+    ref_feat = enc.get_structure_features(rel)                               # PyTorch ops on an fp32 bmm covariance
     ref_abs = enc.compute_absolute_position_encoding(xyz)
     a = 6 * F
     r = rows.view(B, N, k, -1)
