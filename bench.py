@@ -45,6 +45,10 @@ def parse():
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of one CUDA graph per step")
     ap.add_argument("--cpu-sample-blocks", type=int, default=4)
     ap.add_argument("--repeats", type=int, default=5, help="timed K-step regions; the median one is reported")
+    ap.add_argument("--config", default="c2", choices=["c1", "c2", "c3", "c4", "c5", "c5scene"],
+                    help="BASELINE.json configuration; c2 (default) is the headline this file measures itself, the others "
+                         "delegate to tools/bench_configs.py (c1 SSG forward, c3 DGCNN forward, c4 BriStruNet train step, c5 "
+                         "block-sharded inference) and tools/bench_scene_e2e.py (c5scene: one scene end to end)")
     return ap.parse_args()
 
 
@@ -442,8 +446,19 @@ def run_ours(a):
         dist.destroy_process_group()
 
 
+def run_other_config(a):
+    """The secondary BASELINE configurations through their own tools (same launch line, one JSON line per measurement on
+    stdout; torchrun environment passed through)."""
+    import runpy
+    tool = "bench_scene_e2e.py" if a.config == "c5scene" else "bench_configs.py"
+    sys.argv = [os.path.join(ROOT, "tools", tool)] + ([] if a.config == "c5scene" else ["--only", a.config])
+    runpy.run_path(sys.argv[0], run_name="__main__")
+
+
 def main():
     a = parse()
+    if a.config != "c2" and a.impl == "ours":
+        return run_other_config(a)
     if a.impl == "reference":
         run_reference(a)
     else:
