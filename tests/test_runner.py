@@ -40,6 +40,26 @@ def test_adam_state_round_trips_through_torch_format():
     assert torch.equal(b.exp_avg_sq[12:16], ref.state[params[1]]["exp_avg_sq"])
 
 
+def test_adam_state_omits_parameters_that_never_had_a_gradient():
+    """torch.optim.Adam keeps no state for grad = None parameters; the converted state must look the same, and a
+    reference optimizer that only stepped the other parameters must load it and produce it."""
+    params = [torch.nn.Parameter(torch.randn(3, 2)), torch.nn.Parameter(torch.randn(5)), torch.nn.Parameter(torch.randn(2, 2))]
+    a = _FakeFlatAdam(sum(p.numel() for p in params))
+    sd = runner.adam_state_to_torch(a, params, frozen=[1])
+    assert set(sd["state"]) == {0, 2} and sd["param_groups"][0]["params"] == [0, 1, 2]
+    assert torch.equal(sd["state"][2]["exp_avg"], a.exp_avg[11:].view(2, 2))
+    ref = torch.optim.Adam(params, lr=1e-3)
+    ref.load_state_dict(sd)
+    assert params[1] not in ref.state
+    params[0].grad, params[2].grad = torch.randn(3, 2), torch.randn(2, 2)          # params[1] stays without gradient
+    ref.step()
+    assert set(ref.state_dict()["state"]) == {0, 2}
+    b = _FakeFlatAdam(a.exp_avg.numel())
+    keep = b.exp_avg[6:11].clone()
+    runner.adam_state_from_torch(b, ref.state_dict(), params)
+    assert torch.equal(b.exp_avg[6:11], keep) and int(b.step_t) == 8
+
+
 @pytest.mark.gpu
 def test_fit_save_resume_bristrunet(tmp_path):
     """Two epochs of the BriStruNet runner on a tiny synthetic loader, checkpoints in the reference's dictionary
